@@ -1,0 +1,134 @@
+"""ctypes binding of the C ABI declared in include/pvder_b200.h (libpvder_b200.so).
+
+This is the only bridge between the Python host code and the CUDA kernels; signatures carry
+plain pointers/sizes only.  There is deliberately no fallback: if the shared library is missing
+the loader raises with the build command.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libpvder_b200.so")
+SOURCES = ["pvder_kernels.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-diag-suppress", "177", "-shared", "-Xcompiler", "-fPIC"]
+
+MAX_STATES = 23
+OBS_DIM = 11
+N_ACTIONS = 5
+SI_K, SI_STEPS, SI_EPISODE, SI_STATUS, SI_DONE, SI_HIST, SI_WINDUP, SI_FIELDS = 0, 1, 2, 3, 4, 5, 10, 11
+GOALS = {"voltage_regulation": 0, "Q_regulation": 1, "power_regulation": 2}
+EVENT_MODES = {"none": 0, "philox": 1, "table": 2}
+STATUS_OK, STATUS_BAD_ACTION, STATUS_NONFINITE = 0, 1, 2
+
+
+def sd_fields(ns):
+    return ns + 6
+
+
+def sd_index(ns):
+    return dict(Q_ref=ns, Vdc_ref=ns + 1, Vgrid=ns + 2, Sinsol=ns + 3, ep_return=ns + 4, last_reward=ns + 5)
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "Rf", "Rt", "Xt", "inv_Lf", "inv_wb", "Kp_GCC", "Ki_GCC", "Kp_DC", "Ki_DC", "Kp_Q", "Ki_Q", "wp",
+        "Kp_PLL", "Ki_PLL", "inv_C", "w0", "dw", "vgs", "np_iph100", "np_irs", "kappa", "pv_scale",
+        "Vrms_ref", "iref_limit", "m_limit10", "p_target", "q_target", "Lf", "Rf_Rt")]
+
+
+class EnvConfigC(C.Structure):
+    _fields_ = [
+        ("par", Params),
+        ("phases", C.c_int32), ("n_sub_per_step", C.c_int32), ("micro", C.c_int32), ("done_substep", C.c_int32),
+        ("discrete_reward", C.c_int32), ("goal", C.c_int32), ("auto_reset", C.c_int32), ("event_mode", C.c_int32),
+        ("ev_start_k", C.c_int32), ("ev_step_k", C.c_int32), ("ev_count", C.c_int32),
+        ("ev_voltage_enable", C.c_int32), ("ev_insol_enable", C.c_int32),
+        ("ev_v_min", C.c_double), ("ev_v_max", C.c_double), ("ev_s_min", C.c_double), ("ev_s_max", C.c_double),
+        ("delQ_pu", C.c_double), ("delVdc_pu", C.c_double), ("max_sim_time", C.c_double),
+        ("substeps_per_sec", C.c_double), ("seed", C.c_uint64), ("Q_ref0", C.c_double), ("Vdc_ref0", C.c_double),
+        ("y0", C.c_double * MAX_STATES),
+    ]
+
+
+_vp, _i64, _i32, _u64, _dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_double
+_cfgp = C.POINTER(EnvConfigC)
+
+# name -> (restype, argtypes); every symbol include/pvder_b200.h declares
+SIGNATURES = {
+    "pvder_abi_version": (C.c_int, []),
+    "pvder_error_string": (C.c_char_p, [C.c_int]),
+    "pvder_sd_fields": (C.c_size_t, [C.c_int]),
+    "pvder_si_fields": (C.c_size_t, []),
+    "pvder_steady_state": (C.c_int, [C.POINTER(Params), C.c_int, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
+    "pvder_reset": (C.c_int, [_cfgp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _i64, _i64, _vp]),
+    "pvder_step": (C.c_int, [_cfgp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "pvder_generate_events": (C.c_int, [_cfgp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "pvder_sample_actions": (C.c_int, [_u64, _i64, _vp, _i64, _i64, _vp]),
+    "pvder_stats_reduce": (C.c_int, [_vp, _vp, _i64, C.c_int, _i64, _vp, _vp]),
+    "pvder_fp64_peak": (C.c_int, [C.c_int, C.POINTER(_dbl), C.POINTER(_dbl)]),
+    "pvder_env_create": (C.c_int, [_cfgp, _i64, _i64, C.POINTER(_vp)]),
+    "pvder_env_destroy": (C.c_int, [_vp]),
+    "pvder_env_set_event_tables": (C.c_int, [_vp, _vp, _vp]),
+    "pvder_env_reset_host": (C.c_int, [_vp, _vp, _vp]),
+    "pvder_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "pvder_env_state_host": (C.c_int, [_vp, _vp, _vp]),
+    "pvder_env_set_refs_host": (C.c_int, [_vp, _vp]),
+    "pvder_env_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    "pvder_env_kernel_ms": (C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "pvder_host_alloc": (_vp, [C.c_size_t]),
+    "pvder_host_free": (None, [_vp]),
+}
+
+_lib = None
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into csrc/libpvder_b200.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    deps.append(os.path.join(os.path.dirname(_HERE), "include", "pvder_b200.h"))
+    if not force and os.path.exists(LIB_PATH):
+        if os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(d) for d in deps):
+            return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """Load libpvder_b200.so; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"CUDA extension {LIB_PATH} is missing. Build it with `python -c \"import __graft_entry__ as g; "
+            "g.build()\"` (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pvder_abi_version() != 1:
+        raise RuntimeError("libpvder_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+class PVDERError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().pvder_error_string(rc)
+        raise PVDERError(f"libpvder_b200 call failed ({rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,78 @@
+// Shared device-side definitions for the PVDER-v0 step kernels (sm_100a).
+//
+// Replaces, per environment thread, what the reference obtains from the un-vendored `pvder`
+// simulator objects built at reference gym_PVDER/envs/PVDER_env.py:371-391 (DER model, grid
+// model, simulation events) -- equations in SURVEY.md Appendix A.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/pvder_b200.h"
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define PVDER_DEV __device__ __forceinline__
+#define PVDER_HD __host__ __device__ __forceinline__
+#else
+// Plain C++ build of the per-env logic (tests/host_emul only): round-to-nearest intrinsics map
+// to the plain IEEE operations (build with -ffp-contract=off).
+#define PVDER_DEV inline
+#define PVDER_HD inline
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+using std::isfinite;
+#endif
+
+namespace pvder {
+
+using Params = ::pvder_params;
+
+// Exogenous inputs held constant over one half-cycle sub-step (events frozen per sub-step, A.8).
+struct Inputs {
+  double vg;       // LV-side grid phasor magnitude  = Vgrid_event * par.vgs
+  double Qref;     // external reactive power reference (pu), changed only by actions
+  double Vdcref;   // external DC-link reference (pu), changed only by actions
+  double np_iph;   // Np * Iph(Sinsol)  (A)
+};
+
+// PV array power (pu) and its slope wrt Vdc.
+PVDER_DEV void ppv_eval(const Params& par, const Inputs& in, double Vdc, double& P,
+                                         double& dP) {
+  const double e = exp(par.kappa * Vdc);
+  const double Ipv = in.np_iph - par.np_irs * (e - 1.0);
+  const double Pr = Ipv * Vdc * par.pv_scale;
+  const double dPr = par.pv_scale * (Ipv - Vdc * (par.np_irs * par.kappa * e));
+  const bool pos = Pr > 0.0;
+  P = pos ? Pr : 0.0;
+  dP = pos ? dPr : 0.0;
+}
+
+// ---- Philox4x32-10 (counter-based RNG; bit-exact numpy twin in oracle/philox_twin.py) ----------
+PVDER_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                       uint32_t k0, uint32_t k1, uint32_t (&out)[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0;
+    const uint64_t p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit uniform in [0,1) from two 32-bit words (same construction as numpy's random double).
+PVDER_HD double u53(uint32_t hi, uint32_t lo) {
+  const uint64_t a = hi >> 5, b = lo >> 6;
+  return (double)(a * 67108864ull + b) * (1.0 / 9007199254740992.0);
+}
+
+enum : uint32_t { STREAM_EVENTS = 0u, STREAM_ACTIONS = 1u };
+
+}  // namespace pvder

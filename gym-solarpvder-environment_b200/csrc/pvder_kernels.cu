@@ -1,0 +1,599 @@
+// B200 (sm_100a) kernels + C ABI for the PVDER-v0 hot path.
+//
+// One thread owns one environment: the 11/23 ODE states, the references and the event values
+// stay in FP64 registers for all 2n half-cycle sub-steps of an env step; HBM sees one coalesced
+// SoA read + write of the per-env state, the action read and the obs/reward/done writes.
+//
+// step kernel      <- PVDER.step            reference gym_PVDER/envs/PVDER_env.py:138-196
+//   action         <- PVDER.action_calc     :198-229
+//   integrator     <- sim.run_simulation()  :166 (pvder DynamicSimulation -> scipy odeint/LSODA,
+//                     SURVEY.md A.7) replaced by a fixed half-cycle Rodas4 (L-stable, stiffly
+//                     accurate Rosenbrock, 6 stages, order 4) on the generated model code
+//   events/RNG     <- generate_simulation_events :400-411 (pvder create_random_events, A.8)
+//   reward         <- PVDER.reward_calc     :231-301
+//   observation    <- PVDER.state           :531-542
+//   done           <- :183-191
+// reset kernel     <- PVDER.reset / setup_PVDER_simulation :316-334, :366-398
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "pvder_common.cuh"
+#include "pvder_model_1ph.cuh"
+#include "pvder_model_3ph.cuh"
+#include "pvder_env_step.cuh"
+
+namespace pvder {
+
+constexpr int BLOCK = 128;
+
+struct StepArgs {
+  double* sd;
+  int32_t* si;
+  int64_t ld;
+  const int32_t* action;
+  const double* vtab;
+  const double* stab;
+  float* obs_f32;
+  double* obs_f64;
+  double* reward_f64;
+  int32_t* reward_i32;
+  uint8_t* done;
+  int64_t n;
+  int64_t env_offset;
+};
+
+// Coalesced store of a block's obs rows ([BLOCK][11] contiguous in HBM) through shared memory.
+__device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const Outputs& o, int64_t block_first,
+                                                int64_t n, float* stage) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < PVDER_OBS_DIM; ++j) stage[t * PVDER_OBS_DIM + j] = (float)o.obs[j];
+  __syncthreads();
+  const int64_t rows = min((int64_t)BLOCK, n - block_first);
+  const int total = (int)rows * PVDER_OBS_DIM;
+  float* dst = obs + block_first * PVDER_OBS_DIM;
+  for (int idx = t; idx < total; idx += BLOCK) dst[idx] = stage[idx];
+}
+
+template <class M>
+__global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ pvder_env_config cfg, const StepArgs a) {
+  constexpr int NS = M::NS;
+  __shared__ float stage[BLOCK * PVDER_OBS_DIM];
+  const int64_t block_first = (int64_t)blockIdx.x * BLOCK;
+  const int64_t e = block_first + threadIdx.x;
+  const bool active = e < a.n;
+  const int64_t ec = active ? e : (a.n - 1);   // inactive lanes shadow the last env and never store
+
+  EnvRegs<M> r;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) r.y[i] = a.sd[(int64_t)i * a.ld + ec];
+  r.Qref = a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + ec];
+  r.Vdcref = a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + ec];
+  r.Vgrid = a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + ec];
+  r.Sinsol = a.sd[(int64_t)PVDER_SD_SINSOL(NS) * a.ld + ec];
+  r.ret = a.sd[(int64_t)PVDER_SD_RETURN(NS) * a.ld + ec];
+  r.last_reward = a.sd[(int64_t)PVDER_SD_REWARD(NS) * a.ld + ec];
+  r.k = a.si[(int64_t)PVDER_SI_K * a.ld + ec];
+  r.steps = a.si[(int64_t)PVDER_SI_STEPS * a.ld + ec];
+  r.episode = a.si[(int64_t)PVDER_SI_EPISODE * a.ld + ec];
+  r.status = a.si[(int64_t)PVDER_SI_STATUS * a.ld + ec];
+  r.done = a.si[(int64_t)PVDER_SI_DONE * a.ld + ec];
+  r.windup = a.si[(int64_t)PVDER_SI_WINDUP * a.ld + ec];
+  const int act = a.action[ec];
+
+  Outputs o;
+  int done_out, hist_inc;
+  bool hist_clear;
+  const bool run = advance_env<M>(cfg, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
+                                  done_out, hist_inc, hist_clear);
+
+  if (active) {
+    if (a.reward_f64) a.reward_f64[e] = o.reward;
+    if (a.reward_i32) a.reward_i32[e] = o.reward_i;
+    if (a.done) a.done[e] = (uint8_t)done_out;
+  }
+  if (run) {
+#pragma unroll
+    for (int i = 0; i < NS; ++i) a.sd[(int64_t)i * a.ld + e] = r.y[i];
+    a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + e] = r.Qref;
+    a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + e] = r.Vdcref;
+    a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + e] = r.Vgrid;
+    a.sd[(int64_t)PVDER_SD_SINSOL(NS) * a.ld + e] = r.Sinsol;
+    a.sd[(int64_t)PVDER_SD_RETURN(NS) * a.ld + e] = r.ret;
+    a.sd[(int64_t)PVDER_SD_REWARD(NS) * a.ld + e] = r.last_reward;
+    a.si[(int64_t)PVDER_SI_K * a.ld + e] = r.k;
+    a.si[(int64_t)PVDER_SI_STEPS * a.ld + e] = r.steps;
+    a.si[(int64_t)PVDER_SI_EPISODE * a.ld + e] = r.episode;
+    a.si[(int64_t)PVDER_SI_DONE * a.ld + e] = r.done;
+    a.si[(int64_t)PVDER_SI_WINDUP * a.ld + e] = r.windup;
+    if (hist_inc >= 0) a.si[(int64_t)(PVDER_SI_HIST + hist_inc) * a.ld + e] += 1;
+    if (hist_clear) {
+#pragma unroll
+      for (int h = 0; h < PVDER_N_ACTIONS; ++h) a.si[(int64_t)(PVDER_SI_HIST + h) * a.ld + e] = 0;
+    }
+  }
+  if (active) a.si[(int64_t)PVDER_SI_STATUS * a.ld + e] = r.status;
+  if (a.obs_f64 && active) {
+#pragma unroll
+    for (int j = 0; j < PVDER_OBS_DIM; ++j) a.obs_f64[e * PVDER_OBS_DIM + j] = o.obs[j];
+  }
+  if (a.obs_f32) store_obs_block(a.obs_f32, o, block_first, a.n, stage);
+}
+
+struct ResetArgs {
+  double* sd;
+  int32_t* si;
+  int64_t ld;
+  const uint8_t* mask;
+  const double* vtab;
+  const double* stab;
+  int32_t init;
+  float* obs_f32;
+  double* obs_f64;
+  int64_t n;
+  int64_t env_offset;
+};
+
+template <class M>
+__global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ pvder_env_config cfg, const ResetArgs a) {
+  constexpr int NS = M::NS;
+  const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (e >= a.n) return;
+  if (a.mask && !a.mask[e]) return;
+  double y[NS], Qref, Vdcref, Vgrid, Sinsol;
+  init_env<M>(cfg, y, Qref, Vdcref, Vgrid, Sinsol);
+  const int episode = a.init ? 0 : a.si[(int64_t)PVDER_SI_EPISODE * a.ld + e] + 1;
+  if (cfg.ev_start_k == 0 && cfg.ev_count > 0)
+    apply_event(cfg, a.vtab, a.stab, a.ld, e, (uint32_t)(a.env_offset + e), (uint32_t)episode, 0, Vgrid, Sinsol);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) a.sd[(int64_t)i * a.ld + e] = y[i];
+  a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + e] = Qref;
+  a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + e] = Vdcref;
+  a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + e] = Vgrid;
+  a.sd[(int64_t)PVDER_SD_SINSOL(NS) * a.ld + e] = Sinsol;
+  a.sd[(int64_t)PVDER_SD_RETURN(NS) * a.ld + e] = 0.0;
+  a.sd[(int64_t)PVDER_SD_REWARD(NS) * a.ld + e] = 0.0;
+  a.si[(int64_t)PVDER_SI_K * a.ld + e] = 0;
+  a.si[(int64_t)PVDER_SI_STEPS * a.ld + e] = 0;
+  a.si[(int64_t)PVDER_SI_EPISODE * a.ld + e] = episode;
+  a.si[(int64_t)PVDER_SI_STATUS * a.ld + e] = PVDER_STATUS_OK;
+  a.si[(int64_t)PVDER_SI_DONE * a.ld + e] = 0;
+  a.si[(int64_t)PVDER_SI_WINDUP * a.ld + e] = 0;
+#pragma unroll
+  for (int h = 0; h < PVDER_N_ACTIONS; ++h) a.si[(int64_t)(PVDER_SI_HIST + h) * a.ld + e] = 0;
+  Outputs o;
+  compute_outputs<M>(cfg, y, Qref, Vdcref, Vgrid, Sinsol, 0, o);
+#pragma unroll
+  for (int j = 0; j < PVDER_OBS_DIM; ++j) {
+    if (a.obs_f32) a.obs_f32[e * PVDER_OBS_DIM + j] = (float)o.obs[j];
+    if (a.obs_f64) a.obs_f64[e * PVDER_OBS_DIM + j] = o.obs[j];
+  }
+}
+
+// Materialise the event tables the step kernel draws on the fly (value in force from instant j).
+__global__ void __launch_bounds__(BLOCK) events_kernel(const __grid_constant__ pvder_env_config cfg,
+                                                       const int32_t* episode, double* vtab, double* stab,
+                                                       int64_t ld, int64_t n, int64_t env_offset) {
+  const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (e >= n) return;
+  double Vgrid = 1.0, Sinsol = 100.0;
+  const uint32_t ep = episode ? (uint32_t)episode[e] : 0u;
+  for (int j = 0; j < cfg.ev_count; ++j) {
+    if (cfg.ev_voltage_enable || cfg.ev_insol_enable) draw_event(cfg, (uint32_t)(env_offset + e), ep, (uint32_t)j, Vgrid, Sinsol);
+    vtab[(int64_t)j * ld + e] = Vgrid;
+    stab[(int64_t)j * ld + e] = Sinsol;
+  }
+}
+
+__global__ void __launch_bounds__(BLOCK) actions_kernel(uint64_t seed, int64_t step_index, int32_t* action, int64_t n,
+                                                        int64_t env_offset) {
+  const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (e >= n) return;
+  uint32_t r[4];
+  philox4x32_10((uint32_t)(env_offset + e), (uint32_t)step_index, (uint32_t)(step_index >> 32), STREAM_ACTIONS,
+                (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  action[e] = (int32_t)(((uint64_t)r[0] * PVDER_N_ACTIONS) >> 32);   // unbiased to 2^-32
+}
+
+__global__ void stats_kernel(const double* sd, const int32_t* si, int64_t ld, int ns, int64_t n, double* out) {
+  double acc[11];
+#pragma unroll
+  for (int i = 0; i < 11; ++i) acc[i] = 0.0;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    acc[0] += sd[(int64_t)PVDER_SD_RETURN(ns) * ld + e];
+    acc[1] += (double)si[(int64_t)PVDER_SI_STEPS * ld + e];
+    acc[2] += (double)(si[(int64_t)PVDER_SI_DONE * ld + e] != 0);
+    acc[3] += (double)(si[(int64_t)PVDER_SI_STATUS * ld + e] != PVDER_STATUS_OK);
+    for (int h = 0; h < PVDER_N_ACTIONS; ++h) acc[4 + h] += (double)si[(int64_t)(PVDER_SI_HIST + h) * ld + e];
+    acc[9] += (double)si[(int64_t)PVDER_SI_WINDUP * ld + e];
+    acc[10] += 1.0;
+  }
+#pragma unroll
+  for (int i = 0; i < 11; ++i) {
+    double v = acc[i];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + i, v);
+  }
+}
+
+// K0: FP64 FMA peak.  8 independent dependent-chains per thread, 2 flop per DFMA.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* sink, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (s == 123.456) sink[0] = s;
+}
+
+}  // namespace pvder
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace pvder;
+
+static thread_local cudaError_t g_last_cuda = cudaSuccess;
+static int cuda_fail(cudaError_t e) {
+  g_last_cuda = e;
+  return PVDER_ERR_CUDA;
+}
+#define CK(call)                                  \
+  do {                                            \
+    cudaError_t _e = (call);                      \
+    if (_e != cudaSuccess) return cuda_fail(_e);  \
+  } while (0)
+
+static int check_cfg(const pvder_env_config* c) {
+  if (!c) return PVDER_ERR_INVALID;
+  if (c->phases != 1 && c->phases != 3) return PVDER_ERR_INVALID;
+  if (c->n_sub_per_step < 1 || c->micro < 1 || c->ev_step_k < 1 || c->ev_count < 0) return PVDER_ERR_INVALID;
+  if (c->goal < 0 || c->goal > 2) return PVDER_ERR_INVALID;
+  if (c->event_mode < 0 || c->event_mode > 2) return PVDER_ERR_INVALID;
+  return PVDER_OK;
+}
+
+extern "C" {
+
+int pvder_abi_version(void) { return PVDER_ABI_VERSION; }
+
+const char* pvder_error_string(int code) {
+  switch (code) {
+    case PVDER_OK: return "ok";
+    case PVDER_ERR_INVALID: return "invalid argument";
+    case PVDER_ERR_NOMEM: return "out of memory";
+    case PVDER_ERR_CUDA: return cudaGetErrorString(g_last_cuda);
+    default: return "unknown error";
+  }
+}
+
+size_t pvder_sd_fields(int phases) { return PVDER_SD_FIELDS(6 * phases + 5); }
+size_t pvder_si_fields(void) { return PVDER_SI_FIELDS; }
+
+int pvder_steady_state(const pvder_params* par, int phases, double Vdc, double Vgrid, double Sinsol, double Q_ref,
+                       double wte0, double* y0, double* ma0, double* ia0) {
+  if (!par || !y0 || (phases != 1 && phases != 3)) return PVDER_ERR_INVALID;
+  typedef std::complex<double> cd;
+  const double np_iph = par->np_iph100 * (Sinsol / 100.0);
+  const double ex = std::exp(par->kappa * Vdc);
+  const double Ipv = np_iph - par->np_irs * (ex - 1.0);
+  double Ppv = Ipv * Vdc * par->pv_scale;
+  if (Ppv < 0.0) Ppv = 0.0;
+  const double vg = Vgrid * par->vgs;
+  const double Lf = 1.0 / par->inv_Lf;
+  const cd Zt(par->Rt, par->Xt);
+  auto resid = [&](double iR, double iI, double& r0, double& r1, cd& vt) {
+    const cd i(iR, iI);
+    const cd v = vg + Zt * i;
+    vt = v + par->Rf * i + cd(0.0, Lf) * i;
+    const cd S = 0.5 * (double)phases * vt * std::conj(i);
+    const cd Sp = 0.5 * (double)phases * v * std::conj(i);
+    r0 = S.real() - Ppv;
+    r1 = Sp.imag() - Q_ref;
+  };
+  // Newton on (iR, iI); start from a power-balance guess
+  double z0 = 2.0 * Ppv / ((double)phases * vg), z1 = 0.0;
+  cd vt;
+  for (int it = 0; it < 60; ++it) {
+    double r0, r1, a0, a1, b0, b1, c0, c1, d0, d1;
+    resid(z0, z1, r0, r1, vt);
+    const double h = 1e-7;
+    resid(z0 + h, z1, a0, a1, vt);
+    resid(z0 - h, z1, b0, b1, vt);
+    resid(z0, z1 + h, c0, c1, vt);
+    resid(z0, z1 - h, d0, d1, vt);
+    const double J00 = (a0 - b0) / (2 * h), J10 = (a1 - b1) / (2 * h), J01 = (c0 - d0) / (2 * h), J11 = (c1 - d1) / (2 * h);
+    const double det = J00 * J11 - J01 * J10;
+    if (!(std::fabs(det) > 0.0)) return PVDER_ERR_INVALID;
+    const double s0 = (J11 * r0 - J01 * r1) / det, s1 = (-J10 * r0 + J00 * r1) / det;
+    z0 -= s0;
+    z1 -= s1;
+    if (std::fabs(s0) + std::fabs(s1) < 1e-15) break;
+  }
+  double r0, r1;
+  resid(z0, z1, r0, r1, vt);
+  if (!(std::fabs(r0) + std::fabs(r1) < 1e-10)) return PVDER_ERR_INVALID;
+  const cd m0 = 2.0 * vt / Vdc, i0(z0, z1);
+  const cd rot[3] = {cd(1.0, 0.0), cd(-0.5, -0.86602540378443864676), cd(-0.5, 0.86602540378443864676)};
+  for (int k = 0; k < phases; ++k) {
+    const cd ik = i0 * rot[k], mk = m0 * rot[k];
+    y0[6 * k + 0] = ik.real(); y0[6 * k + 1] = ik.imag();
+    y0[6 * k + 2] = mk.real(); y0[6 * k + 3] = mk.imag();
+    y0[6 * k + 4] = 0.0; y0[6 * k + 5] = 0.0;
+  }
+  const int B = 6 * phases;
+  y0[B] = Vdc; y0[B + 1] = i0.real(); y0[B + 2] = i0.imag(); y0[B + 3] = 0.0; y0[B + 4] = wte0;
+  if (ma0) { ma0[0] = m0.real(); ma0[1] = m0.imag(); }
+  if (ia0) { ia0[0] = i0.real(); ia0[1] = i0.imag(); }
+  return PVDER_OK;
+}
+
+static int launch_reset(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const uint8_t* mask,
+                        const double* vtab, const double* stab, int32_t init, float* obs_f32, double* obs_f64,
+                        int64_t n, int64_t off, cudaStream_t st) {
+  if (n == 0) return PVDER_OK;
+  ResetArgs a{sd, si, ld, mask, vtab, stab, init, obs_f32, obs_f64, n, off};
+  const unsigned grid = (unsigned)((n + BLOCK - 1) / BLOCK);
+  if (cfg->phases == 1) reset_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, a);
+  else reset_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, a);
+  CK(cudaGetLastError());
+  return PVDER_OK;
+}
+
+int pvder_reset(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const uint8_t* mask, int32_t init,
+                float* obs_f32, double* obs_f64, int64_t n_envs, int64_t env_offset, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!sd || !si || n_envs < 0 || ld < n_envs) return PVDER_ERR_INVALID;
+  if (cfg->event_mode == PVDER_EVENTS_TABLE && cfg->ev_start_k == 0) return PVDER_ERR_INVALID;  // tables start after t=0
+  return launch_reset(cfg, sd, si, ld, mask, nullptr, nullptr, init, obs_f32, obs_f64, n_envs, env_offset,
+                      (cudaStream_t)stream);
+}
+
+int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+               const double* vgrid_tab, const double* sinsol_tab, float* obs_f32, double* obs_f64, double* reward_f64,
+               int32_t* reward_i32, uint8_t* done, int64_t n_envs, int64_t env_offset, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!sd || !si || !action || n_envs < 0 || ld < n_envs) return PVDER_ERR_INVALID;
+  if (cfg->event_mode == PVDER_EVENTS_TABLE && cfg->ev_count > 0 && (!vgrid_tab || !sinsol_tab)) return PVDER_ERR_INVALID;
+  if (n_envs == 0) return PVDER_OK;
+  StepArgs a{sd, si, ld, action, vgrid_tab, sinsol_tab, obs_f32, obs_f64, reward_f64, reward_i32, done, n_envs, env_offset};
+  const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cfg->phases == 1) step_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, a);
+  else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, a);
+  CK(cudaGetLastError());
+  return PVDER_OK;
+}
+
+int pvder_generate_events(const pvder_env_config* cfg, const int32_t* episode, double* vgrid_tab, double* sinsol_tab,
+                          int64_t ld, int64_t n_envs, int64_t env_offset, void* stream) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!vgrid_tab || !sinsol_tab || n_envs < 0 || ld < n_envs) return PVDER_ERR_INVALID;
+  if (n_envs == 0 || cfg->ev_count == 0) return PVDER_OK;
+  const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
+  events_kernel<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(*cfg, episode, vgrid_tab, sinsol_tab, ld, n_envs, env_offset);
+  CK(cudaGetLastError());
+  return PVDER_OK;
+}
+
+int pvder_sample_actions(uint64_t seed, int64_t step_index, int32_t* action, int64_t n_envs, int64_t env_offset,
+                         void* stream) {
+  if (!action || n_envs < 0) return PVDER_ERR_INVALID;
+  if (n_envs == 0) return PVDER_OK;
+  const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
+  actions_kernel<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(seed, step_index, action, n_envs, env_offset);
+  CK(cudaGetLastError());
+  return PVDER_OK;
+}
+
+int pvder_stats_reduce(const double* sd, const int32_t* si, int64_t ld, int phases, int64_t n_envs, double* out16,
+                       void* stream) {
+  if (!sd || !si || !out16 || (phases != 1 && phases != 3) || n_envs < 0) return PVDER_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(out16, 0, 16 * sizeof(double), st));
+  if (n_envs == 0) return PVDER_OK;
+  int grid = (int)((n_envs + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  stats_kernel<<<grid, 256, 0, st>>>(sd, si, ld, 6 * phases + 5, n_envs, out16);
+  CK(cudaGetLastError());
+  return PVDER_OK;
+}
+
+int pvder_fp64_peak(int iters, double* tflops, double* ms_out) {
+  if (iters < 1 || !tflops) return PVDER_ERR_INVALID;
+  double* sink = nullptr;
+  CK(cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  const int grid = 148 * 8, block = 256;
+  fp64_peak_kernel<<<grid, block>>>(sink, 64, 1.0000001, 1e-9);   // warm-up
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(e0));
+    fp64_peak_kernel<<<grid, block>>>(sink, iters, 1.0000001, 1e-9);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  const double flops = 2.0 * 64.0 * (double)iters * (double)grid * (double)block;
+  *tflops = flops / ((double)best * 1e-3) * 1e-12;
+  if (ms_out) *ms_out = best;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return PVDER_OK;
+}
+
+// ---- host-buffer handle API ------------------------------------------------------------------
+struct pvder_env {
+  pvder_env_config cfg;
+  int64_t n, off, ld;
+  int ns;
+  double* sd;
+  int32_t* si;
+  int32_t* d_action;
+  float* d_obs;
+  double* d_obs64;
+  double* d_reward;
+  uint8_t* d_done;
+  double* d_vtab;
+  double* d_stab;
+  cudaStream_t stream;
+  cudaEvent_t e0, e1;
+  double ms_total;
+  int64_t launches;
+};
+
+int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_offset, pvder_env** out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!out || n_envs < 1) return PVDER_ERR_INVALID;
+  pvder_env* h = new (std::nothrow) pvder_env();
+  if (!h) return PVDER_ERR_NOMEM;
+  std::memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->n = n_envs;
+  h->off = env_offset;
+  h->ld = (n_envs + 31) / 32 * 32;
+  h->ns = 6 * cfg->phases + 5;
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->e0));
+  CK(cudaEventCreate(&h->e1));
+  CK(cudaMalloc(&h->sd, sizeof(double) * PVDER_SD_FIELDS(h->ns) * h->ld));
+  CK(cudaMalloc(&h->si, sizeof(int32_t) * PVDER_SI_FIELDS * h->ld));
+  CK(cudaMemsetAsync(h->sd, 0, sizeof(double) * PVDER_SD_FIELDS(h->ns) * h->ld, h->stream));
+  CK(cudaMemsetAsync(h->si, 0, sizeof(int32_t) * PVDER_SI_FIELDS * h->ld, h->stream));
+  CK(cudaMalloc(&h->d_action, sizeof(int32_t) * h->n));
+  CK(cudaMalloc(&h->d_obs, sizeof(float) * PVDER_OBS_DIM * h->n));
+  CK(cudaMalloc(&h->d_obs64, sizeof(double) * PVDER_OBS_DIM * h->n));
+  CK(cudaMalloc(&h->d_reward, sizeof(double) * h->n));
+  CK(cudaMalloc(&h->d_done, h->n));
+  if (cfg->event_mode == PVDER_EVENTS_TABLE && cfg->ev_count > 0) {
+    CK(cudaMalloc(&h->d_vtab, sizeof(double) * cfg->ev_count * h->ld));
+    CK(cudaMalloc(&h->d_stab, sizeof(double) * cfg->ev_count * h->ld));
+  }
+  rc = launch_reset(&h->cfg, h->sd, h->si, h->ld, nullptr, h->d_vtab, h->d_stab, 1, nullptr, nullptr, h->n, h->off, h->stream);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return PVDER_OK;
+}
+
+int pvder_env_destroy(pvder_env* h) {
+  if (!h) return PVDER_ERR_INVALID;
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->sd); cudaFree(h->si); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_obs64);
+  cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_vtab); cudaFree(h->d_stab);
+  cudaEventDestroy(h->e0); cudaEventDestroy(h->e1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return PVDER_OK;
+}
+
+int pvder_env_set_event_tables(pvder_env* h, const double* vgrid_tab, const double* sinsol_tab) {
+  if (!h || !h->d_vtab || !vgrid_tab || !sinsol_tab) return PVDER_ERR_INVALID;
+  // host tables are [ev_count][n]; device rows are padded to ld
+  CK(cudaMemcpy2DAsync(h->d_vtab, sizeof(double) * h->ld, vgrid_tab, sizeof(double) * h->n, sizeof(double) * h->n,
+                       h->cfg.ev_count, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(h->d_stab, sizeof(double) * h->ld, sinsol_tab, sizeof(double) * h->n, sizeof(double) * h->n,
+                       h->cfg.ev_count, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PVDER_OK;
+}
+
+int pvder_env_reset_host(pvder_env* h, float* obs_out, double* obs64_out) {
+  if (!h) return PVDER_ERR_INVALID;
+  int rc = launch_reset(&h->cfg, h->sd, h->si, h->ld, nullptr, h->d_vtab, h->d_stab, 0, h->d_obs, h->d_obs64, h->n, h->off,
+                        h->stream);
+  if (rc) return rc;
+  if (obs_out) CK(cudaMemcpyAsync(obs_out, h->d_obs, sizeof(float) * PVDER_OBS_DIM * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (obs64_out)
+    CK(cudaMemcpyAsync(obs64_out, h->d_obs64, sizeof(double) * PVDER_OBS_DIM * h->n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PVDER_OK;
+}
+
+int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
+                        uint8_t* done_out) {
+  if (!h || !action) return PVDER_ERR_INVALID;
+  CK(cudaMemcpyAsync(h->d_action, action, sizeof(int32_t) * h->n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->e0, h->stream));
+  int rc = pvder_step(&h->cfg, h->sd, h->si, h->ld, h->d_action, h->d_vtab, h->d_stab, obs_out ? h->d_obs : nullptr,
+                      obs64_out ? h->d_obs64 : nullptr, h->d_reward, nullptr, h->d_done, h->n, h->off, h->stream);
+  if (rc) return rc;
+  CK(cudaEventRecord(h->e1, h->stream));
+  if (obs_out) CK(cudaMemcpyAsync(obs_out, h->d_obs, sizeof(float) * PVDER_OBS_DIM * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (obs64_out)
+    CK(cudaMemcpyAsync(obs64_out, h->d_obs64, sizeof(double) * PVDER_OBS_DIM * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (reward_out) CK(cudaMemcpyAsync(reward_out, h->d_reward, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
+  if (done_out) CK(cudaMemcpyAsync(done_out, h->d_done, h->n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->e0, h->e1));
+  h->ms_total += ms;
+  h->launches += 1;
+  return PVDER_OK;
+}
+
+int pvder_env_state_host(pvder_env* h, double* sd_out, int32_t* si_out) {
+  if (!h) return PVDER_ERR_INVALID;
+  if (sd_out)
+    CK(cudaMemcpy2DAsync(sd_out, sizeof(double) * h->n, h->sd, sizeof(double) * h->ld, sizeof(double) * h->n,
+                         PVDER_SD_FIELDS(h->ns), cudaMemcpyDeviceToHost, h->stream));
+  if (si_out)
+    CK(cudaMemcpy2DAsync(si_out, sizeof(int32_t) * h->n, h->si, sizeof(int32_t) * h->ld, sizeof(int32_t) * h->n,
+                         PVDER_SI_FIELDS, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PVDER_OK;
+}
+
+int pvder_env_set_refs_host(pvder_env* h, const double* sd_in) {
+  if (!h || !sd_in) return PVDER_ERR_INVALID;
+  CK(cudaMemcpy2DAsync(h->sd, sizeof(double) * h->ld, sd_in, sizeof(double) * h->n, sizeof(double) * h->n,
+                       PVDER_SD_FIELDS(h->ns), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return PVDER_OK;
+}
+
+int pvder_env_device_ptrs(pvder_env* h, double** sd, int32_t** si, int64_t* ld) {
+  if (!h) return PVDER_ERR_INVALID;
+  if (sd) *sd = h->sd;
+  if (si) *si = h->si;
+  if (ld) *ld = h->ld;
+  return PVDER_OK;
+}
+
+int pvder_env_kernel_ms(pvder_env* h, double* ms_total, int64_t* launches) {
+  if (!h) return PVDER_ERR_INVALID;
+  if (ms_total) *ms_total = h->ms_total;
+  if (launches) *launches = h->launches;
+  h->ms_total = 0.0;
+  h->launches = 0;
+  return PVDER_OK;
+}
+
+void* pvder_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void pvder_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+"""Vectorised PVDER-v0: N independent environments stepped by ONE CUDA launch.
+
+The per-step contract is the reference's (gym_PVDER/envs/PVDER_env.py:138-196) applied
+element-wise: ``step(actions[N]) -> (obs[N,11] f32, reward[N], done[N] bool, info)``; the env
+state lives in two SoA device tensors and never leaves HBM.  Tensors are torch CUDA tensors whose
+raw pointers are handed to libpvder_b200.so (C ABI, include/pvder_b200.h) on torch's current
+stream -- torch is plumbing (memory + streams) only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .. import _cabi
+from ..config import EnvConfig
+from ..spaces import Box, Discrete
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class PVDERVecEnv:
+    metadata = {"render.modes": ["vector"]}
+    observed_quantities = ["iaR", "iaI", "vaR", "vaI", "P_PCC", "Q_PCC", "Vdc", "Ppv", "Vdc_ref", "Q_ref", "tStart"]
+
+    def __init__(self, num_envs, device="cuda", seed=0, env_offset=0, model_type="model_2",
+                 n_sim_time_steps_per_env_step=15, max_sim_time=40.0, DISCRETE_REWARD=True,
+                 goals_list=("voltage_regulation",), events_spec=None, event_mode="philox", auto_reset=False,
+                 obs_f64=False, micro=1, config=None):
+        import torch
+
+        self.torch = torch
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("PVDERVecEnv needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        self.cfg = config or EnvConfig(model_type=model_type,
+                                       n_sim_time_steps_per_env_step=n_sim_time_steps_per_env_step,
+                                       max_sim_time=max_sim_time, DISCRETE_REWARD=DISCRETE_REWARD,
+                                       goals_list=list(goals_list), events_spec=events_spec,
+                                       event_mode=event_mode, seed=seed, auto_reset=auto_reset, micro=micro)
+        self.num_envs = int(num_envs)
+        self.env_offset = int(env_offset)
+        self.ns = self.cfg.n_state
+        self.ld = (self.num_envs + 31) // 32 * 32
+        self.action_space = Discrete(_cabi.N_ACTIONS)                             # PVDER_env.py:50
+        self.observation_space = Box(-10, 10, (_cabi.OBS_DIM,), np.float32)       # PVDER_env.py:51
+        with torch.cuda.device(self.device):
+            dev = self.device
+            self.sd = torch.zeros((_cabi.sd_fields(self.ns), self.ld), dtype=torch.float64, device=dev)
+            self.si = torch.zeros((_cabi.SI_FIELDS, self.ld), dtype=torch.int32, device=dev)
+            self.obs = torch.zeros((self.num_envs, _cabi.OBS_DIM), dtype=torch.float32, device=dev)
+            self.obs64 = torch.zeros((self.num_envs, _cabi.OBS_DIM), dtype=torch.float64, device=dev) if obs_f64 else None
+            self.reward = torch.zeros(self.num_envs, dtype=torch.float64, device=dev)
+            self.reward_i = torch.zeros(self.num_envs, dtype=torch.int32, device=dev) if self.cfg.DISCRETE_REWARD else None
+            self.done = torch.zeros(self.num_envs, dtype=torch.uint8, device=dev)
+            self._actions = torch.zeros(self.num_envs, dtype=torch.int32, device=dev)
+            self._stats = torch.zeros(16, dtype=torch.float64, device=dev)
+            self.vgrid_tab = self.sinsol_tab = None
+            if self.cfg.c.event_mode == _cabi.EVENT_MODES["table"]:
+                k = max(1, self.cfg.c.ev_count)
+                self.vgrid_tab = torch.ones((k, self.ld), dtype=torch.float64, device=dev)
+                self.sinsol_tab = torch.full((k, self.ld), 100.0, dtype=torch.float64, device=dev)
+        self._initialised = False
+        self._step_index = 0
+        self.launches = 0
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _cfgp(self):
+        return C.byref(self.cfg.c)
+
+    # ---- API ------------------------------------------------------------------------------
+    def reset(self, mask=None):
+        """PVDER.reset (PVDER_env.py:316-334) for all envs, or those with mask != 0."""
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=self.torch.uint8).contiguous()
+        with self.torch.cuda.device(self.device):
+            _cabi.check(self.lib.pvder_reset(self._cfgp(), _ptr(self.sd), _ptr(self.si), self.ld, _ptr(m),
+                                             0 if self._initialised else 1, _ptr(self.obs), _ptr(self.obs64),
+                                             self.num_envs, self.env_offset, self._stream()))
+        self._initialised = True
+        self.launches += 1
+        return self.obs
+
+    def step(self, actions):
+        """PVDER.step (PVDER_env.py:138-196) for every env; one kernel launch."""
+        if not self._initialised:
+            raise RuntimeError("Cannot call step() before reset()")
+        t = self.torch
+        if not isinstance(actions, t.Tensor):
+            actions = t.as_tensor(np.asarray(actions), device=self.device)
+        if actions.dtype != t.int32 or actions.device != self.device or not actions.is_contiguous():
+            self._actions.copy_(actions.to(self.device))
+            actions = self._actions
+        if actions.numel() != self.num_envs:
+            raise ValueError("actions must have num_envs elements")
+        with t.cuda.device(self.device):
+            _cabi.check(self.lib.pvder_step(self._cfgp(), _ptr(self.sd), _ptr(self.si), self.ld, _ptr(actions),
+                                            _ptr(self.vgrid_tab), _ptr(self.sinsol_tab), _ptr(self.obs),
+                                            _ptr(self.obs64), _ptr(self.reward), _ptr(self.reward_i), _ptr(self.done),
+                                            self.num_envs, self.env_offset, self._stream()))
+        self.launches += 1
+        self._step_index += 1
+        reward = self.reward_i if self.cfg.DISCRETE_REWARD else self.reward
+        return self.obs, reward, self.done.view(t.bool), {}
+
+    def sample_actions(self, out=None):
+        """action_space.sample() for every env, on device (Philox stream 1)."""
+        out = self._actions if out is None else out
+        with self.torch.cuda.device(self.device):
+            _cabi.check(self.lib.pvder_sample_actions(self.cfg.c.seed, self._step_index, _ptr(out), self.num_envs,
+                                                      self.env_offset, self._stream()))
+        self.launches += 1
+        return out
+
+    def set_event_tables(self, vgrid, sinsol):
+        """event_mode='table': value in force from event instant j on, shape [ev_count, num_envs]."""
+        t = self.torch
+        self.vgrid_tab[:, :self.num_envs].copy_(t.as_tensor(vgrid, dtype=t.float64))
+        self.sinsol_tab[:, :self.num_envs].copy_(t.as_tensor(sinsol, dtype=t.float64))
+
+    def generate_events(self):
+        """Materialise the Philox event tables (what the step kernel draws on the fly)."""
+        t = self.torch
+        k = max(1, self.cfg.c.ev_count)
+        v = t.ones((k, self.ld), dtype=t.float64, device=self.device)
+        s = t.full((k, self.ld), 100.0, dtype=t.float64, device=self.device)
+        ep = self.si[_cabi.SI_EPISODE].contiguous()
+        with t.cuda.device(self.device):
+            _cabi.check(self.lib.pvder_generate_events(self._cfgp(), _ptr(ep), _ptr(v), _ptr(s), self.ld, self.num_envs,
+                                                       self.env_offset, self._stream()))
+        return v[:, :self.num_envs], s[:, :self.num_envs]
+
+    def stats(self):
+        """Episode statistics summed over this shard (env_utilities.py:12-46) as a device tensor[16]."""
+        with self.torch.cuda.device(self.device):
+            _cabi.check(self.lib.pvder_stats_reduce(_ptr(self.sd), _ptr(self.si), self.ld, self.cfg.phases, self.num_envs,
+                                                    _ptr(self._stats), self._stream()))
+        return self._stats
+
+    # ---- state views ------------------------------------------------------------------------
+    @property
+    def y(self):
+        return self.sd[:self.ns, :self.num_envs]
+
+    def field(self, name):
+        return self.sd[_cabi.sd_index(self.ns)[name], :self.num_envs]
+
+    @property
+    def k(self):
+        return self.si[_cabi.SI_K, :self.num_envs]
+
+    @property
+    def steps(self):
+        return self.si[_cabi.SI_STEPS, :self.num_envs]
+
+    @property
+    def status(self):
+        return self.si[_cabi.SI_STATUS, :self.num_envs]
+
+    def check_status(self):
+        """Raise like the reference does (AssertionError, PVDER_env.py:177/201) if any env failed."""
+        st = self.status
+        if bool((st == _cabi.STATUS_BAD_ACTION).any()):
+            raise AssertionError("an action is not available in the environment action space!")
+        if bool((st == _cabi.STATUS_NONFINITE).any()):
+            raise AssertionError("Convergence flag should be true to calculate reward!")
+
+    def close(self):
+        pass

@@ -1,0 +1,97 @@
+"""Tiny environment registry with the old-gym surface the reference relies on:
+``register`` / ``make`` / ``spec`` and the ``TimeLimit`` wrapper that ``gym.make`` puts around
+the env (reference gym_PVDER/__init__.py:3-10; tests use env.spec.id, env.unwrapped and
+attribute pass-through such as env.steps / env.sim, gym_PVDER/tests/test_gym_PVDER.py:11-14,
+:108).  When a real ``gym`` is importable the id is registered there as well."""
+from __future__ import annotations
+
+import copy
+
+
+class EnvSpec:
+    def __init__(self, id, entry_point, kwargs=None, max_episode_steps=None):
+        self.id = id
+        self.entry_point = entry_point
+        self.kwargs = dict(kwargs or {})
+        self.max_episode_steps = max_episode_steps
+
+    def make(self, **kwargs):
+        kw = copy.deepcopy(self.kwargs)
+        kw.update(kwargs)
+        env = self.entry_point(spec=self, **kw)
+        if self.max_episode_steps is not None:
+            env = TimeLimit(env, self.max_episode_steps)
+        return env
+
+    def __repr__(self):
+        return f"EnvSpec({self.id})"
+
+
+class TimeLimit:
+    """gym.wrappers.TimeLimit (old API: 4-tuple step)."""
+
+    def __init__(self, env, max_episode_steps):
+        self.env = env
+        self._max_episode_steps = int(max_episode_steps)
+        self._elapsed_steps = None
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.env, name)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+    @property
+    def spec(self):
+        return self.env.spec
+
+    def step(self, action):
+        assert self._elapsed_steps is not None, "Cannot call env.step() before calling reset()"
+        observation, reward, done, info = self.env.step(action)
+        self._elapsed_steps += 1
+        if self._elapsed_steps >= self._max_episode_steps:
+            info["TimeLimit.truncated"] = not done
+            done = True
+        return observation, reward, done, info
+
+    def reset(self, **kwargs):
+        self._elapsed_steps = 0
+        return self.env.reset(**kwargs)
+
+    def render(self, mode="vector", **kwargs):
+        return self.env.render(mode=mode, **kwargs)
+
+    def close(self):
+        return self.env.close()
+
+    def seed(self, seed=None):
+        return self.env.seed(seed)
+
+
+registry: dict[str, EnvSpec] = {}
+
+
+def register(id, entry_point, kwargs=None, max_episode_steps=None):
+    registry[id] = EnvSpec(id, entry_point, kwargs, max_episode_steps)
+    try:  # also expose the id through a real gym, when there is one
+        import gym  # type: ignore
+
+        if id not in getattr(gym.envs.registry, "env_specs", gym.envs.registry):
+            gym.register(id=id + "-b200" if False else id, entry_point=entry_point, kwargs=kwargs,
+                         max_episode_steps=max_episode_steps)
+    except Exception:
+        pass
+    return registry[id]
+
+
+def spec(id):
+    if id not in registry:
+        raise KeyError(f"No registered env with id: {id}")
+    return registry[id]
+
+
+def make(id, **kwargs):
+    return spec(id).make(**kwargs)

@@ -1,0 +1,159 @@
+/* pvder_b200.h -- C ABI of the B200-native PVDER-v0 hot path (libpvder_b200.so).
+ *
+ * The reference is pure Python and has no FFI; its "operator interface" for this path is the
+ * Gym Env API of gym_PVDER/envs/PVDER_env.py.  Each entry point below names the reference
+ * method(s) it replaces (file:line under /root/reference).  All pointers are plain C pointers;
+ * "device" pointers are CUDA device addresses owned by the caller, `stream` is a cudaStream_t
+ * passed as void* (NULL = default stream).  No call synchronises unless it says so.
+ *
+ * Per-env state is SoA with leading dimension `ld` (>= n_envs), env index fastest:
+ *   sd : double  [PVDER_SD_FIELDS(ns)][ld]   ns = 11 (single-phase) or 23 (three-phase)
+ *   si : int32_t [PVDER_SI_FIELDS][ld]
+ */
+#ifndef PVDER_B200_H_
+#define PVDER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVDER_ABI_VERSION 1
+#define PVDER_OBS_DIM 11          /* PVDER_env.py:44-51 observed_quantities */
+#define PVDER_N_ACTIONS 5         /* PVDER_env.py:50 Discrete(5) */
+#define PVDER_MAX_STATES 23
+
+/* ---- sd field offsets (rows of the double state matrix), ns = number of ODE states ---- */
+#define PVDER_SD_Y 0              /* rows 0..ns-1: ODE state, order SURVEY.md A.1, last = delta = wte - w*t */
+#define PVDER_SD_QREF(ns) ((ns) + 0)      /* PV_model.Q_ref   (PVDER_env.py:225) */
+#define PVDER_SD_VDCREF(ns) ((ns) + 1)    /* PV_model.Vdc_ref (PVDER_env.py:229) */
+#define PVDER_SD_VGRID(ns) ((ns) + 2)     /* grid-voltage event value in force */
+#define PVDER_SD_SINSOL(ns) ((ns) + 3)    /* insolation event value in force */
+#define PVDER_SD_RETURN(ns) ((ns) + 4)    /* episode return (env_utilities.py:32-38) */
+#define PVDER_SD_REWARD(ns) ((ns) + 5)    /* last reward (cached tuple of PVDER_env.py:145-152,196) */
+#define PVDER_SD_FIELDS(ns) ((ns) + 6)
+
+/* ---- si field offsets ---- */
+#define PVDER_SI_K 0              /* half-cycle counter: t = k/120 s  (sim.tStart, PVDER_env.py:180) */
+#define PVDER_SI_STEPS 1          /* env._steps (PVDER_env.py:156) */
+#define PVDER_SI_EPISODE 2        /* episode counter (RNG key) */
+#define PVDER_SI_STATUS 3         /* PVDER_STATUS_* */
+#define PVDER_SI_DONE 4           /* env.done (PVDER_env.py:183-184) */
+#define PVDER_SI_HIST 5           /* 5 rows: action histogram (env_utilities.py:25-30) */
+#define PVDER_SI_WINDUP 10        /* sub-steps taken with an anti-windup clamp active */
+#define PVDER_SI_FIELDS 11
+
+enum { PVDER_GOAL_VOLTAGE = 0, PVDER_GOAL_Q = 1, PVDER_GOAL_POWER = 2 };      /* PVDER_env.py:78-93 */
+enum { PVDER_EVENTS_NONE = 0, PVDER_EVENTS_PHILOX = 1, PVDER_EVENTS_TABLE = 2 };
+enum { PVDER_STATUS_OK = 0, PVDER_STATUS_BAD_ACTION = 1, PVDER_STATUS_NONFINITE = 2 };
+enum { PVDER_OK = 0, PVDER_ERR_INVALID = -1, PVDER_ERR_CUDA = -2, PVDER_ERR_NOMEM = -3 };
+
+/* Per-unit DER parameters (values from config_der.json:2-21 / :66-84). */
+typedef struct pvder_params {
+  double Rf, Rt, Xt, inv_Lf, inv_wb;
+  double Kp_GCC, Ki_GCC, Kp_DC, Ki_DC, Kp_Q, Ki_Q, wp, Kp_PLL, Ki_PLL;
+  double inv_C, w0, dw;
+  double vgs;        /* LV-side grid phasor magnitude at Vgrid = 1.0 pu */
+  double np_iph100;  /* Np*(Iscr + Kv (T - T0)): array photo-current at Sinsol = 100 */
+  double np_irs;     /* Np*Irs */
+  double kappa;      /* q Vdcbase / (k T A Ns) */
+  double pv_scale;   /* Vdcbase / Sbase */
+  double Vrms_ref;   /* PV_model.Vrms_ref (PVDER_env.py:280) */
+  double iref_limit; /* anti-windup current limit (A.3) */
+  double m_limit10;  /* 10 * m_limit (A.3) */
+  double p_target;   /* P_ref / Sbase (PVDER_env.py:69, :245) */
+  double q_target;   /* Q_ref / Sbase (PVDER_env.py:69, :241) */
+  double Lf, Rf_Rt;  /* reserved for the steady-state solve */
+} pvder_params;
+
+typedef struct pvder_env_config {
+  pvder_params par;
+  int32_t phases;            /* 1: model_1 / derId 10, 3: model_2 / derId 50 (PVDER_env.py:56-58) */
+  int32_t n_sub_per_step;    /* half-cycle sub-steps per env step = 2 * n_sim_time_steps_per_env_step */
+  int32_t micro;             /* integrator steps per half-cycle sub-step (1) */
+  int32_t done_substep;      /* done when k >= done_substep  (tStop >= max_sim_time, PVDER_env.py:183) */
+  int32_t discrete_reward;   /* DISCRETE_REWARD (PVDER_env.py:590-600) */
+  int32_t goal;              /* PVDER_GOAL_* = goals_list[0] (PVDER_env.py:234) */
+  int32_t auto_reset;        /* vector-env option: reset in place when done */
+  int32_t event_mode;        /* PVDER_EVENTS_* */
+  int32_t ev_start_k, ev_step_k, ev_count;   /* event instants on the 1/120 s grid (PVDER_env.py:60-61) */
+  int32_t ev_voltage_enable, ev_insol_enable;
+  double ev_v_min, ev_v_max, ev_s_min, ev_s_max;
+  double delQ_pu, delVdc_pu; /* per-step reference increments (PVDER_env.py:617-618, :225, :229) */
+  double max_sim_time;       /* PVDER_env.py:561-575 */
+  double substeps_per_sec;   /* 120 */
+  uint64_t seed;
+  double Q_ref0, Vdc_ref0;
+  double y0[PVDER_MAX_STATES]; /* reset state (steady-state init, A.6), delta form */
+} pvder_env_config;
+
+int pvder_abi_version(void);
+const char* pvder_error_string(int code);
+size_t pvder_sd_fields(int phases);
+size_t pvder_si_fields(void);
+
+/* Steady-state initialisation (replaces DERModel(..., steadyStateInitialization=True),
+ * PVDER_env.py:374-378).  Host-only Newton solve; y0 gets ns doubles. */
+int pvder_steady_state(const pvder_params* par, int phases, double Vdc, double Vgrid, double Sinsol,
+                       double Q_ref, double wte0, double* y0, double* ma0, double* ia0);
+
+/* reset(): PVDER_env.py:316-334 + 366-398 + 400-411.  mask (device, nullable): reset only envs
+ * with mask[i] != 0.  init != 0: first reset after allocation (episode := 0). */
+int pvder_reset(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const uint8_t* mask,
+                int32_t init, float* obs_f32, double* obs_f64, int64_t n_envs, int64_t env_offset,
+                void* stream);
+
+/* step(action): PVDER_env.py:138-196 (action_calc 198-229, run_simulation 166, reward_calc
+ * 231-301, state 531-542, done 183) for n_envs environments in ONE launch.
+ * action: device int32[n_envs]; vgrid_tab/sinsol_tab: device double[ev_count][ld] when
+ * event_mode == PVDER_EVENTS_TABLE (value in force from event instant j on), else NULL.
+ * Outputs (device, each nullable): obs_f32[n_envs][11], obs_f64[n_envs][11], reward_f64[n_envs],
+ * reward_i32[n_envs] (discrete mode), done[n_envs]. */
+int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+               const double* vgrid_tab, const double* sinsol_tab, float* obs_f32, double* obs_f64,
+               double* reward_f64, int32_t* reward_i32, uint8_t* done, int64_t n_envs, int64_t env_offset,
+               void* stream);
+
+/* Event generator (replaces SimulationEvents.create_random_events as called at
+ * PVDER_env.py:408-411): materialises the per-env tables the step kernel draws on the fly in
+ * PVDER_EVENTS_PHILOX mode.  episode: device int32[n_envs] or NULL (= 0). */
+int pvder_generate_events(const pvder_env_config* cfg, const int32_t* episode, double* vgrid_tab,
+                          double* sinsol_tab, int64_t ld, int64_t n_envs, int64_t env_offset, void* stream);
+
+/* action_space.sample() for every env (examples/gym_PVDER_environment_import_test.py:23). */
+int pvder_sample_actions(uint64_t seed, int64_t step_index, int32_t* action, int64_t n_envs,
+                         int64_t env_offset, void* stream);
+
+/* Episode statistics (env_utilities.py:12-46) reduced over envs into 16 device doubles:
+ * [0] sum return, [1] sum steps, [2] n done, [3] n failed, [4..8] action histogram,
+ * [9] windup sub-steps, [10] n_envs. */
+int pvder_stats_reduce(const double* sd, const int32_t* si, int64_t ld, int phases, int64_t n_envs,
+                       double* out16, void* stream);
+
+/* FP64 FMA peak micro-benchmark (roofline denominator; synchronises). */
+int pvder_fp64_peak(int iters, double* tflops, double* ms);
+
+/* ---- host-buffer handle API: the call a Gym user makes, numpy in / numpy out ---- */
+typedef struct pvder_env pvder_env;
+int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_offset, pvder_env** out);
+int pvder_env_destroy(pvder_env* env);
+int pvder_env_set_event_tables(pvder_env* env, const double* vgrid_tab, const double* sinsol_tab);
+int pvder_env_reset_host(pvder_env* env, float* obs_out, double* obs64_out);
+/* Copies action host->device, launches pvder_step, copies obs/reward/done device->host, waits. */
+int pvder_env_step_host(pvder_env* env, const int32_t* action, float* obs_out, double* obs64_out,
+                        double* reward_out, uint8_t* done_out);
+int pvder_env_state_host(pvder_env* env, double* sd_out, int32_t* si_out);
+int pvder_env_set_refs_host(pvder_env* env, const double* sd_in);
+/* Device pointers of the handle's state (for zero-copy interop). */
+int pvder_env_device_ptrs(pvder_env* env, double** sd, int32_t** si, int64_t* ld);
+/* Average device time (ms) of the step kernel launches since the last call (CUDA events). */
+int pvder_env_kernel_ms(pvder_env* env, double* ms_total, int64_t* launches);
+void* pvder_host_alloc(size_t bytes);   /* pinned host memory */
+void pvder_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVDER_B200_H_ */

@@ -1,0 +1,233 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE ONLY (never imported by the product path).
+
+Single-environment restatement of the reference's PVDER-v0 hot path
+(reference gym_PVDER/envs/PVDER_env.py): step 138-196, action_calc 198-229,
+reward_calc 231-301, reset/setup 316-334 + 366-398, events 400-411, obs 531-542,
+with the simulator calls (``sim.run_simulation()`` -> scipy ``odeint``/LSODA,
+SURVEY.md A.7) restated on top of oracle/pvder_model.py.
+
+PARITY UNPINNED (see pvder_model.py header): the reference cannot run here.
+
+Two integrator tiers:
+  solver="reference": one LSODA call per env step, hmax=1/120, mxstep=50,
+      rtol=atol=1e-4, analytic Jacobian, events looked up by time inside the
+      RHS -- the reference's configuration; used for CPU-baseline timing.
+  solver="tight": LSODA at rtol=1e-11/atol=1e-12 per half-cycle piece with the
+      event values and anti-windup mode sampled at the piece start -- the
+      numerical truth the CUDA trajectories are compared against.
+"""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+from scipy.integrate import odeint
+
+from .pvder_model import Inputs, PVDERModel, load_der_params
+
+SUBSTEPS_PER_SEC = 120            # half-cycle grid (README.md:11; hmax in A.7)
+TINC = 1.0 / 60.0                 # PVDER_env.py:63, :396
+MODEL_SPEC = {"model_1": "10", "model_2": "50"}   # PVDER_env.py:56-58
+
+DEFAULT_EVENTS_SPEC = {           # PVDER_env.py:60-61
+    "insolation": dict(t_events_start=1.0, t_events_stop=39.0, t_events_step=1.0,
+                       min=85.0, max=100.0, ENABLE=False),
+    "voltage": dict(t_events_start=1.0, t_events_stop=39.0, t_events_step=1.0,
+                    min=0.98, max=1.02, ENABLE=True),
+}
+P_REF_W, Q_REF_VAR = 45.4e3, 5.5e3   # PVDER_env.py:69
+DEL_QREF, DEL_VDCREF = 25.0, 0.02    # PVDER_env.py:75
+
+
+class EventTable:
+    """Piece-wise constant event lookup: value of the last event
+    with T <= t, defaults before the first one."""
+
+    def __init__(self):
+        self.grid = []    # (T, Vgrid)
+        self.solar = []   # (T, Sinsol)
+
+    def add_grid_event(self, T, Vgrid):
+        self.grid.append((float(T), float(Vgrid)))
+        self.grid.sort(key=lambda e: e[0])
+
+    def add_solar_event(self, T, Sinsol):
+        self.solar.append((float(T), float(Sinsol)))
+        self.solar.sort(key=lambda e: e[0])
+
+    @staticmethod
+    def _lookup(lst, t, default):
+        val = default
+        for T, v in lst:
+            if T <= t:
+                val = v
+            else:
+                break
+        return val
+
+    def vgrid(self, t):
+        return self._lookup(self.grid, t, 1.0)
+
+    def sinsol(self, t):
+        return self._lookup(self.solar, t, 100.0)
+
+
+def create_random_events(spec, rng: random.Random) -> EventTable:
+    """Restatement of pvder SimulationEvents.create_random_events as driven by
+    PVDER_env.py:400-411 (instants from the *voltage* entry; one event per instant,
+    type chosen among the ENABLEd ones, value uniform in [min, max])."""
+    types = [k for k in spec if spec[k]["ENABLE"]]
+    tab = EventTable()
+    if not types:
+        return tab
+    v = spec["voltage"]
+    for t in np.arange(v["t_events_start"], v["t_events_stop"], v["t_events_step"]):
+        kind = rng.choice(types)
+        if kind == "voltage":
+            tab.add_grid_event(t, rng.uniform(spec["voltage"]["min"], spec["voltage"]["max"]))
+        else:
+            tab.add_solar_event(t, rng.uniform(spec["insolation"]["min"], spec["insolation"]["max"]))
+    return tab
+
+
+def discrete_class(err_rel: float, hi: float) -> int:
+    """PVDER_env.py:280-285 (and 268-273, 292-297)."""
+    if err_rel <= 0.01:
+        return 1
+    if err_rel >= hi:
+        return -5
+    return -1
+
+
+class OraclePVDEREnv:
+    """Old-gym-API single env: reset() -> obs[11]; step(a) -> (obs, reward, done, {})."""
+
+    def __init__(self, n_sim_time_steps_per_env_step=15, max_sim_time=40.0, DISCRETE_REWARD=True,
+                 goals_list=("voltage_regulation",), model_type="model_2", solver="reference",
+                 events_spec=None, events: EventTable | None = None, seed=None,
+                 max_episode_steps=500):
+        self.n = int(n_sim_time_steps_per_env_step)
+        limit = max_episode_steps * self.n * TINC
+        self.max_sim_time = min(max(float(max_sim_time), 1.0), limit)   # PVDER_env.py:561-575
+        self.DISCRETE_REWARD = bool(DISCRETE_REWARD)
+        self.goal = list(goals_list)[0]
+        self.params = load_der_params(MODEL_SPEC[model_type])
+        self.model = PVDERModel(self.params)
+        self.solver = solver
+        self.events_spec = events_spec or {k: dict(v) for k, v in DEFAULT_EVENTS_SPEC.items()}
+        self.fixed_events = events
+        self.rng = random.Random(seed)
+        self.delQ_pu = DEL_QREF * self.n / self.params.Sbase          # PVDER_env.py:617, :225
+        self.delVdc_pu = DEL_VDCREF * self.n / self.params.Vdcbase    # PVDER_env.py:618, :229
+        self.done_substep = int(math.ceil(self.max_sim_time * SUBSTEPS_PER_SEC - 1e-9))
+        self.rhs_evals = 0
+        # A.7 recalls mxstep=50; the restated start-up transient (PLL 90 deg from lock, wte0=6.28)
+        # plus an action step needs up to ~115 LSODA steps in the first 1/60 s, so the restated
+        # reference path raises the cap (documented deviation).
+        self.mxstep = 500
+        self.max_nst = 0
+
+    # -- reset (PVDER_env.py:316-334, 366-398) --
+    def reset(self, y0=None):
+        self.y = np.array(self.model.steady_state()[0] if y0 is None else y0, dtype=float)
+        self.Q_ref = 0.0
+        self.Vdc_ref = self.params.Vdc_ref0
+        self.k = 0                  # half-cycle counter: t = k/120
+        self.steps = 0
+        self.done = False
+        self._reward = 0
+        self.action_stats = [0] * 5
+        self.windup_substeps = 0
+        self.events = self.fixed_events if self.fixed_events is not None else \
+            create_random_events(self.events_spec, self.rng)
+        return np.array(self.state)
+
+    def t(self, k=None):
+        return (self.k if k is None else k) / SUBSTEPS_PER_SEC
+
+    def _inputs(self, t, freeze=None):
+        return Inputs(Vgrid=self.events.vgrid(t), Sinsol=self.events.sinsol(t), Q_ref=self.Q_ref,
+                      Vdc_ref=self.Vdc_ref, freeze=freeze)
+
+    # -- step (PVDER_env.py:138-196) --
+    def step(self, action):
+        if self.done:
+            return np.array(self.state), self._reward, self.done, {}
+        assert action in range(5), "action not in Discrete(5)"      # :201
+        self.action_stats[action] += 1                               # :209
+        dQ = self.delQ_pu if action == 1 else -self.delQ_pu if action == 2 else 0.0
+        dV = self.delVdc_pu if action == 3 else -self.delVdc_pu if action == 4 else 0.0
+        self.Q_ref = self.Q_ref + dQ                                 # :225
+        self.Vdc_ref = self.Vdc_ref + dV                             # :229
+        self.steps += 1
+        ok = self._integrate(2 * self.n)
+        assert ok, "Convergence flag should be true to calculate reward!"   # :177
+        self._reward = self.reward_calc()
+        if self.k >= self.done_substep:                              # :183
+            self.done = True
+        return np.array(self.state), self._reward, self.done, {}
+
+    def _integrate(self, n_sub):
+        m = self.model
+        if self.solver == "reference":
+            t0 = self.t()
+            tt = t0 + np.arange(self.n + 1) * TINC
+
+            def f(y, t):
+                self.rhs_evals += 1
+                return m.rhs(y, t, self._inputs(t))
+
+            def jf(y, t):
+                return m.jac(y, t, self._inputs(t))
+
+            sol, info = odeint(f, self.y, tt, Dfun=jf, full_output=1, hmax=1.0 / 120.0, mxstep=self.mxstep,
+                               atol=1e-4, rtol=1e-4)
+            self.k += n_sub
+            self.y = sol[-1]
+            self.max_nst = max(self.max_nst, int(np.max(np.diff(np.concatenate([[0], info["nst"]])))))
+            return info["message"] == "Integration successful."
+        for _ in range(n_sub):
+            t0 = self.t()
+            t1 = self.t(self.k + 1)
+            mask = m.freeze_mask(self.y, self._inputs(t0))
+            if any(mask):
+                self.windup_substeps += 1
+            inp = self._inputs(t0, freeze=mask)
+            sol, info = odeint(lambda y, t: m.rhs(y, t, inp), self.y, [t0, t1],
+                               Dfun=lambda y, t: m.jac(y, t, inp), full_output=1, mxstep=200000,
+                               atol=1e-12, rtol=1e-11)
+            if info["message"] != "Integration successful.":
+                return False
+            self.y = sol[-1]
+            self.k += 1
+        return True
+
+    # -- reward (PVDER_env.py:231-301) --
+    def reward_calc(self):
+        out = self.model.outputs(self.y, self._inputs(self.t()))
+        return reward_from_outputs(out, self.goal, self.DISCRETE_REWARD, self.Q_ref, self.params)
+
+    # -- obs (PVDER_env.py:531-542) --
+    @property
+    def state(self):
+        out = self.model.outputs(self.y, self._inputs(self.t()))
+        return (out["iaR"], out["iaI"], out["vaR"], out["vaI"], out["P_PCC"], out["Q_PCC"],
+                out["Vdc"], out["Ppv"], self.Vdc_ref, self.Q_ref, self.t() / self.max_sim_time)
+
+
+def reward_from_outputs(out, goal, discrete, Q_ref, params):
+    """PVDER_env.py:231-301 for the 'required' reward of each goal (:249, :451)."""
+    if goal == "voltage_regulation":
+        x, target, hi = out["Vrms"], params.Vrms_ref, 0.05
+    elif goal == "Q_regulation":
+        x, target, hi = out["Q_PCC"], Q_REF_VAR / params.Sbase, 0.05
+    elif goal == "power_regulation":
+        x, target, hi = out["P_PCC"], P_REF_W / params.Sbase, 0.03
+    else:
+        raise ValueError(goal)
+    if discrete:
+        if goal == "Q_regulation" and target == 0.0:
+            target = 1e-6
+        return discrete_class(abs(x - target) / abs(target), hi)
+    return -((x - target) ** 2)

@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE: loader for the plain-C++ build of the per-env device logic
+(tests/host_emul/emul.cpp).  Lets the CPU test tier check the *generated kernel source*
+(model RHS, symbolic LU, Rodas4, events, outputs) against the oracle without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import gym_pvder_b200 as G
+from gym_pvder_b200 import _cabi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "host_emul", "emul.cpp")
+_LIB = os.path.join(_HERE, "host_emul", "libpvder_emul.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    deps = [_SRC] + [os.path.join(_cabi.CSRC, f) for f in os.listdir(_cabi.CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                        "-o", _LIB, _SRC], check=True)
+    _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class EmulVecEnv:
+    """Same SoA state layout and step semantics as PVDERVecEnv, run by the C++ emulation."""
+
+    def __init__(self, num_envs, env_offset=0, **kw):
+        self.lib = load()
+        self.cfg = G.EnvConfig(**kw)
+        self.n = num_envs
+        self.off = env_offset
+        self.ns = self.cfg.n_state
+        self.ld = num_envs
+        self.sd = np.zeros((_cabi.sd_fields(self.ns), self.ld))
+        self.si = np.zeros((_cabi.SI_FIELDS, self.ld), dtype=np.int32)
+        self.obs64 = np.zeros((num_envs, 11))
+        self.reward = np.zeros(num_envs)
+        self.reward_i = np.zeros(num_envs, dtype=np.int32)
+        self.done = np.zeros(num_envs, dtype=np.uint8)
+        self.vtab = self.stab = None
+        self._init = False
+
+    def set_event_tables(self, v, s):
+        self.vtab = np.ascontiguousarray(v, dtype=np.float64)
+        self.stab = np.ascontiguousarray(s, dtype=np.float64)
+
+    def reset(self):
+        self.lib.emul_reset(C.byref(self.cfg.c), _p(self.sd), _p(self.si), C.c_int64(self.ld), 0 if self._init else 1,
+                            _p(self.obs64), C.c_int64(self.n), C.c_int64(self.off))
+        self._init = True
+        return self.obs64.copy()
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        self.lib.emul_step(C.byref(self.cfg.c), _p(self.sd), _p(self.si), C.c_int64(self.ld), _p(a), _p(self.vtab),
+                           _p(self.stab), _p(self.obs64), _p(self.reward), _p(self.reward_i), _p(self.done),
+                           C.c_int64(self.n), C.c_int64(self.off))
+        rew = self.reward_i.copy() if self.cfg.DISCRETE_REWARD else self.reward.copy()
+        return self.obs64.copy(), rew, self.done.astype(bool), {}
+
+    def events(self):
+        k = max(1, self.cfg.c.ev_count)
+        v = np.ones((k, self.ld))
+        s = np.full((k, self.ld), 100.0)
+        ep = np.ascontiguousarray(self.si[_cabi.SI_EPISODE])
+        self.lib.emul_events(C.byref(self.cfg.c), _p(ep), _p(v), _p(s), C.c_int64(self.ld), C.c_int64(self.n),
+                             C.c_int64(self.off))
+        return v, s
+
+
+def rhs(cfg, y, inp4, frz=0):
+    f = np.zeros(cfg.n_state)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    i4 = np.ascontiguousarray(inp4, dtype=np.float64)
+    load().emul_rhs(C.byref(cfg.c), _p(y), _p(i4), C.c_uint(frz), _p(f))
+    return f
+
+
+def wsolve(cfg, y, inp4, ghinv, b, frz=0):
+    b = np.array(b, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    i4 = np.ascontiguousarray(inp4, dtype=np.float64)
+    load().emul_wsolve(C.byref(cfg.c), _p(y), _p(i4), C.c_uint(frz), C.c_double(ghinv), _p(b))
+    return b
+
+
+def freeze_bits(cfg, y, inp4):
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    i4 = np.ascontiguousarray(inp4, dtype=np.float64)
+    load().emul_freeze_bits.restype = C.c_uint
+    return int(load().emul_freeze_bits(C.byref(cfg.c), _p(y), _p(i4)))

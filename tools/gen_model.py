@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Code generator for the register-resident PV-DER model kernels.
+
+Emits gym-solarpvder-environment_b200/csrc/pvder_model_{1ph,3ph}.cuh, each holding, for one
+model (single-phase n=11, three-phase n=23; state order SURVEY.md A.1 with the PLL angle kept
+as delta = wte - w_grid*t, A.4):
+
+  * rhs():    the autonomous ODE right-hand side,
+  * factor(): W = I/(h*gamma) - df/dy built from the analytic Jacobian (differentiated here with
+              sympy) and LU-factorised *symbolically*: the sparsity pattern and the pivot order
+              are fixed at generation time, so the factorisation is straight-line scalar code
+              with no indexing, no pivot search and no zero work (41 of 121 / 165 of 529 entries
+              are structurally non-zero) -- everything lives in registers,
+  * solve():  the matching forward/backward substitution.
+
+The anti-windup clamp (A.3) is a per-row freeze mask sampled by the caller on the half-cycle
+grid: a frozen row has f_r = 0 and W_r = e_r/(h*gamma).
+
+Run:  python tools/gen_model.py     (sympy needed only here, never at run time)
+"""
+import os
+import sys
+
+import sympy as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
+
+PAR = ["Rf", "Rt", "Xt", "inv_Lf", "inv_wb", "Kp_GCC", "Ki_GCC", "Kp_DC", "Ki_DC", "Kp_Q", "Ki_Q",
+       "wp", "Kp_PLL", "Ki_PLL", "inv_C", "w0", "dw"]
+INP = ["vg", "Qref", "Vdcref", "Ppv", "dPpv"]
+
+
+def build(P):
+    par = {n: sp.Symbol("p_" + n) for n in PAR}
+    inp = {n: sp.Symbol("in_" + n) for n in INP}
+    names = []
+    for k in range(P):
+        ph = "abc"[k]
+        names += [f"i{ph}R", f"i{ph}I", f"x{ph}R", f"x{ph}I", f"u{ph}R", f"u{ph}I"]
+    names += ["Vdc", "xDC", "xQ", "xPLL", "dl"]
+    y = [sp.Symbol("y_" + n) for n in names]
+    n = len(y)
+    base = 6 * P
+    Vdc, xDC, xQ, xPLL, dl = y[base:base + 5]
+    sn, cs = sp.Symbol("sn"), sp.Symbol("cs")          # sin(dl), cos(dl), supplied by sincos()
+    if P == 1:
+        rot = [(sp.Integer(1), sp.Integer(0))]
+        alpha = [(sp.Integer(1), sp.Integer(0))]       # (cos a_k, sin a_k)
+    else:
+        h3 = sp.Symbol("SQ3") / 2     # sqrt(3), emitted as a literal
+        rot = [(sp.Integer(1), sp.Integer(0)), (-sp.Rational(1, 2), -h3), (-sp.Rational(1, 2), h3)]
+        alpha = [(sp.Integer(1), sp.Integer(0)), (-sp.Rational(1, 2), h3), (-sp.Rational(1, 2), -h3)]
+    p = par
+    vR, vI, mR, mI = [], [], [], []
+    Q = 0
+    Pinv = 0
+    vd = 0
+    for k in range(P):
+        o = 6 * k
+        iR, iI, xR, xI, uR, uI = y[o:o + 6]
+        rr, ri = rot[k]
+        vR.append(inp["vg"] * rr + p["Rt"] * iR - p["Xt"] * iI)
+        vI.append(inp["vg"] * ri + p["Xt"] * iR + p["Rt"] * iI)
+        mR.append(p["Kp_GCC"] * uR + xR)
+        mI.append(p["Kp_GCC"] * uI + xI)
+        Q += sp.Rational(1, 2) * (vI[k] * iR - vR[k] * iI)
+        Pinv += sp.Rational(1, 4) * Vdc * (mR[k] * iR + mI[k] * iI)
+        ca, sa = alpha[k]
+        ck = cs * ca + sn * sa       # cos(dl - a_k)
+        sk = sn * ca - cs * sa       # sin(dl - a_k)
+        vd += (vR[k] * ck + vI[k] * sk) / P
+    we = p["Kp_PLL"] * vd + xPLL + p["w0"]
+    wr = we * p["inv_wb"]
+    irefR = xDC + p["Kp_DC"] * (inp["Vdcref"] - Vdc)
+    irefI = xQ - p["Kp_Q"] * (inp["Qref"] - Q)
+    f = [None] * n
+    for k in range(P):
+        o = 6 * k
+        iR, iI, xR, xI, uR, uI = y[o:o + 6]
+        rr, ri = rot[k]
+        f[o] = p["inv_Lf"] * (-p["Rf"] * iR - vR[k] + sp.Rational(1, 2) * mR[k] * Vdc) + wr * iI
+        f[o + 1] = p["inv_Lf"] * (-p["Rf"] * iI - vI[k] + sp.Rational(1, 2) * mI[k] * Vdc) - wr * iR
+        f[o + 2] = p["Ki_GCC"] * uR
+        f[o + 3] = p["Ki_GCC"] * uI
+        f[o + 4] = p["wp"] * (-uR + (rr * irefR - ri * irefI) - iR)
+        f[o + 5] = p["wp"] * (-uI + (ri * irefR + rr * irefI) - iI)
+    inv_Vdc = sp.Symbol("inv_Vdc")
+    f[base] = (inp["Ppv"] - Pinv) * p["inv_C"] * inv_Vdc
+    f[base + 1] = p["Ki_DC"] * (inp["Vdcref"] - Vdc)
+    f[base + 2] = -p["Ki_Q"] * (inp["Qref"] - Q)
+    f[base + 3] = p["Ki_PLL"] * vd
+    f[base + 4] = p["Kp_PLL"] * vd + xPLL + p["dw"]
+    # Jacobian: chain rule through the helper symbols
+    helpers = {sn: sp.sin(dl), cs: sp.cos(dl), inv_Vdc: 1 / Vdc}
+    Ppv_f = sp.Function("Ppvf")(Vdc)
+    J = {}
+    for r in range(n):
+        fr = f[r].subs(inp["Ppv"], Ppv_f)
+        fr_full = fr.subs(helpers)
+        for c in range(n):
+            d = sp.diff(fr_full, y[c])
+            if d == 0:
+                continue
+            d = d.subs(sp.Derivative(Ppv_f, Vdc), inp["dPpv"]).subs(Ppv_f, inp["Ppv"])
+            d = d.subs({sp.sin(dl): sn, sp.cos(dl): cs})
+            d = d.subs(1 / Vdc, inv_Vdc)
+            d = sp.simplify(d) if P == 1 else d
+            d = d.subs(1 / Vdc, inv_Vdc).subs(Vdc ** -2, inv_Vdc ** 2)
+            if d != 0:
+                J[(r, c)] = d
+    frozen_rows = []
+    for k in range(P):
+        frozen_rows += [6 * k + 2, 6 * k + 3, 6 * k + 4, 6 * k + 5]
+    frozen_rows += [base + 1, base + 2]
+    return dict(P=P, n=n, names=names, y=y, f=f, J=J, par=par, inp=inp, frozen=frozen_rows,
+                helpers=(sn, cs, inv_Vdc))
+
+
+def ccode(e):
+    return sp.ccode(e, standard="c99")
+
+
+def emit_block(assignments, tmp_prefix, indent="    "):
+    """CSE + C emission of [(lhs, expr)] ; returns list of lines."""
+    exprs = [e for _, e in assignments]
+    repl, red = sp.cse(exprs, symbols=sp.numbered_symbols(tmp_prefix), optimizations="basic")
+    lines = []
+    for s, e in repl:
+        lines.append(f"{indent}const double {s} = {ccode(e)};")
+    for (lhs, _), e in zip(assignments, red):
+        lines.append(f"{indent}{lhs} = {ccode(e)};")
+    return lines
+
+
+def elimination_order(n, pattern, P):
+    """Diagonal pivots only.  Integrator-like states (x, xDC, xQ, xPLL: rows with one or two
+    entries and a 1/(h*gamma) pivot) go first, then the controller outputs u (pivot
+    1/(h*gamma)+wp), then the stiff core (currents, Vdc, delta) -- i.e. block elimination down
+    to a dense (2P+2)x(2P+2) Schur complement, found here by a greedy minimum-fill search
+    within each tier."""
+    base = 6 * P
+    tier = {}
+    for k in range(P):
+        o = 6 * k
+        tier[o + 2] = tier[o + 3] = 0
+        tier[o + 4] = tier[o + 5] = 1
+        tier[o] = tier[o + 1] = 2
+    tier[base + 1] = tier[base + 2] = tier[base + 3] = 0
+    tier[base] = 2
+    tier[base + 4] = 2
+    pat = set(pattern)
+    remaining = set(range(n))
+    order = []
+    while remaining:
+        best = None
+        for k in sorted(remaining):
+            rows = [r for r in remaining if r != k and (r, k) in pat]
+            cols = [c for c in remaining if c != k and (k, c) in pat]
+            fill = sum(1 for r in rows for c in cols if (r, c) not in pat)
+            cost = (tier[k], fill, len(rows) * len(cols), k)
+            if best is None or cost < best[0]:
+                best = (cost, k, rows, cols)
+        _, k, rows, cols = best
+        for r in rows:
+            for c in cols:
+                pat.add((r, c))
+        remaining.remove(k)
+        order.append(k)
+    return order
+
+
+def generate(P):
+    m = build(P)
+    n, y, f, J = m["n"], m["y"], m["f"], m["J"]
+    tag = f"{P}ph"
+    cls = f"Model{P}ph"
+    L = []
+    A = L.append
+    A("// GENERATED by tools/gen_model.py -- do not edit by hand.")
+    A(f"// PV-DER model, {P} phase(s), {n} states: " + " ".join(m["names"]))
+    A("// Equations: SURVEY.md Appendix A.2-A.4 (restated from the un-vendored pvder package that")
+    A("// reference gym_PVDER/envs/PVDER_env.py:26-35 imports); PLL angle stored as delta = wte - w*t.")
+    A("#pragma once")
+    A('#include "pvder_common.cuh"')
+    A("")
+    A("namespace pvder {")
+    A("")
+    A(f"struct {cls} {{")
+    A(f"  static constexpr int NS = {n};")
+    A(f"  static constexpr int PHASES = {P};")
+    A(f"  static constexpr int NNZ_J = {len(J)};")
+    nf = len(m["frozen"])
+    A(f"  static constexpr int NFRZ = {nf};   // freeze-mask bits (rows: " +
+      ",".join(m["names"][r] for r in m["frozen"]) + ")")
+    A("")
+    # ---------- unpack macros
+    def unpack(indent="    "):
+        out = []
+        for i, s in enumerate(y):
+            out.append(f"{indent}const double {s} = y[{i}];")
+        return out
+
+    par_unpack = [f"    const double p_{nme} = par.{nme};" for nme in PAR]
+    # ---------- rhs
+    A("  // Autonomous right-hand side f(y).  frz: bit b set => row frozen_rows[b] is clamped (f = 0).")
+    A("  template <bool FRZ>")
+    A("  static PVDER_DEV void rhs(const double (&y)[NS], const Params& par, const Inputs& in,")
+    A("                                             unsigned frz, double (&f)[NS]) {")
+    L.extend(par_unpack)
+    L.extend(unpack())
+    A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
+    A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
+    A("    double sn, cs;")
+    A("    sincos(y_dl, &sn, &cs);")
+    A("    double in_Ppv, in_dPpv;")
+    A("    ppv_eval(par, in, y_Vdc, in_Ppv, in_dPpv);")
+    A("    (void)in_dPpv;")
+    A("    const double inv_Vdc = 1.0 / y_Vdc;")
+    L.extend(emit_block([(f"f[{r}]", f[r]) for r in range(n)], "t"))
+    A("    if (FRZ) {")
+    for b, r in enumerate(m["frozen"]):
+        A(f"      if (frz & {1 << b}u) f[{r}] = 0.0;")
+    A("    }")
+    A("  }")
+    A("")
+    # ---------- factor
+    pattern = set(J.keys()) | {(i, i) for i in range(n)}
+    order = elimination_order(n, pattern, P)
+    wname = lambda r, c: f"w_{r}_{c}"
+    A("  // LU factors of W = I/(h*gamma) - J(y), fixed pattern, fixed pivot order:")
+    A("  //   " + " ".join(m["names"][k] for k in order))
+    # symbolic elimination to learn the final pattern
+    pat = set(pattern)
+    pos = {k: i for i, k in enumerate(order)}
+    ops = []   # ('inv', k) ('mul', r, k) ('fma', r, c, k) ('new', r, c, k)
+    for k in order:
+        ops.append(("inv", k))
+        rows = sorted(r for r in range(n) if pos[r] > pos[k] and (r, k) in pat)
+        cols = sorted(c for c in range(n) if pos[c] > pos[k] and (k, c) in pat)
+        for r in rows:
+            ops.append(("mul", r, k))
+            for c in cols:
+                if (r, c) in pat:
+                    ops.append(("fma", r, c, k))
+                else:
+                    pat.add((r, c))
+                    ops.append(("new", r, c, k))
+    members = sorted(pat)
+    A("  struct LU {")
+    A("    // strictly-lower entries hold multipliers, upper entries hold U, d_k = 1/pivot")
+    for (r, c) in members:
+        if r != c:
+            A(f"    double {wname(r, c)};")
+    for k in range(n):
+        A(f"    double d_{k};")
+    A("  };")
+    nflop_f = sum(2 if o[0] in ("fma",) else 1 for o in ops)
+    A(f"  static constexpr int LU_ENTRIES = {len(members)};   // incl. {len(members) - len(pattern)} fill-ins")
+    A("")
+    A("  template <bool FRZ>")
+    A("  static PVDER_DEV void factor(const double (&y)[NS], const Params& par, const Inputs& in,")
+    A("                                                unsigned frz, double ghinv, LU& lu) {")
+    L.extend(par_unpack)
+    L.extend(unpack())
+    A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
+    A("    (void)in_Qref; (void)in_Vdcref;")
+    A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
+    A("    double sn, cs;")
+    A("    sincos(y_dl, &sn, &cs);")
+    A("    double in_Ppv, in_dPpv;")
+    A("    ppv_eval(par, in, y_Vdc, in_Ppv, in_dPpv);")
+    A("    const double inv_Vdc = 1.0 / y_Vdc;")
+    keys = sorted(J.keys())
+    for (r, c) in keys:
+        A(f"    double j_{r}_{c};")
+    L.extend(emit_block([(f"j_{r}_{c}", J[(r, c)]) for (r, c) in keys], "q"))
+    A("    if (FRZ) {")
+    for b, r in enumerate(m["frozen"]):
+        ent = [f"j_{rr}_{cc} = 0.0;" for (rr, cc) in keys if rr == r]
+        A(f"      if (frz & {1 << b}u) {{ " + " ".join(ent) + " }")
+    A("    }")
+    # W entries
+    for i in range(n):
+        if (i, i) in J:
+            A(f"    double w_{i}_{i} = ghinv - j_{i}_{i};")
+        else:
+            A(f"    double w_{i}_{i} = ghinv;")
+    for (r, c) in keys:
+        if r != c:
+            A(f"    double {wname(r, c)} = -j_{r}_{c};")
+    for op in ops:
+        if op[0] == "inv":
+            k = op[1]
+            A(f"    const double d_{k} = 1.0 / w_{k}_{k};")
+        elif op[0] == "mul":
+            _, r, k = op
+            A(f"    {wname(r, k)} *= d_{k};")
+        elif op[0] == "fma":
+            _, r, c, k = op
+            A(f"    {wname(r, c)} = fma(-{wname(r, k)}, {wname(k, c)}, {wname(r, c)});")
+        else:
+            _, r, c, k = op
+            A(f"    double {wname(r, c)} = -{wname(r, k)} * {wname(k, c)};")
+    for (r, c) in members:
+        if r != c:
+            A(f"    lu.{wname(r, c)} = {wname(r, c)};")
+    for k in range(n):
+        A(f"    lu.d_{k} = d_{k};")
+    A("  }")
+    A("")
+    # ---------- solve
+    A("  static PVDER_DEV void solve(const LU& lu, double (&b)[NS]) {")
+    nflop_s = 0
+    for k in order:
+        for r in sorted(r for r in range(n) if pos[r] > pos[k] and (r, k) in pat):
+            A(f"    b[{r}] = fma(-lu.{wname(r, k)}, b[{k}], b[{r}]);")
+            nflop_s += 2
+    for k in reversed(order):
+        for c in sorted(c for c in range(n) if pos[c] > pos[k] and (k, c) in pat):
+            A(f"    b[{k}] = fma(-lu.{wname(k, c)}, b[{c}], b[{k}]);")
+            nflop_s += 2
+        A(f"    b[{k}] *= lu.d_{k};")
+        nflop_s += 1
+    A("  }")
+    A("")
+    A(f"  static constexpr int FLOPS_LU = {nflop_f};      // executed flops of the symbolic LU")
+    A(f"  static constexpr int FLOPS_SOLVE = {nflop_s};   // executed flops of one substitution pair")
+    A("};")
+    A("")
+    A("}  // namespace pvder")
+    path = os.path.join(OUT, f"pvder_model_{tag}.cuh")
+    with open(path, "w") as fh:
+        fh.write("\n".join(L) + "\n")
+    print(f"{path}: n={n} nnz(J)={len(J)} LU entries={len(members)} order={[m['names'][k] for k in order]} "
+          f"lu_flops={nflop_f} solve_flops={nflop_s}")
+    return m, order
+
+
+if __name__ == "__main__":
+    for P in ([1, 3] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:]]):
+        generate(P)
