@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""PVDER-v0 hot-path benchmark (driver contract: one JSON line on rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is ONE env step of every environment of the batch: 2n = 30 half-cycle (1/120 s) Rodas4
+sub-steps per env, fused with action, events/RNG, reward, observation and done in one kernel
+launch (reference gym_PVDER/envs/PVDER_env.py:138-196).  Workload at N GPUs: 1,048,576
+single-phase envs PER GPU (BASELINE.json metric: "env-steps/sec ... (1M envs)"), sharded by global
+env index, no collective on the data path ("scaling": "weak").
+
+  value        env-steps/s with state, actions and outputs resident in HBM (CUDA events, max over ranks)
+  e2e          same metric through the host-buffer C ABI call a Gym user makes
+               (pvder_env_step_host: pinned numpy action H2D -> kernel -> obs/reward/done D2H, every step)
+  roofline     FP64-compute bound: achieved = sub-steps/s x F, F = 2.2 kflop
+               (1-ph) / 12.5 kflop (3-ph) per sub-step; peak = FP64 FMA peak measured live by the
+               K0 micro-benchmark (MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline the restated reference path (oracle O2: scipy LSODA with the reference's settings,
+               Python RHS/Jacobian callbacks) timed on this box's host cores on a bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_ALGO = {"model_1": 2.2e3, "model_2": 12.5e3}   # algorithmic flop per half-cycle sub-step
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: oracle O2 on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    model_type, n_sim, steps, warmup, seed = args
+    import random
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    from oracle.env_oracle import OraclePVDEREnv
+
+    env = OraclePVDEREnv(model_type=model_type, n_sim_time_steps_per_env_step=n_sim, solver="reference",
+                         DISCRETE_REWARD=False, seed=seed)
+    rng = random.Random(seed)
+    env.reset()
+    done_steps = 0
+    for _ in range(warmup):
+        _, _, d, _ = env.step(rng.randrange(5))
+        if d:
+            env.reset()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, d, _ = env.step(rng.randrange(5))
+        done_steps += 1
+        if d:
+            env.reset()
+    return time.perf_counter() - t0, done_steps
+
+
+def cpu_reference(model_type, n_sim, steps, warmup, envs_per_core=1):
+    """All host cores, one oracle env per worker process; returns (env_steps_per_s, cores, sample)."""
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    jobs = [(model_type, n_sim, steps, warmup, 1000 + i) for i in range(cores * envs_per_core)]
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[1] for r in res)
+    busy = max(r[0] for r in res) * envs_per_core
+    sample = (f"{len(jobs)} oracle envs ({model_type}, n={n_sim}, LSODA rtol=atol=1e-4 hmax=1/120, random actions) x "
+              f"{steps} env steps on {cores} processes; slowest worker {busy:.2f} s, wall incl. spawn {wall:.2f} s")
+    return total / busy, cores, sample
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [x.strip() for x in s.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+                pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=160)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="model_1", choices=["model_1", "model_2"])
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--n-sim", type=int, default=15)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0: min(steps, 40))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric, unit = "env-steps/sec", "env-steps/s"
+    workload = (f"{args.envs_per_gpu} PVDER-v0 envs per GPU ({args.model}: "
+                f"{'single-phase derId 10, 11 states' if args.model == 'model_1' else 'three-phase derId 50, 23 states'}), "
+                f"n_sim_time_steps_per_env_step={args.n_sim} ({2 * args.n_sim} half-cycle sub-steps per env step), continuous reward, "
+                f"default voltage events (Philox per-env streams), random actions, auto-reset at 40 s (160 steps/episode)")
+    config = {"workload": workload, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
+              "sub_steps_per_env_step": 2 * args.n_sim, "sharding": f"env-index x{world}, no data-path collective",
+              "l2_policy": "state+outputs per step (>=270 MB at 1M envs) exceed the 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        v, cores, sample = cpu_reference(args.model, args.n_sim, args.steps, args.warmup)
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * cores / v, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
+                                 "note": "restated reference path (pvder unavailable): oracle O2"},
+                "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import gym_pvder_b200 as G
+    from gym_pvder_b200 import _cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    n = args.envs_per_gpu
+    K, Wm = args.steps, args.warmup
+    cfg = G.EnvConfig(model_type=args.model, n_sim_time_steps_per_env_step=args.n_sim, max_sim_time=40.0,
+                      DISCRETE_REWARD=False, goals_list=["voltage_regulation"], event_mode="philox", seed=2026,
+                      auto_reset=True)
+    env = G.PVDERVecEnv(n, device=dev, env_offset=rank * n, config=cfg)
+    env.reset()
+    acts = torch.empty((K + Wm, n), dtype=torch.int32, device=dev)
+    for s in range(K + Wm):
+        _cabi.check(lib.pvder_sample_actions(cfg.c.seed, s, C.c_void_p(acts[s].data_ptr()), n, rank * n,
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    for s in range(Wm):
+        env.step(acts[s])
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for s in range(K):
+        env.step(acts[Wm + s])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    env.check_status()
+    stats = env.stats().clone()
+    if world > 1:
+        dist.all_reduce(stats)                       # optional episode-statistics reduction (NCCL), off the timed path
+    value = world * n * K / (ms_max * 1e-3)
+    kernel_ms = ms / K
+
+    # ---- e2e leg: host buffers through the handle C ABI ----------------------------------------------
+    Ke = args.e2e_steps or min(K, 40)
+    h = C.c_void_p()
+    _cabi.check(lib.pvder_env_create(C.byref(cfg.c), n, rank * n, C.byref(h)))
+    h_act = torch.empty((8, n), dtype=torch.int32).pin_memory()
+    h_act.copy_(acts[:8].cpu())
+    h_obs = torch.empty((n, 11), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    _cabi.check(lib.pvder_env_reset_host(h, C.c_void_p(h_obs.data_ptr()), None))
+
+    def host_step(s):
+        _cabi.check(lib.pvder_env_step_host(h, C.c_void_p(h_act[s % 8].data_ptr()), C.c_void_p(h_obs.data_ptr()), None,
+                                            C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_done.data_ptr())))
+
+    for s in range(3):
+        host_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        host_step(3 + s)
+    barrier()
+    wall = time.perf_counter() - t0
+    tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * Ke / float(tw.item())
+    kms, kcnt = C.c_double(), C.c_int64()
+    _cabi.check(lib.pvder_env_kernel_ms(h, C.byref(kms), C.byref(kcnt)))
+    e2e_checksum = float(h_rew.sum())
+    _cabi.check(lib.pvder_env_destroy(h))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline: FP64 FMA peak measured live (K0) ----------------------------------------------------
+    tf, pms = C.c_double(), C.c_double()
+    _cabi.check(lib.pvder_fp64_peak(4000, C.byref(tf), C.byref(pms)))
+    sub_per_launch = n * 2 * args.n_sim
+    achieved = sub_per_launch * F_ALGO[args.model] / (kernel_ms * 1e-3) * 1e-12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
+                "traffic": None, "kernel": f"pvder::step_kernel<Model{'1' if args.model == 'model_1' else '3'}ph>",
+                "kernel_ms": kernel_ms, "flop_per_sub_step": F_ALGO[args.model],
+                "peak_source": "FP64 FMA micro-benchmark pvder_fp64_peak run in this process (MEASURED_PEAKS.json has no FP64 entry)",
+                "hbm_algorithmic_bytes_per_launch": n * (2 * 8 * _cabi.sd_fields(cfg.n_state) + 4 * 8 + 4 + 44 + 8 + 1),
+                "note": "SURVEY.md 8d: the path is FP64-compute bound, not HBM/tensor; the contract's enum has no fp64 "
+                        "member so the bound is named explicitly"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+        hb = roofline["hbm_algorithmic_bytes_per_launch"] / (kernel_ms * 1e-3) * 1e-9
+        roofline["hbm_gbs_achieved"] = hb
+        roofline["hbm_frac_of_measured"] = hb / peaks["hbm_gbs"]
+    except Exception:
+        pass
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, cores, sample = cpu_reference(args.model, args.n_sim, 160, 2, envs_per_core=1)
+        cpu = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
+               "note": "restated reference path (pvder unavailable): oracle O2"}
+
+    st = stats.cpu().numpy()
+    line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config,
+            "sub_steps_per_sec": value * 2 * args.n_sim,
+            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (44 + 8 + 1) * n,
+                    "steps": Ke, "kernel_ms_in_e2e": kms.value / max(1, kcnt.value), "reward_checksum": e2e_checksum},
+            "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "episode_stats": {"envs": st[10], "windup_sub_steps": st[9], "failed": st[3]}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

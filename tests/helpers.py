@@ -1,0 +1,59 @@
+"""Shared helpers of the test-suite (oracle-side plumbing)."""
+import math
+import random
+
+import numpy as np
+
+from oracle.env_oracle import DEFAULT_EVENTS_SPEC, EventTable, OraclePVDEREnv, create_random_events
+
+W = 2.0 * math.pi * 60.0
+SAG_SPEC = {"voltage": {"min": 0.90, "max": 1.02, "ENABLE": True}, "insolation": {"ENABLE": True}}
+
+
+def full_spec(partial):
+    spec = {k: dict(v) for k, v in DEFAULT_EVENTS_SPEC.items()}
+    for k, v in (partial or {}).items():
+        spec[k].update(v)
+    return spec
+
+
+def oracle_tables(events: EventTable, c):
+    """Forward-filled [ev_count, 1] tables (value in force from instant j on) of an oracle EventTable."""
+    K = max(1, c.ev_count)
+    v = np.ones((K, 1))
+    s = np.full((K, 1), 100.0)
+    for j in range(c.ev_count):
+        T = (c.ev_start_k + j * c.ev_step_k) / 120.0
+        v[j, 0] = events.vgrid(T)
+        s[j, 0] = events.sinsol(T)
+    return v, s
+
+
+def table_to_events(vcol, scol, c):
+    """Inverse: an oracle EventTable reproducing forward-filled columns."""
+    ev = EventTable()
+    for j in range(c.ev_count):
+        T = (c.ev_start_k + j * c.ev_step_k) / 120.0
+        ev.add_grid_event(T, float(vcol[j]))
+        ev.add_solar_event(T, float(scol[j]))
+    return ev
+
+
+def oracle_delta_state(orc: OraclePVDEREnv):
+    y = orc.y.copy()
+    y[-1] -= W * orc.t()
+    return y
+
+
+# state tolerances (DESIGN.md "Tolerances"): electrical + controller states rtol 1e-5 / atol 1e-8;
+# PLL integrator xPLL (rad/s, ~0 at lock, compare as frequency w_e = xPLL + 377) and angle separately.
+def assert_state_close(y_gpu, y_ref, phases, rtol=1e-5, atol=1e-8, xpll_atol=2e-4, delta_atol=5e-6, what=""):
+    B = 6 * phases
+    main = list(range(B + 3))
+    np.testing.assert_allclose(y_gpu[main], y_ref[main], rtol=rtol, atol=atol, err_msg=f"{what} states")
+    assert abs(y_gpu[B + 3] - y_ref[B + 3]) <= xpll_atol, f"{what} xPLL {y_gpu[B + 3]} vs {y_ref[B + 3]}"
+    assert abs(y_gpu[B + 4] - y_ref[B + 4]) <= delta_atol, f"{what} delta {y_gpu[B + 4]} vs {y_ref[B + 4]}"
+
+
+def random_events(seed, partial=SAG_SPEC):
+    return create_random_events(full_spec(partial), random.Random(seed))

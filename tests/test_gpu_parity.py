@@ -1,0 +1,306 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against
+  (1) the oracle (tight LSODA) on seeded inputs,
+  (2) the committed golden fixtures (tests/golden),
+  (3) the bit-exact numpy twins for events / actions / rewards,
+  (4) the plain-C++ build of the same per-env source (tests/host_emul) -- catches nvcc/ptxas
+      issues and gives ~1e-12 agreement on whole trajectories.
+Tolerances: DESIGN.md "Tolerances" (rtol 1e-5 / atol 1e-8 on states and observations; separate
+absolute bounds for the two PLL states)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from oracle import twin
+from oracle.env_oracle import EventTable, OraclePVDEREnv
+from oracle.pvder_model import load_der_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _venv(cuda, n, **kw):
+    import gym_pvder_b200 as G
+
+    return G.PVDERVecEnv(n, device=cuda, obs_f64=True, **kw)
+
+
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_matches_cpp_emulation(cuda, model_type):
+    import torch
+    import emul_harness as E
+
+    n = 300   # not a multiple of the block size
+    kw = dict(model_type=model_type, events_spec=H.SAG_SPEC, seed=1234, DISCRETE_REWARD=True)
+    g = _venv(cuda, n, env_offset=17, **kw)
+    e = E.EmulVecEnv(n, env_offset=17, **kw)
+    og = g.reset().cpu().numpy()
+    oe = e.reset()
+    np.testing.assert_allclose(g.obs64.cpu().numpy(), oe, rtol=0, atol=1e-15)
+    assert og.dtype == np.float32
+    near = 0
+    for step in range(10):
+        a = g.sample_actions()
+        a_np = a.cpu().numpy().copy()
+        np.testing.assert_array_equal(a_np, twin.sample_actions_twin(1234, step, n, 17))
+        obs, rew, done, _ = g.step(a)
+        oe, re_, de, _ = e.step(a_np)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(g.sd[:, :n].cpu().numpy(), e.sd, rtol=1e-9, atol=1e-11)
+        np.testing.assert_array_equal(g.si[:, :n].cpu().numpy(), e.si)
+        np.testing.assert_array_equal(done.cpu().numpy(), de)
+        mism = rew.cpu().numpy() != re_
+        near += int(mism.sum())
+    assert near <= 1, "discrete rewards differ from the C++ build of the same source"
+    assert int(g.si[10, :n].sum()) == int(e.si[10].sum())
+
+
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_trajectory_vs_tight_oracle(cuda, model_type):
+    """Same y0, parameters, actions and event sequence as the oracle's tight LSODA path."""
+    import torch
+
+    schedules = [[0] * 6, [1, 2, 0, 3, 4, 1], [3, 3, 4, 1, 2, 0], [4, 1, 1, 2, 3, 0]]
+    n = len(schedules)
+    g = _venv(cuda, n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False)
+    c = g.cfg.c
+    evs = [H.random_events(100 + i) for i in range(n)]
+    vt = np.concatenate([H.oracle_tables(ev, c)[0] for ev in evs], axis=1)
+    st = np.concatenate([H.oracle_tables(ev, c)[1] for ev in evs], axis=1)
+    g.set_event_tables(vt, st)
+    g.reset()
+    orcs = [OraclePVDEREnv(model_type=model_type, solver="tight", events=ev, DISCRETE_REWARD=False) for ev in evs]
+    for o in orcs:
+        o.reset()
+    phases = g.cfg.phases
+    for step in range(6):
+        acts = torch.tensor([s[step] for s in schedules], dtype=torch.int32, device=cuda)
+        obs, rew, done, _ = g.step(acts)
+        y = g.y.cpu().numpy()
+        o64 = g.obs64.cpu().numpy()
+        for i, o in enumerate(orcs):
+            oo, orw, od, _ = o.step(schedules[i][step])
+            H.assert_state_close(y[:, i], H.oracle_delta_state(o), phases, what=f"{model_type} env{i} step{step}")
+            np.testing.assert_allclose(o64[i], oo, rtol=1e-5, atol=1e-8)
+            assert abs(float(rew[i]) - orw) <= 1e-5 * abs(orw) + 1e-10
+            assert bool(done[i]) == od
+
+
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_golden_fixture(cuda, model_type):
+    """Committed golden vectors (oracle tight path, tests/golden/make_golden.py)."""
+    import torch
+
+    gold = np.load(f"tests/golden/golden_{model_type}.npz")
+    acts, vt, st = gold["actions"], gold["vgrid_tab"], gold["sinsol_tab"]
+    n, nsteps = acts.shape
+    g = _venv(cuda, n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True)
+    g.set_event_tables(vt, st)
+    g.reset()
+    bad = 0
+    for s in range(nsteps):
+        obs, rew, done, _ = g.step(torch.as_tensor(acts[:, s].astype(np.int32), device=cuda))
+        np.testing.assert_allclose(g.obs64.cpu().numpy(), gold["obs"][:, s], rtol=1e-5, atol=1e-8)
+        bad += int((rew.cpu().numpy() != gold["reward"][:, s]).sum())
+        y = g.y.cpu().numpy()
+        for i in range(n):
+            H.assert_state_close(y[:, i], gold["state"][i, s], g.cfg.phases, what=f"golden env{i} step{s}")
+    assert bad == 0
+
+
+def test_events_bit_exact_65536(cuda):
+    n = 65536
+    g = _venv(cuda, n, model_type="model_1", events_spec=H.SAG_SPEC, seed=1234, env_offset=3)
+    g.reset()
+    v, s = g.generate_events()
+    c = g.cfg.c
+    vt, st = twin.event_tables_twin(1234, n, 3, 0, c.ev_count, True, True, c.ev_v_min, c.ev_v_max, c.ev_s_min, c.ev_s_max)
+    np.testing.assert_array_equal(v.cpu().numpy(), vt)
+    np.testing.assert_array_equal(s.cpu().numpy(), st)
+    assert vt.min() >= 0.90 and vt.max() <= 1.02 and st.min() >= 85.0 and st.max() <= 100.0
+    # the step kernel draws the same values on the fly: after 8 s of sim time the values in force are event #7
+    n_steps = 8 * 120 // c.n_sub_per_step
+    import torch
+    a = torch.zeros(n, dtype=torch.int32, device=cuda)
+    for _ in range(n_steps):
+        g.step(a)
+    np.testing.assert_array_equal(g.field("Vgrid").cpu().numpy(), vt[7])
+    np.testing.assert_array_equal(g.field("Sinsol").cpu().numpy(), st[7])
+
+
+@pytest.mark.parametrize("model_type,goal,discrete", [("model_1", "voltage_regulation", True),
+                                                      ("model_2", "voltage_regulation", True),
+                                                      ("model_2", "power_regulation", True),
+                                                      ("model_1", "Q_regulation", True),
+                                                      ("model_2", "voltage_regulation", False)])
+def test_rewards_bit_exact_given_state_65536(cuda, model_type, goal, discrete):
+    """Integer outputs are bit-exact: reward/obs recomputed by the numpy twin from the fp64 state the
+    kernel wrote must equal what the kernel emitted (same state => same integer)."""
+    import torch
+    from gym_pvder_b200 import _cabi
+
+    n = 65536
+    g = _venv(cuda, n, model_type=model_type, events_spec=H.SAG_SPEC, seed=7, goals_list=[goal], DISCRETE_REWARD=discrete)
+    g.reset()
+    for _ in range(6):
+        obs, rew, done, _ = g.step(g.sample_actions())
+    y = g.y.cpu().numpy()
+    o, r, _ = twin.outputs_twin(g.cfg.par, g.cfg.phases, y, g.field("Q_ref").cpu().numpy(), g.field("Vdc_ref").cpu().numpy(),
+                                g.field("Vgrid").cpu().numpy(), g.field("Sinsol").cpu().numpy(), g.k.cpu().numpy(),
+                                g.cfg.max_sim_time, _cabi.GOALS[goal], discrete)
+    np.testing.assert_array_equal(rew.cpu().numpy().astype(np.float64), r)
+    o64 = g.obs64.cpu().numpy()
+    cols = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10]          # everything but Ppv (exp is not correctly rounded)
+    np.testing.assert_array_equal(o64[:, cols], o[:, cols])
+    np.testing.assert_allclose(o64[:, 7], o[:, 7], rtol=1e-13)
+    np.testing.assert_array_equal(obs.cpu().numpy(), o64.astype(np.float32))
+    if discrete:
+        assert set(np.unique(r)).issubset({1.0, -1.0, -5.0}) and len(np.unique(r)) >= 2
+
+
+def test_full_episode_done_and_counters(cuda):
+    """reference test_time_steps (gym_PVDER/tests/test_gym_PVDER.py:87-111) for the vector env."""
+    import torch
+
+    n = 1000
+    g = _venv(cuda, n, model_type="model_1", n_sim_time_steps_per_env_step=10, max_sim_time=25.0)
+    g.reset()
+    steps = 0
+    done = torch.zeros(n, dtype=torch.bool, device=cuda)
+    while not bool(done.all()):
+        obs, rew, done, _ = g.step(g.sample_actions())
+        steps += 1
+        assert steps <= 150
+        assert bool((obs.abs() <= 10).all())
+    assert steps == 150
+    assert round(steps * 10 * (1 / 60), 6) == 25.0
+    assert bool((g.steps == 150).all()) and bool((g.k == 3000).all())
+    np.testing.assert_array_equal(g.obs64[:, 10].cpu().numpy(), np.ones(n))
+    hist = g.si[5:10, :n].sum(0)
+    assert bool((hist == 150).all())
+    # step after done: cached tuple, nothing advances (PVDER_env.py:145-152, 196)
+    before = g.sd.clone()
+    obs2, rew2, done2, _ = g.step(g.sample_actions())
+    assert torch.equal(before, g.sd) and bool(done2.all()) and bool((g.steps == 150).all())
+    assert torch.equal(rew2, rew)
+    st = g.stats().cpu().numpy()
+    assert st[10] == n and st[1] == 150 * n and st[2] == n and st[3] == 0
+    # reset starts a new episode with new events
+    g.reset()
+    assert bool((g.k == 0).all()) and bool((g.si[2, :n] == 1).all())
+
+
+def test_auto_reset_and_masked_reset(cuda):
+    import torch
+
+    n = 256
+    g = _venv(cuda, n, model_type="model_1", n_sim_time_steps_per_env_step=30, max_sim_time=1.0, auto_reset=True,
+              events_spec={"voltage": {"ENABLE": False}})
+    first = g.reset().clone()
+    a = torch.zeros(n, dtype=torch.int32, device=cuda)
+    obs, rew, done, _ = g.step(a)
+    assert not bool(done.any())
+    obs, rew, done, _ = g.step(a)
+    assert bool(done.all())                       # t = 1.0 s reached
+    assert torch.equal(obs, first)                # obs is the first observation of the next episode
+    assert bool((g.k == 0).all()) and bool((g.si[2, :n] == 1).all()) and bool((g.si[4, :n] == 0).all())
+    obs, rew, done, _ = g.step(a)
+    assert not bool(done.any()) and bool((g.steps == 1).all())
+    mask = torch.zeros(n, dtype=torch.uint8, device=cuda)
+    mask[::2] = 1
+    g.reset(mask)
+    assert bool((g.k[::2] == 0).all()) and bool((g.k[1::2] == 60).all())
+
+
+def test_bad_action_sets_status(cuda):
+    import torch
+    from gym_pvder_b200 import _cabi
+
+    g = _venv(cuda, 64, model_type="model_1")
+    g.reset()
+    a = torch.zeros(64, dtype=torch.int32, device=cuda)
+    a[5] = 7
+    a[6] = -1
+    g.step(a)
+    st = g.status.cpu().numpy()
+    assert st[5] == _cabi.STATUS_BAD_ACTION and st[6] == _cabi.STATUS_BAD_ACTION and (np.delete(st, [5, 6]) == 0).all()
+    assert int(g.steps[5]) == 0 and int(g.steps[0]) == 1
+    with pytest.raises(AssertionError):
+        g.check_status()
+
+
+def test_shard_and_permutation_invariance(cuda):
+    """Env i gives the same trajectory wherever it is computed (global-index RNG keys)."""
+    import torch
+
+    n = 512
+    kw = dict(model_type="model_1", events_spec=H.SAG_SPEC, seed=99)
+    whole = _venv(cuda, n, **kw)
+    lo = _venv(cuda, 200, env_offset=0, **kw)
+    hi = _venv(cuda, n - 200, env_offset=200, **kw)
+    for v in (whole, lo, hi):
+        v.reset()
+    for s in range(5):
+        a = whole.sample_actions().clone()
+        whole.step(a)
+        lo.step(a[:200].contiguous())
+        hi.step(a[200:].contiguous())
+    assert torch.equal(whole.sd[:, :200], lo.sd[:, :200]) and torch.equal(whole.sd[:, 200:n], hi.sd[:, :n - 200])
+    assert torch.equal(whole.obs[:200], lo.obs) and torch.equal(whole.obs[200:], hi.obs)
+    assert torch.equal(whole.reward_i[200:], hi.reward_i)
+
+
+def test_windup_mode_matches_oracle(cuda):
+    """Aggressive +Q policy drives |i_ref| over the limit: the anti-windup clamp (sampled on the
+    half-cycle grid in both implementations) must engage and trajectories must still agree."""
+    import torch
+
+    g = _venv(cuda, 1, model_type="model_1", events_spec={"voltage": {"ENABLE": False}}, DISCRETE_REWARD=False)
+    g.reset()
+    o = OraclePVDEREnv(model_type="model_1", solver="tight", events=EventTable(), DISCRETE_REWARD=False)
+    o.reset()
+    a = torch.ones(1, dtype=torch.int32, device=cuda)
+    for s in range(24):
+        g.step(a)
+        o.step(1)
+    assert int(g.si[10, 0]) > 0 and o.windup_substeps > 0
+    assert abs(int(g.si[10, 0]) - o.windup_substeps) <= 2
+    y = g.y.cpu().numpy()[:, 0]
+    np.testing.assert_allclose(y[:9], H.oracle_delta_state(o)[:9], rtol=2e-4, atol=1e-6)
+
+
+def test_host_handle_api_matches_device_api(cuda):
+    """pvder_env_step_host (numpy in / numpy out: the call a Gym user makes) == raw device API."""
+    import ctypes as C
+    import gym_pvder_b200 as G
+    from gym_pvder_b200 import _cabi
+
+    n = 1000
+    cfg = G.EnvConfig(model_type="model_2", events_spec=H.SAG_SPEC, seed=5)
+    lib = _cabi.load()
+    h = C.c_void_p()
+    _cabi.check(lib.pvder_env_create(C.byref(cfg.c), n, 0, C.byref(h)))
+    obs = np.zeros((n, 11), np.float32)
+    rew = np.zeros(n)
+    done = np.zeros(n, np.uint8)
+    _cabi.check(lib.pvder_env_reset_host(h, obs.ctypes.data, None))
+    g = _venv(cuda, n, config=cfg)
+    og = g.reset()
+    np.testing.assert_array_equal(og.cpu().numpy(), obs)
+    for s in range(4):
+        a = twin.sample_actions_twin(5, s, n, 0)
+        _cabi.check(lib.pvder_env_step_host(h, a.ctypes.data, obs.ctypes.data, None, rew.ctypes.data, done.ctypes.data))
+        o2, r2, d2, _ = g.step(a)
+        np.testing.assert_array_equal(o2.cpu().numpy(), obs)
+        np.testing.assert_array_equal(r2.cpu().numpy().astype(np.float64), rew)
+    ms, cnt = C.c_double(), C.c_int64()
+    _cabi.check(lib.pvder_env_kernel_ms(h, C.byref(ms), C.byref(cnt)))
+    assert cnt.value == 4 and ms.value > 0
+    _cabi.check(lib.pvder_env_destroy(h))
+
+
+def test_fp64_peak_microbenchmark(cuda):
+    import ctypes as C
+    from gym_pvder_b200 import _cabi
+
+    tf, ms = C.c_double(), C.c_double()
+    _cabi.check(_cabi.load().pvder_fp64_peak(2000, C.byref(tf), C.byref(ms)))
+    assert 5.0 < tf.value < 80.0, tf.value
