@@ -456,6 +456,7 @@ struct pvder_env {
   cudaEvent_t e0, e1;
   double ms_total;
   int64_t launches;
+  int fresh;   // no reset_host() yet: the first one starts episode 0
 };
 
 int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_offset, pvder_env** out) {
@@ -489,6 +490,7 @@ int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_of
   rc = launch_reset(&h->cfg, h->sd, h->si, h->ld, nullptr, h->d_vtab, h->d_stab, 1, nullptr, nullptr, h->n, h->off, h->stream);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
+  h->fresh = 1;
   *out = h;
   return PVDER_OK;
 }
@@ -517,8 +519,9 @@ int pvder_env_set_event_tables(pvder_env* h, const double* vgrid_tab, const doub
 
 int pvder_env_reset_host(pvder_env* h, float* obs_out, double* obs64_out) {
   if (!h) return PVDER_ERR_INVALID;
-  int rc = launch_reset(&h->cfg, h->sd, h->si, h->ld, nullptr, h->d_vtab, h->d_stab, 0, h->d_obs, h->d_obs64, h->n, h->off,
-                        h->stream);
+  int rc = launch_reset(&h->cfg, h->sd, h->si, h->ld, nullptr, h->d_vtab, h->d_stab, h->fresh, h->d_obs, h->d_obs64, h->n,
+                        h->off, h->stream);
+  h->fresh = 0;
   if (rc) return rc;
   if (obs_out) CK(cudaMemcpyAsync(obs_out, h->d_obs, sizeof(float) * PVDER_OBS_DIM * h->n, cudaMemcpyDeviceToHost, h->stream));
   if (obs64_out)

@@ -4,7 +4,7 @@
   (3) the bit-exact numpy twins for events / actions / rewards,
   (4) the plain-C++ build of the same per-env source (tests/host_emul) -- catches nvcc/ptxas
       issues and gives ~1e-12 agreement on whole trajectories.
-Tolerances: DESIGN.md "Tolerances" (rtol 1e-5 / atol 1e-8 on states and observations; separate
+Tolerances: DESIGN.md "Tolerances" (rtol 1e-5 / atol 1e-7 pu on states and observations; separate
 absolute bounds for the two PLL states)."""
 import numpy as np
 import pytest
@@ -79,7 +79,7 @@ def test_trajectory_vs_tight_oracle(cuda, model_type):
         for i, o in enumerate(orcs):
             oo, orw, od, _ = o.step(schedules[i][step])
             H.assert_state_close(y[:, i], H.oracle_delta_state(o), phases, what=f"{model_type} env{i} step{step}")
-            np.testing.assert_allclose(o64[i], oo, rtol=1e-5, atol=1e-8)
+            np.testing.assert_allclose(o64[i], oo, rtol=H.RTOL, atol=H.ATOL)
             assert abs(float(rew[i]) - orw) <= 1e-5 * abs(orw) + 1e-10
             assert bool(done[i]) == od
 
@@ -98,7 +98,7 @@ def test_golden_fixture(cuda, model_type):
     bad = 0
     for s in range(nsteps):
         obs, rew, done, _ = g.step(torch.as_tensor(acts[:, s].astype(np.int32), device=cuda))
-        np.testing.assert_allclose(g.obs64.cpu().numpy(), gold["obs"][:, s], rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(g.obs64.cpu().numpy(), gold["obs"][:, s], rtol=H.RTOL, atol=H.ATOL)
         bad += int((rew.cpu().numpy() != gold["reward"][:, s]).sum())
         y = g.y.cpu().numpy()
         for i in range(n):
@@ -153,7 +153,9 @@ def test_rewards_bit_exact_given_state_65536(cuda, model_type, goal, discrete):
     np.testing.assert_allclose(o64[:, 7], o[:, 7], rtol=1e-13)
     np.testing.assert_array_equal(obs.cpu().numpy(), o64.astype(np.float32))
     if discrete:
-        assert set(np.unique(r)).issubset({1.0, -1.0, -5.0}) and len(np.unique(r)) >= 2
+        assert set(np.unique(r)).issubset({1.0, -1.0, -5.0})
+        if goal == "voltage_regulation":
+            assert len(np.unique(r)) == 3      # sags to 0.90 pu exercise all three classes
 
 
 def test_full_episode_done_and_counters(cuda):
