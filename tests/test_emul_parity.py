@@ -1,0 +1,226 @@
+"""CPU tier: the *kernel source itself* (generated model code, symbolic LU, Rodas4, events,
+outputs) compiled as plain C++ (tests/host_emul) and checked against the oracle and the bit-exact
+twins.  This is what makes the CUDA path debuggable without a GPU; the GPU tier then asserts that
+the nvcc build of the same source agrees with this build to ~1e-11 (test_gpu_parity.py)."""
+import math
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import emul_harness as E
+import gym_pvder_b200 as G
+import helpers as H
+from gym_pvder_b200 import _cabi
+from oracle import twin
+from oracle.env_oracle import EventTable, OraclePVDEREnv
+from oracle.pvder_model import Inputs, PVDERModel, load_der_params
+
+DER = {"model_1": "10", "model_2": "50"}
+
+
+def _balanced_state(cfg, rng, pert=0.02):
+    """Random state near the operating point; three-phase stays a balanced set (the env never
+    leaves the balanced manifold)."""
+    P = cfg.phases
+    y = np.array(cfg.y0)
+    ia = complex(y[0], y[1]) * (1 + pert * rng.standard_normal()) * np.exp(1j * pert * rng.standard_normal())
+    xa = complex(y[2], y[3]) * (1 + pert * rng.standard_normal())
+    ua = 1e-5 * complex(rng.standard_normal(), rng.standard_normal())
+    rot = [1.0, np.exp(-2j * math.pi / 3), np.exp(2j * math.pi / 3)]
+    for k in range(P):
+        for j, z in enumerate((ia, xa, ua)):
+            y[6 * k + 2 * j], y[6 * k + 2 * j + 1] = (z * rot[k]).real, (z * rot[k]).imag
+    B = 6 * P
+    y[B] *= 1 + 0.01 * rng.standard_normal()
+    y[B + 1], y[B + 2] = ia.real * 1.01, ia.imag * 0.9
+    y[B + 3], y[B + 4] = 0.3 * rng.standard_normal(), 7.874 + 0.2 * rng.standard_normal()
+    return y
+
+
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_generated_rhs_and_lu_match_oracle(model_type):
+    cfg = G.EnvConfig(model_type=model_type)
+    p = load_der_params(DER[model_type])
+    m = PVDERModel(p)
+    rng = np.random.default_rng(1)
+    nofrz = (False,) * (4 * p.phases + 2)
+    for trial in range(5):
+        y = _balanced_state(cfg, rng)
+        inp = Inputs(Vgrid=0.95, Sinsol=90.0, Q_ref=0.03, Vdc_ref=p.Vdc_ref0 * 1.01, freeze=nofrz)
+        inp4 = [0.95 * cfg.par.vgs, 0.03, p.Vdc_ref0 * 1.01, cfg.par.np_iph100 * 0.9]
+        f_or = np.array(m.rhs(list(y), 0.0, inp))
+        f_or[-1] -= H.W                                     # autonomous form: d(delta)/dt = d(wte)/dt - w
+        f_em = E.rhs(cfg, y, inp4)
+        np.testing.assert_allclose(f_em, f_or, rtol=1e-12, atol=1e-9 * np.abs(f_or).max())
+        gh = 480.0
+        b = rng.standard_normal(len(y))
+        x = E.wsolve(cfg, y, inp4, gh, b)
+        if model_type == "model_1":       # same function => same Jacobian as the oracle's analytic one
+            Wm = np.eye(len(y)) * gh - m.jac(list(y), 0.0, inp)
+            np.testing.assert_allclose(x, np.linalg.solve(Wm, b), rtol=1e-9, atol=1e-15)
+        # the kernel's three-phase PLL input is the positive-sequence projection: equal to
+        # the oracle's abc->dq0 value on balanced sets, but with its own off-manifold derivative, so the
+        # symbolic LU is checked against finite differences of the generated RHS itself
+        Jfd = np.zeros((len(y), len(y)))
+        for j in range(len(y)):
+            hstep = 1e-6 * max(1.0, abs(y[j]))
+            yp, ym = y.copy(), y.copy()
+            yp[j] += hstep
+            ym[j] -= hstep
+            Jfd[:, j] = (E.rhs(cfg, yp, inp4) - E.rhs(cfg, ym, inp4)) / (2 * hstep)
+        xs = np.linalg.solve(np.eye(len(y)) * gh - Jfd, b)
+        np.testing.assert_allclose(x, xs, rtol=2e-5, atol=1e-9 * np.abs(xs).max())
+
+
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_freeze_mask_matches_oracle(model_type):
+    cfg = G.EnvConfig(model_type=model_type)
+    p = load_der_params(DER[model_type])
+    m = PVDERModel(p)
+    rng = np.random.default_rng(2)
+    seen = set()
+    for trial in range(200):
+        y = _balanced_state(cfg, rng, pert=0.3)
+        if trial % 3 == 0:
+            y[4] = 2e-3 * rng.standard_normal()             # |m| > 10: duty-cycle clamp
+        q = 0.3 * rng.standard_normal()
+        inp = Inputs(Vgrid=1.0, Q_ref=q, Vdc_ref=p.Vdc_ref0)
+        bits = E.freeze_bits(cfg, y, [cfg.par.vgs, q, p.Vdc_ref0, cfg.par.np_iph100])
+        mask = m.freeze_mask(list(y), inp)
+        assert bits == sum(1 << i for i, b in enumerate(mask) if b)
+        seen.add(bits != 0)
+    assert seen == {True, False}
+
+
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_trajectory_vs_tight_oracle(model_type):
+    ev = H.random_events(7)
+    orc = OraclePVDEREnv(model_type=model_type, solver="tight", events=ev, DISCRETE_REWARD=True)
+    em = E.EmulVecEnv(1, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True)
+    em.set_event_tables(*H.oracle_tables(ev, em.cfg.c))
+    np.testing.assert_allclose(em.reset()[0], orc.reset(), rtol=0, atol=1e-15)
+    for a in [3, 1, 0, 4, 2]:
+        oo, orw, od, _ = orc.step(a)
+        eo, erw, ed, _ = em.step([a])
+        np.testing.assert_allclose(eo[0], oo, rtol=H.RTOL, atol=H.ATOL)
+        H.assert_state_close(em.sd[:orc.model.n, 0], H.oracle_delta_state(orc), em.cfg.phases, what=f"{model_type} a={a}")
+        assert orw == erw[0] and od == ed[0]
+
+
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_golden_fixture(model_type):
+    gold = np.load(f"tests/golden/golden_{model_type}.npz")
+    acts = gold["actions"]
+    n, nsteps = acts.shape
+    em = E.EmulVecEnv(n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True)
+    em.set_event_tables(gold["vgrid_tab"], gold["sinsol_tab"])
+    em.reset()
+    for s in range(nsteps):
+        obs, rew, done, _ = em.step(acts[:, s])
+        np.testing.assert_allclose(obs, gold["obs"][:, s], rtol=H.RTOL, atol=H.ATOL)
+        np.testing.assert_array_equal(rew, gold["reward"][:, s])
+        for i in range(n):
+            H.assert_state_close(em.sd[:em.ns, i], gold["state"][i, s], em.cfg.phases, what=f"env{i} step{s}")
+
+
+def test_event_tables_bit_exact_vs_twin():
+    em = E.EmulVecEnv(4096, env_offset=11, model_type="model_1", events_spec=H.SAG_SPEC, seed=1234)
+    em.reset()
+    v, s = em.events()
+    c = em.cfg.c
+    vt, stw = twin.event_tables_twin(1234, 4096, 11, 0, c.ev_count, True, True, c.ev_v_min, c.ev_v_max, c.ev_s_min, c.ev_s_max)
+    np.testing.assert_array_equal(v, vt)
+    np.testing.assert_array_equal(s, stw)
+    frac_v = np.mean(np.diff(vt, axis=0) != 0)
+    assert 0.4 < frac_v < 0.6                        # random.choice between the two enabled kinds
+    only_v = E.EmulVecEnv(64, model_type="model_1", seed=5)
+    only_v.reset()
+    v2, s2 = only_v.events()
+    assert (s2 == 100.0).all() and v2.min() >= 0.98 and v2.max() <= 1.02 and len(np.unique(v2)) > 2000
+
+
+@pytest.mark.parametrize("model_type,goal,discrete", [("model_1", "voltage_regulation", True),
+                                                      ("model_2", "power_regulation", True),
+                                                      ("model_2", "Q_regulation", False)])
+def test_outputs_bit_exact_vs_twin(model_type, goal, discrete):
+    n = 512
+    em = E.EmulVecEnv(n, model_type=model_type, events_spec=H.SAG_SPEC, seed=3, goals_list=[goal], DISCRETE_REWARD=discrete)
+    em.reset()
+    for s in range(5):
+        obs, rew, done, _ = em.step(twin.sample_actions_twin(3, s, n, 0))
+    ix = _cabi.sd_index(em.ns)
+    o, r, _ = twin.outputs_twin(em.cfg.par, em.cfg.phases, em.sd[:em.ns], em.sd[ix["Q_ref"]], em.sd[ix["Vdc_ref"]],
+                                em.sd[ix["Vgrid"]], em.sd[ix["Sinsol"]], em.si[_cabi.SI_K], em.cfg.max_sim_time,
+                                _cabi.GOALS[goal], discrete)
+    np.testing.assert_array_equal(rew.astype(np.float64), r)
+    cols = [0, 1, 2, 3, 4, 5, 6, 8, 9, 10]               # all but Ppv: exp() is not correctly rounded everywhere
+    np.testing.assert_array_equal(obs[:, cols], o[:, cols])
+    np.testing.assert_allclose(obs[:, 7], o[:, 7], rtol=1e-14)
+    assert (np.abs(obs) <= 10).all()                      # Box(-10, 10), PVDER_env.py:51
+
+
+def test_episode_counters_done_and_noop_after_done():
+    """reference test_time_steps (tests:87-111) + step-after-done (PVDER_env.py:145-152)."""
+    n = 8
+    em = E.EmulVecEnv(n, model_type="model_1", n_sim_time_steps_per_env_step=10, max_sim_time=2.0)
+    em.reset()
+    steps = 0
+    done = np.zeros(n, bool)
+    while not done.all():
+        obs, rew, done, _ = em.step(np.full(n, steps % 5))
+        steps += 1
+    assert steps == 12 and round(steps * 10 * (1 / 60), 6) == 2.0
+    assert (em.si[_cabi.SI_STEPS] == 12).all() and (em.si[_cabi.SI_K] == 240).all()
+    assert (obs[:, 10] == 1.0).all()
+    sd0, si0 = em.sd.copy(), em.si.copy()
+    obs2, rew2, done2, _ = em.step(np.ones(n))
+    assert done2.all() and (rew2 == rew).all() and (obs2 == obs).all()
+    assert (em.sd == sd0).all() and (em.si == si0).all()
+    assert (em.si[_cabi.SI_HIST:_cabi.SI_HIST + 5].sum(0) == 12).all()
+    bad = E.EmulVecEnv(2, model_type="model_1")
+    bad.reset()
+    bad.step([7, 0])
+    assert list(bad.si[_cabi.SI_STATUS]) == [_cabi.STATUS_BAD_ACTION, 0] and list(bad.si[_cabi.SI_STEPS]) == [0, 1]
+
+
+def test_auto_reset_and_shard_invariance():
+    kw = dict(model_type="model_1", events_spec=H.SAG_SPEC, seed=9, n_sim_time_steps_per_env_step=30, max_sim_time=1.5)
+    whole = E.EmulVecEnv(12, auto_reset=True, **kw)
+    lo = E.EmulVecEnv(5, env_offset=0, auto_reset=True, **kw)
+    hi = E.EmulVecEnv(7, env_offset=5, auto_reset=True, **kw)
+    first = whole.reset()
+    lo.reset()
+    hi.reset()
+    for s in range(8):
+        a = twin.sample_actions_twin(9, s, 12, 0)
+        obs, rew, done, _ = whole.step(a)
+        lo.step(a[:5])
+        hi.step(a[5:])
+        assert done.all() == (s % 3 == 2)
+        if s % 3 == 2:
+            assert (obs[:, 10] == 0).all() and (whole.si[_cabi.SI_K] == 0).all()
+            np.testing.assert_array_equal(obs[:, [0, 1, 6, 8, 9]], first[:, [0, 1, 6, 8, 9]])
+    assert (whole.si[_cabi.SI_EPISODE] == 2).all()
+    np.testing.assert_array_equal(whole.sd[:, :5], lo.sd)
+    np.testing.assert_array_equal(whole.sd[:, 5:], hi.sd)
+    np.testing.assert_array_equal(whole.si[:, 5:], hi.si)
+    # events differ between episodes and between envs (keyed by global index and episode)
+    assert len(np.unique(whole.sd[_cabi.sd_index(11)["Vgrid"]])) > 1
+
+
+@settings(max_examples=15, deadline=None)
+@given(actions=st.lists(st.integers(0, 4), min_size=1, max_size=6), n_sim=st.sampled_from([1, 7, 15]))
+def test_property_reference_increments_and_counters(actions, n_sim):
+    """Q_ref/Vdc_ref are changed only by actions (PVDER_env.py:211-229) and k advances 2n per step."""
+    em = E.EmulVecEnv(1, model_type="model_1", n_sim_time_steps_per_env_step=n_sim, events_spec={"voltage": {"ENABLE": False}})
+    em.reset()
+    q, v = 0.0, 1.5
+    dq, dv = 25.0 * n_sim / 50e3, 0.02 * n_sim / 500.0
+    for a in actions:
+        obs, rew, done, _ = em.step([a])
+        q = q + (dq if a == 1 else -dq if a == 2 else 0.0)
+        v = v + (dv if a == 3 else -dv if a == 4 else 0.0)
+        assert obs[0, 9] == q and obs[0, 8] == v
+        assert np.isfinite(obs).all() and (np.abs(obs) <= 10).all()
+    assert em.si[_cabi.SI_K, 0] == 2 * n_sim * len(actions) and em.si[_cabi.SI_STATUS, 0] == 0

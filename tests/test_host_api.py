@@ -1,0 +1,159 @@
+"""CPU tier: host logic of the drop-in package and the C-ABI library surface (no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import gym_pvder_b200 as G
+from gym_pvder_b200 import _cabi, config as cfgmod
+from gym_pvder_b200.sharding import shard_bounds
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _cabi.load()
+    header = open(os.path.join(ROOT, "include", "pvder_b200.h")).read()
+    declared = set(re.findall(r"\b(pvder_[a-z0-9_]+)\s*\(", header)) - {"pvder_env"}
+    assert declared == set(_cabi.SIGNATURES), declared ^ set(_cabi.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pvder_abi_version() == 1
+    assert lib.pvder_sd_fields(1) == 17 and lib.pvder_sd_fields(3) == 29 and lib.pvder_si_fields() == _cabi.SI_FIELDS
+    assert lib.pvder_error_string(-1) == b"invalid argument"
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirror and C struct agree (size is checked through a host-only call using the struct)."""
+    cfg = G.EnvConfig(model_type="model_1")
+    assert C.sizeof(_cabi.Params) == 29 * 8
+    assert C.sizeof(_cabi.EnvConfigC) == 29 * 8 + 13 * 4 + 4 + 11 * 8 + 23 * 8   # 13 ints padded to 8-byte alignment
+    assert list(cfg.c.y0)[:11] == cfg.y0 and cfg.c.y0[10] == 6.28
+
+
+def test_missing_extension_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", "/nonexistent/libpvder_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _cabi.load()
+
+
+def test_vec_env_refuses_to_run_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        G.PVDERVecEnv(4)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gym-solarpvder-environment_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, re.M), f
+                assert "host_emul" not in txt or f == "pvder_env_step.cuh" or f == "pvder_common.cuh", f
+
+
+def test_make_and_registration():
+    """reference gym_PVDER/__init__.py:3-10, tests:11-14."""
+    env = G.make("PVDER-v0")
+    assert env.spec.id == "PVDER-v0" and env.spec.max_episode_steps == 500
+    assert isinstance(env.unwrapped, G.PVDER)
+    assert env.n_sim_time_steps_per_env_step == 15 and env.max_sim_time == 40.0
+    assert env.DISCRETE_REWARD is True and env.goals_list == ["voltage_regulation"]
+    assert env.action_space == G.Discrete(5) and env.action_space.n == 5
+    assert env.observation_space.shape == (11,) and env.observation_space.dtype == np.float32
+    assert env.metadata == {"render.modes": ["vector", "human"]}
+    assert len(env.observed_quantities) == 11
+    with pytest.raises(KeyError):
+        G.make("PVDER-v1")
+    with pytest.raises(AssertionError):
+        env.step(0)                      # TimeLimit: step before reset
+
+
+def test_kwargs_validation():
+    """PVDER_env.py:561-620."""
+    assert cfgmod.validate_n_sim(None) == 60 and cfgmod.validate_n_sim(0) == 1 and cfgmod.validate_n_sim(7) == 7
+    with pytest.raises(ValueError):
+        cfgmod.validate_n_sim(1.5)
+    assert cfgmod.validate_max_sim_time(None, 15, 500) == pytest.approx(125.0)
+    assert cfgmod.validate_max_sim_time(0.5, 15, 500) == 1.0
+    assert cfgmod.validate_max_sim_time(1e9, 15, 500) == pytest.approx(125.0)
+    with pytest.raises(ValueError):
+        cfgmod.validate_max_sim_time("40", 15, 500)
+    assert cfgmod.validate_discrete(None) is True
+    with pytest.raises(ValueError):
+        cfgmod.validate_discrete(1)
+    with pytest.raises(ValueError):
+        cfgmod.validate_goals(["voltage"])
+    with pytest.raises(ValueError):
+        cfgmod.validate_goals([])
+    with pytest.raises(ValueError):
+        G.make("PVDER-v0", DISCRETE_REWARD="yes")
+    with pytest.raises(ValueError):
+        G.make("PVDER-v0", goals_list=["fly"])
+    env = G.make("PVDER-v0", n_sim_time_steps_per_env_step=10, max_sim_time=25.0)
+    u = env.unwrapped
+    assert u._delQref == 250 and u._delVdcref == pytest.approx(0.2) and u._sim_time_per_env_step == pytest.approx(10 / 60)
+
+
+def test_env_config_packing():
+    c = G.EnvConfig(model_type="model_1", n_sim_time_steps_per_env_step=10, max_sim_time=25.0)
+    assert c.c.phases == 1 and c.c.n_sub_per_step == 20 and c.c.done_substep == 3000 and c.episode_steps == 150
+    assert (c.c.ev_start_k, c.c.ev_step_k, c.c.ev_count) == (120, 120, 38)          # arange(1, 39, 1)
+    assert c.c.ev_voltage_enable == 1 and c.c.ev_insol_enable == 0 and c.c.event_mode == 1
+    assert c.c.delQ_pu == 250 / 50e3 and c.c.delVdc_pu == pytest.approx(0.2 / 500)
+    assert c.c.goal == 0 and c.c.discrete_reward == 1
+    off = G.EnvConfig(events_spec={"voltage": {"ENABLE": False}})
+    assert off.c.event_mode == 0 and off.c.ev_count == 0 and off.c.phases == 3 and off.n_state == 23
+    with pytest.raises(ValueError):
+        G.EnvConfig(events_spec={"voltage": {"t_events_start": 1.001}})
+    with pytest.raises(ValueError):
+        G.EnvConfig(events_spec={"wind": {"min": 1}})
+    with pytest.raises(ValueError):
+        G.EnvConfig(model_type="model_9")
+
+
+def test_steady_state_through_the_c_abi():
+    """pvder_steady_state (host-only) against the oracle's independent Newton solve."""
+    from oracle.pvder_model import PVDERModel, load_der_params
+
+    for mt, der in (("model_1", "10"), ("model_2", "50")):
+        cfg = G.EnvConfig(model_type=mt)
+        y0, ma0, ia0 = PVDERModel(load_der_params(der)).steady_state()
+        np.testing.assert_allclose(cfg.y0, y0, rtol=0, atol=1e-14)
+        assert abs(cfg.ma0 - ma0) < 1e-14 and abs(cfg.ia0 - ia0) < 1e-14
+
+
+def test_spaces():
+    d = G.Discrete(5, seed=0)
+    assert all(0 <= d.sample() < 5 for _ in range(50)) and d.contains(4) and not d.contains(5) and not d.contains(1.0)
+    assert 3 in d and np.int64(2) in d and True not in d
+    b = G.Box(-10, 10, (11,), np.float32)
+    assert b.contains(np.zeros(11, np.float32)) and not b.contains(np.full(11, 11.0, np.float32))
+    assert not b.contains(np.zeros(10, np.float32)) and b.sample().dtype == np.float32
+
+
+def test_update_env_events_is_per_instance():
+    """the reference mutates a class-level dict; here the spec is per instance."""
+    a, b = G.make("PVDER-v0"), G.make("PVDER-v0")
+    a.update_env_events([{"voltage": {"min": 0.95}}])
+    assert a.env_events_spec["voltage"]["min"] == 0.95 and b.env_events_spec["voltage"]["min"] == 0.98
+    with pytest.raises(AssertionError):
+        a.update_env_events({"voltage": {"min": 0.9}})
+    with pytest.raises(ValueError):
+        a.update_env_events([{"voltage": {"foo": 1}}])
+
+
+def test_shard_bounds():
+    for total, world in ((1 << 20, 8), (1000, 3), (5, 8)):
+        spans = [shard_bounds(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == total
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
