@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libpvder_b200.so")
+LIB_PATH = os.environ.get("PVDER_B200_LIB") or os.path.join(CSRC, "libpvder_b200.so")   # env override: kernel-variant sweeps
 SOURCES = ["pvder_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-diag-suppress", "177", "-shared", "-Xcompiler", "-fPIC"]

@@ -12,11 +12,13 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define PVDER_DEV __device__ __forceinline__
+#define PVDER_NOINLINE __device__ __noinline__
 #define PVDER_HD __host__ __device__ __forceinline__
 #else
 // Plain C++ build of the per-env logic (tests/host_emul only): round-to-nearest intrinsics map
 // to the plain IEEE operations (build with -ffp-contract=off).
 #define PVDER_DEV inline
+#define PVDER_NOINLINE static
 #define PVDER_HD inline
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
@@ -37,7 +39,23 @@ struct Inputs {
   double np_iph;   // Np * Iph(Sinsol)  (A)
 };
 
-// PV array power (pu) and its slope wrt Vdc.
+// Transcendental side-inputs of the model at one state: sin/cos of the PLL angle delta, the PV
+// array power and slope (which need exp(kappa*Vdc)) and 1/Vdc.  E = exp(kappa*Vdc) is kept so the
+// record can be advanced incrementally (pvder_env_step.cuh: aux_advance).
+struct Aux {
+  double sn, cs, Ppv, dPpv, inv_Vdc, E;
+};
+
+// PV array power (pu) and its slope wrt Vdc from E = exp(kappa*Vdc).
+PVDER_DEV void ppv_from_exp(const Params& par, const Inputs& in, double Vdc, double e, double& P, double& dP) {
+  const double Ipv = in.np_iph - par.np_irs * (e - 1.0);
+  const double Pr = Ipv * Vdc * par.pv_scale;
+  const double dPr = par.pv_scale * (Ipv - Vdc * (par.np_irs * par.kappa * e));
+  const bool pos = Pr > 0.0;
+  P = pos ? Pr : 0.0;
+  dP = pos ? dPr : 0.0;
+}
+
 PVDER_DEV void ppv_eval(const Params& par, const Inputs& in, double Vdc, double& P,
                                          double& dP) {
   const double e = exp(par.kappa * Vdc);

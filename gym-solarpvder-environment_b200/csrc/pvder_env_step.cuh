@@ -11,87 +11,180 @@
 
 namespace pvder {
 
-// ---- Rodas4 (Hairer & Wanner, Solving ODEs II, sec. IV.10), form  (I/(h g) - J) K_i = f(Y_i) + sum c_ij/h K_j
+// ---- Rodas4 (Hairer & Wanner, Solving ODEs II, sec. IV.10) in the form
+//        (I/(h g) - J) K_i = f(Y_i) + sum_j (c_ij/h) K_j ,  Y_i = y + sum_j a_ij K_j ,  y+ = Y_6 + K_6
+// L-stable, stiffly accurate, order 4, one LU per step.  All 8 order conditions were checked
+// numerically for these digits (tools/integrator_study.py).
 constexpr double RG = 0.25;
-constexpr double A21 = 0.1544000000000000e+01;
-constexpr double A31 = 0.9466785280815826e+00, A32 = 0.2557011698983284e+00;
-constexpr double A41 = 0.3314825187068521e+01, A42 = 0.2896124015972201e+01, A43 = 0.9986419139977817e+00;
-constexpr double A51 = 0.1221224509226641e+01, A52 = 0.6019134481288629e+01, A53 = 0.1253708332932087e+02,
-                 A54 = -0.6878860361058950e+00;
-constexpr double C21 = -0.5668800000000000e+01;
-constexpr double C31 = -0.2430093356833875e+01, C32 = -0.2063599157091915e+00;
-constexpr double C41 = -0.1073529058151375e+00, C42 = -0.9594562251023355e+01, C43 = -0.2047028614809616e+02;
-constexpr double C51 = 0.7496443313967647e+01, C52 = -0.1024680431464352e+02, C53 = -0.3399990352819905e+02,
-                 C54 = 0.1170890893206160e+02;
-constexpr double C61 = 0.8083246795921522e+01, C62 = -0.7981132988064893e+01, C63 = -0.3152159432874371e+02,
-                 C64 = 0.1631930543123136e+02, C65 = -0.6058818238834054e+01;
+struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant bank
+  double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54;
+  double c21, c31, c32, c41, c42, c43, c51, c52, c53, c54, c61, c62, c63, c64, c65;
+  double ghinv;     // 1/(h*gamma)
+};
 
-template <class M, bool FRZ>
-PVDER_DEV void rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& in,
-                                            unsigned frz, double hinv) {
+inline RodasTab make_rodas_tab(double hinv) {
+  RodasTab t;
+  t.a21 = 0.1544000000000000e+01;
+  t.a31 = 0.9466785280815826e+00; t.a32 = 0.2557011698983284e+00;
+  t.a41 = 0.3314825187068521e+01; t.a42 = 0.2896124015972201e+01; t.a43 = 0.9986419139977817e+00;
+  t.a51 = 0.1221224509226641e+01; t.a52 = 0.6019134481288629e+01; t.a53 = 0.1253708332932087e+02;
+  t.a54 = -0.6878860361058950e+00;
+  t.c21 = -0.5668800000000000e+01 * hinv;
+  t.c31 = -0.2430093356833875e+01 * hinv; t.c32 = -0.2063599157091915e+00 * hinv;
+  t.c41 = -0.1073529058151375e+00 * hinv; t.c42 = -0.9594562251023355e+01 * hinv; t.c43 = -0.2047028614809616e+02 * hinv;
+  t.c51 = 0.7496443313967647e+01 * hinv; t.c52 = -0.1024680431464352e+02 * hinv; t.c53 = -0.3399990352819905e+02 * hinv;
+  t.c54 = 0.1170890893206160e+02 * hinv;
+  t.c61 = 0.8083246795921522e+01 * hinv; t.c62 = -0.7981132988064893e+01 * hinv; t.c63 = -0.3152159432874371e+02 * hinv;
+  t.c64 = 0.1631930543123136e+02 * hinv; t.c65 = -0.6058818238834054e+01 * hinv;
+  t.ghinv = hinv * (1.0 / RG);
+  return t;
+}
+
+// Aux record at state y with full-accuracy library functions (once per env step, and whenever a
+// stage leaves the incremental range).
+template <class M>
+PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[M::NS], Aux& a) {
+  sincos(y[M::IDX_DL], &a.sn, &a.cs);
+  a.E = exp(par.kappa * y[M::IDX_VDC]);
+  a.inv_Vdc = 1.0 / y[M::IDX_VDC];
+  ppv_from_exp(par, in, y[M::IDX_VDC], a.E, a.Ppv, a.dPpv);
+}
+
+// Aux record at a state Y close to the base state (angle dl0, DC voltage V0, record b):
+//   sin/cos(dl0 + d) by rotating (sn0, cs0) through d,  exp(kappa (V0 + dv)) = E0 * exp(kappa dv),
+//   1/V by three Newton steps from 1/V0 -- short polynomials (|d|, |kappa dv| < 2^-4: truncation
+//   below 3e-19) instead of 3 library calls per Rodas stage.  Outside that range (PLL pull-in right
+//   after reset) the step is redone by the EXACT instantiation, which is kept out of line so the
+//   hot loop stays small.
+template <class M, bool EXACT>
+PVDER_DEV void aux_advance(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0,
+                           const double (&Y)[M::NS], Aux& a, bool& out_of_range) {
+  if (EXACT) {
+    aux_exact<M>(par, in, Y, a);
+    return;
+  }
+  const double d = Y[M::IDX_DL] - dl0;
+  const double V = Y[M::IDX_VDC];
+  const double dv = V - V0;
+  const double x = par.kappa * dv;
+  // outside the polynomial range the caller discards this step and redoes it with EXACT = true
+  out_of_range |= !(fabs(d) < 0.0625 && fabs(x) < 0.0625 && fabs(dv) < 0.0625 * V0);
+  {
+    const double d2 = d * d;
+    double ps = fma(d2, 1.0 / 362880.0, -1.0 / 5040.0);
+    ps = fma(ps, d2, 1.0 / 120.0);
+    ps = fma(ps, d2, -1.0 / 6.0);
+    const double sd = fma(ps * d2, d, d);                      // sin d
+    double pc = fma(d2, -1.0 / 3628800.0, 1.0 / 40320.0);
+    pc = fma(pc, d2, -1.0 / 720.0);
+    pc = fma(pc, d2, 1.0 / 24.0);
+    pc = fma(pc, d2, -0.5);
+    const double cdm1 = pc * d2;                               // cos d - 1
+    a.sn = fma(b.sn, cdm1, fma(b.cs, sd, b.sn));
+    a.cs = fma(b.cs, cdm1, fma(-b.sn, sd, b.cs));
+    double pe = fma(x, 1.0 / 362880.0, 1.0 / 40320.0);
+    pe = fma(pe, x, 1.0 / 5040.0);
+    pe = fma(pe, x, 1.0 / 720.0);
+    pe = fma(pe, x, 1.0 / 120.0);
+    pe = fma(pe, x, 1.0 / 24.0);
+    pe = fma(pe, x, 1.0 / 6.0);
+    pe = fma(pe, x, 0.5);
+    pe = fma(pe, x, 1.0);
+    a.E = fma(b.E * pe, x, b.E);                               // E0 * exp(x)
+    double r = b.inv_Vdc;
+    r = fma(r, fma(-V, r, 1.0), r);
+    r = fma(r, fma(-V, r, 1.0), r);
+    r = fma(r, fma(-V, r, 1.0), r);
+    a.inv_Vdc = r;
+    ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
+  }
+}
+
+// One half-cycle Rodas4 step.  `base` is the Aux record at y on entry and at the new y on exit.
+// Returns false (y, base untouched) when EXACT == false and a stage left the incremental range.
+template <class M, bool FRZ, bool EXACT>
+PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
+                           unsigned frz, Aux& base) {
   constexpr int NS = M::NS;
+  bool oor = false;
+  const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
+  ppv_from_exp(par, in, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
   typename M::LU lu;
-  M::template factor<FRZ>(y, par, in, frz, hinv * (1.0 / RG), lu);
+  M::template factor<FRZ>(y, par, in, base, frz, tab.ghinv, lu);
   double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], Y[NS];
+  Aux ax;
   // stage 1
-  M::template rhs<FRZ>(y, par, in, frz, K1);
+  M::template rhs<FRZ>(y, par, in, base, frz, K1);
   M::solve(lu, K1);
   // stage 2
 #pragma unroll
-  for (int i = 0; i < NS; ++i) Y[i] = fma(A21, K1[i], y[i]);
-  M::template rhs<FRZ>(Y, par, in, frz, K2);
-  {
-    const double c1 = C21 * hinv;
+  for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a21, K1[i], y[i]);
+  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  M::template rhs<FRZ>(Y, par, in, ax, frz, K2);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) K2[i] = fma(c1, K1[i], K2[i]);
-  }
+  for (int i = 0; i < NS; ++i) K2[i] = fma(tab.c21, K1[i], K2[i]);
   M::solve(lu, K2);
   // stage 3
 #pragma unroll
-  for (int i = 0; i < NS; ++i) Y[i] = fma(A32, K2[i], fma(A31, K1[i], y[i]));
-  M::template rhs<FRZ>(Y, par, in, frz, K3);
-  {
-    const double c1 = C31 * hinv, c2 = C32 * hinv;
+  for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a32, K2[i], fma(tab.a31, K1[i], y[i]));
+  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  M::template rhs<FRZ>(Y, par, in, ax, frz, K3);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) K3[i] = fma(c2, K2[i], fma(c1, K1[i], K3[i]));
-  }
+  for (int i = 0; i < NS; ++i) K3[i] = fma(tab.c32, K2[i], fma(tab.c31, K1[i], K3[i]));
   M::solve(lu, K3);
   // stage 4
 #pragma unroll
-  for (int i = 0; i < NS; ++i) Y[i] = fma(A43, K3[i], fma(A42, K2[i], fma(A41, K1[i], y[i])));
-  M::template rhs<FRZ>(Y, par, in, frz, K4);
-  {
-    const double c1 = C41 * hinv, c2 = C42 * hinv, c3 = C43 * hinv;
+  for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a43, K3[i], fma(tab.a42, K2[i], fma(tab.a41, K1[i], y[i])));
+  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  M::template rhs<FRZ>(Y, par, in, ax, frz, K4);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) K4[i] = fma(c3, K3[i], fma(c2, K2[i], fma(c1, K1[i], K4[i])));
-  }
+  for (int i = 0; i < NS; ++i) K4[i] = fma(tab.c43, K3[i], fma(tab.c42, K2[i], fma(tab.c41, K1[i], K4[i])));
   M::solve(lu, K4);
   // stage 5
 #pragma unroll
   for (int i = 0; i < NS; ++i)
-    Y[i] = fma(A54, K4[i], fma(A53, K3[i], fma(A52, K2[i], fma(A51, K1[i], y[i]))));
-  M::template rhs<FRZ>(Y, par, in, frz, K5);
-  {
-    const double c1 = C51 * hinv, c2 = C52 * hinv, c3 = C53 * hinv, c4 = C54 * hinv;
+    Y[i] = fma(tab.a54, K4[i], fma(tab.a53, K3[i], fma(tab.a52, K2[i], fma(tab.a51, K1[i], y[i]))));
+  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  M::template rhs<FRZ>(Y, par, in, ax, frz, K5);
 #pragma unroll
-    for (int i = 0; i < NS; ++i)
-      K5[i] = fma(c4, K4[i], fma(c3, K3[i], fma(c2, K2[i], fma(c1, K1[i], K5[i]))));
-  }
+  for (int i = 0; i < NS; ++i)
+    K5[i] = fma(tab.c54, K4[i], fma(tab.c53, K3[i], fma(tab.c52, K2[i], fma(tab.c51, K1[i], K5[i]))));
   M::solve(lu, K5);
-  // stage 6 (Y6 = Y5 + K5; y_new = Y6 + K6: stiffly accurate)
+  // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] += K5[i];
+  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
   double K6[NS];
-  M::template rhs<FRZ>(Y, par, in, frz, K6);
-  {
-    const double c1 = C61 * hinv, c2 = C62 * hinv, c3 = C63 * hinv, c4 = C64 * hinv, c5 = C65 * hinv;
+  M::template rhs<FRZ>(Y, par, in, ax, frz, K6);
 #pragma unroll
-    for (int i = 0; i < NS; ++i)
-      K6[i] = fma(c5, K5[i], fma(c4, K4[i], fma(c3, K3[i], fma(c2, K2[i], fma(c1, K1[i], K6[i])))));
-  }
+  for (int i = 0; i < NS; ++i)
+    K6[i] = fma(tab.c65, K5[i], fma(tab.c64, K4[i], fma(tab.c63, K3[i], fma(tab.c62, K2[i], fma(tab.c61, K1[i], K6[i])))));
   M::solve(lu, K6);
 #pragma unroll
-  for (int i = 0; i < NS; ++i) y[i] = Y[i] + K6[i];
+  for (int i = 0; i < NS; ++i) Y[i] += K6[i];
+  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  if (oor) return false;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) y[i] = Y[i];
+  base = ax;
+  return true;
+}
+
+// Out-of-line slow paths: library transcendentals at every stage (and the anti-windup variant).
+template <class M, bool FRZ>
+PVDER_NOINLINE void rodas4_exact(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
+                                 unsigned frz, Aux& base) {
+  rodas4_core<M, FRZ, true>(y, par, in, tab, frz, base);
+}
+
+template <class M>
+PVDER_DEV void rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
+                           unsigned frz, Aux& base) {
+  if (frz) {
+    rodas4_exact<M, true>(y, par, in, tab, frz, base);
+  } else if (!rodas4_core<M, false, false>(y, par, in, tab, 0u, base)) {
+    rodas4_exact<M, false>(y, par, in, tab, 0u, base);
+  }
 }
 
 // pvder's clamping test np.sign(a) == np.sign(b)
@@ -255,7 +348,7 @@ PVDER_DEV void init_env(const pvder_env_config& cfg, double (&y)[M::NS], double&
 // Returns true when the env advanced (state must be written back).  hist_inc: action whose
 // histogram counter must be incremented (-1: none); hist_clear: auto-reset happened.
 template <class M>
-PVDER_DEV bool advance_env(const pvder_env_config& cfg, EnvRegs<M>& r, int act, bool active, const double* vtab,
+PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, EnvRegs<M>& r, int act, bool active, const double* vtab,
                            const double* stab, int64_t ld, int64_t e, uint32_t env_glob, Outputs& o, int& done_out,
                            int& hist_inc, bool& hist_clear) {
   constexpr int NS = M::NS;
@@ -276,17 +369,18 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, EnvRegs<M>& r, int act, 
     r.Vdcref = __dadd_rn(r.Vdcref, dV);                      // PVDER_env.py:229
     int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
     int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
-    const double hinv = cfg.substeps_per_sec * (double)cfg.micro;
+    Aux base;
+    {
+      Inputs in0{__dmul_rn(r.Vgrid, par.vgs), r.Qref, r.Vdcref,
+                 __dmul_rn(par.np_iph100, __ddiv_rn(r.Sinsol, 100.0))};
+      aux_exact<M>(par, in0, r.y, base);      // library sincos/exp/div once per env step, then incremental
+    }
     for (int s = 0; s < cfg.n_sub_per_step; ++s) {
       Inputs in{__dmul_rn(r.Vgrid, par.vgs), r.Qref, r.Vdcref,
                 __dmul_rn(par.np_iph100, __ddiv_rn(r.Sinsol, 100.0))};
       const unsigned frz = freeze_bits<M>(r.y, par, in);
-      if (frz) {
-        r.windup += 1;
-        for (int m = 0; m < cfg.micro; ++m) rodas4_step<M, true>(r.y, par, in, frz, hinv);
-      } else {
-        for (int m = 0; m < cfg.micro; ++m) rodas4_step<M, false>(r.y, par, in, 0u, hinv);
-      }
+      if (frz) r.windup += 1;
+      for (int m = 0; m < cfg.micro; ++m) rodas4_step<M>(r.y, par, in, tab, frz, base);
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);

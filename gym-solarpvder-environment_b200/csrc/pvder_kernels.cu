@@ -27,7 +27,13 @@
 
 namespace pvder {
 
-constexpr int BLOCK = 128;
+#ifndef PVDER_BLOCK
+#define PVDER_BLOCK 128
+#endif
+#ifndef PVDER_MINBLOCKS
+#define PVDER_MINBLOCKS 2
+#endif
+constexpr int BLOCK = PVDER_BLOCK;
 
 struct StepArgs {
   double* sd;
@@ -59,7 +65,8 @@ __device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const O
 }
 
 template <class M>
-__global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ pvder_env_config cfg, const StepArgs a) {
+__global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS) step_kernel(const __grid_constant__ pvder_env_config cfg,
+                                                     const __grid_constant__ RodasTab tab, const StepArgs a) {
   constexpr int NS = M::NS;
   __shared__ float stage[BLOCK * PVDER_OBS_DIM];
   const int64_t block_first = (int64_t)blockIdx.x * BLOCK;
@@ -87,7 +94,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const __grid_constant__ pvd
   Outputs o;
   int done_out, hist_inc;
   bool hist_clear;
-  const bool run = advance_env<M>(cfg, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
+  const bool run = advance_env<M>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
                                   done_out, hist_inc, hist_clear);
 
   if (active) {
@@ -368,8 +375,9 @@ int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld,
   StepArgs a{sd, si, ld, action, vgrid_tab, sinsol_tab, obs_f32, obs_f64, reward_f64, reward_i32, done, n_envs, env_offset};
   const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
-  if (cfg->phases == 1) step_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, a);
-  else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, a);
+  const RodasTab tab = make_rodas_tab(cfg->substeps_per_sec * (double)cfg->micro);
+  if (cfg->phases == 1) step_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, tab, a);
+  else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, tab, a);
   CK(cudaGetLastError());
   return PVDER_OK;
 }

@@ -16,6 +16,7 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
                      const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
                      uint8_t* done, int64_t n, int64_t off) {
   constexpr int NS = M::NS;
+  const RodasTab tab = make_rodas_tab(cfg.substeps_per_sec * (double)cfg.micro);
   for (int64_t e = 0; e < n; ++e) {
     EnvRegs<M> r;
     for (int i = 0; i < NS; ++i) r.y[i] = sd[(int64_t)i * ld + e];
@@ -34,7 +35,7 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
     Outputs o;
     int done_out, hist_inc;
     bool hist_clear;
-    const bool run = advance_env<M>(cfg, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out,
+    const bool run = advance_env<M>(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out,
                                     hist_inc, hist_clear);
     if (reward) reward[e] = o.reward;
     if (reward_i) reward_i[e] = o.reward_i;
@@ -93,8 +94,10 @@ static void rhs_one(const pvder_env_config& cfg, const double* yin, const double
   double y[M::NS], ff[M::NS];
   for (int i = 0; i < M::NS; ++i) y[i] = yin[i];
   Inputs in{inp4[0], inp4[1], inp4[2], inp4[3]};
-  if (frz) M::template rhs<true>(y, cfg.par, in, frz, ff);
-  else M::template rhs<false>(y, cfg.par, in, 0u, ff);
+  Aux ax;
+  aux_exact<M>(cfg.par, in, y, ax);
+  if (frz) M::template rhs<true>(y, cfg.par, in, ax, frz, ff);
+  else M::template rhs<false>(y, cfg.par, in, ax, 0u, ff);
   for (int i = 0; i < M::NS; ++i) f[i] = ff[i];
 }
 
@@ -105,8 +108,10 @@ static void wsolve_one(const pvder_env_config& cfg, const double* yin, const dou
   for (int i = 0; i < M::NS; ++i) { y[i] = yin[i]; bb[i] = b[i]; }
   Inputs in{inp4[0], inp4[1], inp4[2], inp4[3]};
   typename M::LU lu;
-  if (frz) M::template factor<true>(y, cfg.par, in, frz, ghinv, lu);
-  else M::template factor<false>(y, cfg.par, in, 0u, ghinv, lu);
+  Aux ax;
+  aux_exact<M>(cfg.par, in, y, ax);
+  if (frz) M::template factor<true>(y, cfg.par, in, ax, frz, ghinv, lu);
+  else M::template factor<false>(y, cfg.par, in, ax, 0u, ghinv, lu);
   M::solve(lu, bb);
   for (int i = 0; i < M::NS; ++i) b[i] = bb[i];
 }

@@ -13,6 +13,9 @@ as delta = wte - w_grid*t, A.4):
               are structurally non-zero) -- everything lives in registers,
   * solve():  the matching forward/backward substitution.
 
+sin/cos(delta), Ppv(Vdc) and 1/Vdc enter through an ``Aux`` record the stepper maintains
+incrementally (pvder_env_step.cuh), so the generated code is transcendental-free.
+
 The anti-windup clamp (A.3) is a per-row freeze mask sampled by the caller on the half-cycle
 grid: a frozen row has f_r = 0 and W_r = e_r/(h*gamma).
 
@@ -193,6 +196,8 @@ def generate(P):
     nf = len(m["frozen"])
     A(f"  static constexpr int NFRZ = {nf};   // freeze-mask bits (rows: " +
       ",".join(m["names"][r] for r in m["frozen"]) + ")")
+    A(f"  static constexpr int IDX_VDC = {6 * P};")
+    A(f"  static constexpr int IDX_DL = {6 * P + 4};")
     A("")
     # ---------- unpack macros
     def unpack(indent="    "):
@@ -205,18 +210,13 @@ def generate(P):
     # ---------- rhs
     A("  // Autonomous right-hand side f(y).  frz: bit b set => row frozen_rows[b] is clamped (f = 0).")
     A("  template <bool FRZ>")
-    A("  static PVDER_DEV void rhs(const double (&y)[NS], const Params& par, const Inputs& in,")
-    A("                                             unsigned frz, double (&f)[NS]) {")
+    A("  static PVDER_DEV void rhs(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
+    A("                            unsigned frz, double (&f)[NS]) {")
     L.extend(par_unpack)
     L.extend(unpack())
     A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
-    A("    double sn, cs;")
-    A("    sincos(y_dl, &sn, &cs);")
-    A("    double in_Ppv, in_dPpv;")
-    A("    ppv_eval(par, in, y_Vdc, in_Ppv, in_dPpv);")
-    A("    (void)in_dPpv;")
-    A("    const double inv_Vdc = 1.0 / y_Vdc;")
+    A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, inv_Vdc = aux.inv_Vdc;")
     L.extend(emit_block([(f"f[{r}]", f[r]) for r in range(n)], "t"))
     A("    if (FRZ) {")
     for b, r in enumerate(m["frozen"]):
@@ -259,18 +259,14 @@ def generate(P):
     A(f"  static constexpr int LU_ENTRIES = {len(members)};   // incl. {len(members) - len(pattern)} fill-ins")
     A("")
     A("  template <bool FRZ>")
-    A("  static PVDER_DEV void factor(const double (&y)[NS], const Params& par, const Inputs& in,")
-    A("                                                unsigned frz, double ghinv, LU& lu) {")
+    A("  static PVDER_DEV void factor(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
+    A("                               unsigned frz, double ghinv, LU& lu) {")
     L.extend(par_unpack)
     L.extend(unpack())
     A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
     A("    (void)in_Qref; (void)in_Vdcref;")
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
-    A("    double sn, cs;")
-    A("    sincos(y_dl, &sn, &cs);")
-    A("    double in_Ppv, in_dPpv;")
-    A("    ppv_eval(par, in, y_Vdc, in_Ppv, in_dPpv);")
-    A("    const double inv_Vdc = 1.0 / y_Vdc;")
+    A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, in_dPpv = aux.dPpv, inv_Vdc = aux.inv_Vdc;")
     keys = sorted(J.keys())
     for (r, c) in keys:
         A(f"    double j_{r}_{c};")
