@@ -299,7 +299,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": (44 + 8 + 1) * n,
                     "steps": Ke, "kernel_ms_in_e2e": kms.value / max(1, kcnt.value), "reward_checksum": e2e_checksum},
             "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "episode_stats": {"envs": st[10], "windup_sub_steps": st[9], "failed": st[3]}}
+            "episode_stats": {"envs": st[10], "windup_sub_steps": st[9], "exact_sub_steps": st[11], "failed": st[3],
+                              "note": "counters of the episode in progress at the end of the run (auto-reset clears them)"}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

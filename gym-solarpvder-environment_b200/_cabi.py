@@ -20,7 +20,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 MAX_STATES = 23
 OBS_DIM = 11
 N_ACTIONS = 5
-SI_K, SI_STEPS, SI_EPISODE, SI_STATUS, SI_DONE, SI_HIST, SI_WINDUP, SI_FIELDS = 0, 1, 2, 3, 4, 5, 10, 11
+SI_K, SI_STEPS, SI_EPISODE, SI_STATUS, SI_DONE, SI_HIST, SI_WINDUP, SI_EXACT, SI_FIELDS = 0, 1, 2, 3, 4, 5, 10, 11, 12
 GOALS = {"voltage_regulation": 0, "Q_regulation": 1, "power_regulation": 2}
 EVENT_MODES = {"none": 0, "philox": 1, "table": 2}
 STATUS_OK, STATUS_BAD_ACTION, STATUS_NONFINITE = 0, 1, 2

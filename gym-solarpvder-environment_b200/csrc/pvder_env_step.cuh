@@ -178,13 +178,16 @@ PVDER_NOINLINE void rodas4_exact(double (&y)[M::NS], const Params& par, const In
 }
 
 template <class M>
-PVDER_DEV void rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
+PVDER_DEV bool rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
                            unsigned frz, Aux& base) {
-  if (frz) {
+  // One instantiation serves clamped and unclamped envs (the freeze mask is applied with selects):
+  // with a random policy a third of the warps hold a clamped lane late in an episode, so a
+  // separate divergent code path for them would cost far more than the selects.
+  if (!rodas4_core<M, true, false>(y, par, in, tab, frz, base)) {
     rodas4_exact<M, true>(y, par, in, tab, frz, base);
-  } else if (!rodas4_core<M, false, false>(y, par, in, tab, 0u, base)) {
-    rodas4_exact<M, false>(y, par, in, tab, 0u, base);
+    return false;
   }
+  return true;
 }
 
 // pvder's clamping test np.sign(a) == np.sign(b)
@@ -330,7 +333,7 @@ template <class M>
 struct EnvRegs {
   double y[M::NS];
   double Qref, Vdcref, Vgrid, Sinsol, ret, last_reward;
-  int k, steps, episode, status, done, windup;
+  int k, steps, episode, status, done, windup, exact;
 };
 
 template <class M>
@@ -380,7 +383,8 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
                 __dmul_rn(par.np_iph100, __ddiv_rn(r.Sinsol, 100.0))};
       const unsigned frz = freeze_bits<M>(r.y, par, in);
       if (frz) r.windup += 1;
-      for (int m = 0; m < cfg.micro; ++m) rodas4_step<M>(r.y, par, in, tab, frz, base);
+      for (int m = 0; m < cfg.micro; ++m)
+        if (!rodas4_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
@@ -416,7 +420,7 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
     const int rew_i = o.reward_i;
     init_env<M>(cfg, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol);
     r.episode += 1;
-    r.k = 0; r.steps = 0; r.done = 0; r.ret = 0.0; r.status = PVDER_STATUS_OK; r.windup = 0;
+    r.k = 0; r.steps = 0; r.done = 0; r.ret = 0.0; r.status = PVDER_STATUS_OK; r.windup = 0; r.exact = 0;
     if (cfg.ev_start_k == 0 && cfg.ev_count > 0)
       apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, 0, r.Vgrid, r.Sinsol);
     compute_outputs<M>(cfg, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o);

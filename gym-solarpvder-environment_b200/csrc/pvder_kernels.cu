@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS) step_kernel(const __gr
   r.status = a.si[(int64_t)PVDER_SI_STATUS * a.ld + ec];
   r.done = a.si[(int64_t)PVDER_SI_DONE * a.ld + ec];
   r.windup = a.si[(int64_t)PVDER_SI_WINDUP * a.ld + ec];
+  r.exact = a.si[(int64_t)PVDER_SI_EXACT * a.ld + ec];
   const int act = a.action[ec];
 
   Outputs o;
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS) step_kernel(const __gr
     a.si[(int64_t)PVDER_SI_EPISODE * a.ld + e] = r.episode;
     a.si[(int64_t)PVDER_SI_DONE * a.ld + e] = r.done;
     a.si[(int64_t)PVDER_SI_WINDUP * a.ld + e] = r.windup;
+    a.si[(int64_t)PVDER_SI_EXACT * a.ld + e] = r.exact;
     if (hist_inc >= 0) a.si[(int64_t)(PVDER_SI_HIST + hist_inc) * a.ld + e] += 1;
     if (hist_clear) {
 #pragma unroll
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ pv
   a.si[(int64_t)PVDER_SI_STATUS * a.ld + e] = PVDER_STATUS_OK;
   a.si[(int64_t)PVDER_SI_DONE * a.ld + e] = 0;
   a.si[(int64_t)PVDER_SI_WINDUP * a.ld + e] = 0;
+  a.si[(int64_t)PVDER_SI_EXACT * a.ld + e] = 0;
 #pragma unroll
   for (int h = 0; h < PVDER_N_ACTIONS; ++h) a.si[(int64_t)(PVDER_SI_HIST + h) * a.ld + e] = 0;
   Outputs o;
@@ -206,9 +209,9 @@ __global__ void __launch_bounds__(BLOCK) actions_kernel(uint64_t seed, int64_t s
 }
 
 __global__ void stats_kernel(const double* sd, const int32_t* si, int64_t ld, int ns, int64_t n, double* out) {
-  double acc[11];
+  double acc[12];
 #pragma unroll
-  for (int i = 0; i < 11; ++i) acc[i] = 0.0;
+  for (int i = 0; i < 12; ++i) acc[i] = 0.0;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
     acc[0] += sd[(int64_t)PVDER_SD_RETURN(ns) * ld + e];
     acc[1] += (double)si[(int64_t)PVDER_SI_STEPS * ld + e];
@@ -217,9 +220,10 @@ __global__ void stats_kernel(const double* sd, const int32_t* si, int64_t ld, in
     for (int h = 0; h < PVDER_N_ACTIONS; ++h) acc[4 + h] += (double)si[(int64_t)(PVDER_SI_HIST + h) * ld + e];
     acc[9] += (double)si[(int64_t)PVDER_SI_WINDUP * ld + e];
     acc[10] += 1.0;
+    acc[11] += (double)si[(int64_t)PVDER_SI_EXACT * ld + e];
   }
 #pragma unroll
-  for (int i = 0; i < 11; ++i) {
+  for (int i = 0; i < 12; ++i) {
     double v = acc[i];
     for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
     if ((threadIdx.x & 31) == 0) atomicAdd(out + i, v);
@@ -460,8 +464,10 @@ struct pvder_env {
   uint8_t* d_done;
   double* d_vtab;
   double* d_stab;
-  cudaStream_t stream;
+  cudaStream_t stream;        // compute + H2D
+  cudaStream_t copy_stream;   // D2H of finished chunks, overlapped with the next chunk's kernel
   cudaEvent_t e0, e1;
+  cudaEvent_t chunk_done[8];
   double ms_total;
   int64_t launches;
   int fresh;   // no reset_host() yet: the first one starts episode 0
@@ -480,6 +486,8 @@ int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_of
   h->ld = (n_envs + 31) / 32 * 32;
   h->ns = 6 * cfg->phases + 5;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
   CK(cudaEventCreate(&h->e0));
   CK(cudaEventCreate(&h->e1));
   CK(cudaMalloc(&h->sd, sizeof(double) * PVDER_SD_FIELDS(h->ns) * h->ld));
@@ -509,6 +517,8 @@ int pvder_env_destroy(pvder_env* h) {
   cudaFree(h->sd); cudaFree(h->si); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_obs64);
   cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_vtab); cudaFree(h->d_stab);
   cudaEventDestroy(h->e0); cudaEventDestroy(h->e1);
+  for (int c = 0; c < 8; ++c) cudaEventDestroy(h->chunk_done[c]);
+  cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h;
   return PVDER_OK;
@@ -541,17 +551,36 @@ int pvder_env_reset_host(pvder_env* h, float* obs_out, double* obs64_out) {
 int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
                         uint8_t* done_out) {
   if (!h || !action) return PVDER_ERR_INVALID;
+  // Large batches are processed in up to 8 chunks of whole CTAs: the D2H copy of chunk c runs on
+  // the copy stream while the kernel of chunk c+1 runs on the compute stream.
+  int chunks = 1;
+  if (h->n >= (1 << 16)) chunks = 8;
+  const int64_t per = ((h->n + chunks - 1) / chunks + BLOCK - 1) / BLOCK * BLOCK;
   CK(cudaMemcpyAsync(h->d_action, action, sizeof(int32_t) * h->n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaEventRecord(h->e0, h->stream));
-  int rc = pvder_step(&h->cfg, h->sd, h->si, h->ld, h->d_action, h->d_vtab, h->d_stab, obs_out ? h->d_obs : nullptr,
-                      obs64_out ? h->d_obs64 : nullptr, h->d_reward, nullptr, h->d_done, h->n, h->off, h->stream);
-  if (rc) return rc;
-  CK(cudaEventRecord(h->e1, h->stream));
-  if (obs_out) CK(cudaMemcpyAsync(obs_out, h->d_obs, sizeof(float) * PVDER_OBS_DIM * h->n, cudaMemcpyDeviceToHost, h->stream));
-  if (obs64_out)
-    CK(cudaMemcpyAsync(obs64_out, h->d_obs64, sizeof(double) * PVDER_OBS_DIM * h->n, cudaMemcpyDeviceToHost, h->stream));
-  if (reward_out) CK(cudaMemcpyAsync(reward_out, h->d_reward, sizeof(double) * h->n, cudaMemcpyDeviceToHost, h->stream));
-  if (done_out) CK(cudaMemcpyAsync(done_out, h->d_done, h->n, cudaMemcpyDeviceToHost, h->stream));
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t lo = (int64_t)c * per;
+    if (lo >= h->n) break;
+    const int64_t cnt = (h->n - lo < per) ? (h->n - lo) : per;
+    int rc = pvder_step(&h->cfg, h->sd + lo, h->si + lo, h->ld, h->d_action + lo, h->d_vtab ? h->d_vtab + lo : nullptr,
+                        h->d_stab ? h->d_stab + lo : nullptr, obs_out ? h->d_obs + lo * PVDER_OBS_DIM : nullptr,
+                        obs64_out ? h->d_obs64 + lo * PVDER_OBS_DIM : nullptr, h->d_reward + lo, nullptr, h->d_done + lo,
+                        cnt, h->off + lo, h->stream);
+    if (rc) return rc;
+    if (c == chunks - 1 || lo + cnt >= h->n) CK(cudaEventRecord(h->e1, h->stream));
+    CK(cudaEventRecord(h->chunk_done[c], h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+    if (obs_out)
+      CK(cudaMemcpyAsync(obs_out + lo * PVDER_OBS_DIM, h->d_obs + lo * PVDER_OBS_DIM, sizeof(float) * PVDER_OBS_DIM * cnt,
+                         cudaMemcpyDeviceToHost, h->copy_stream));
+    if (obs64_out)
+      CK(cudaMemcpyAsync(obs64_out + lo * PVDER_OBS_DIM, h->d_obs64 + lo * PVDER_OBS_DIM,
+                         sizeof(double) * PVDER_OBS_DIM * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (reward_out)
+      CK(cudaMemcpyAsync(reward_out + lo, h->d_reward + lo, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (done_out) CK(cudaMemcpyAsync(done_out + lo, h->d_done + lo, cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+  }
+  CK(cudaStreamSynchronize(h->copy_stream));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->e0, h->e1));

@@ -9,7 +9,7 @@ counters) -- NCCL on GPUs, gloo in the CPU tests.
 from __future__ import annotations
 
 STATS_FIELDS = ["return_sum", "steps_sum", "n_done", "n_failed", "act0", "act1", "act2", "act3", "act4",
-                "windup_sub_steps", "n_envs"]
+                "windup_sub_steps", "n_envs", "exact_sub_steps"]
 
 
 def shard_bounds(total_envs: int, rank: int, world_size: int):

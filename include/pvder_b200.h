@@ -43,7 +43,8 @@ extern "C" {
 #define PVDER_SI_DONE 4           /* env.done (PVDER_env.py:183-184) */
 #define PVDER_SI_HIST 5           /* 5 rows: action histogram (env_utilities.py:25-30) */
 #define PVDER_SI_WINDUP 10        /* sub-steps taken with an anti-windup clamp active */
-#define PVDER_SI_FIELDS 11
+#define PVDER_SI_EXACT 11         /* sub-steps redone with library sin/cos/exp (outside the incremental range) */
+#define PVDER_SI_FIELDS 12
 
 enum { PVDER_GOAL_VOLTAGE = 0, PVDER_GOAL_Q = 1, PVDER_GOAL_POWER = 2 };      /* PVDER_env.py:78-93 */
 enum { PVDER_EVENTS_NONE = 0, PVDER_EVENTS_PHILOX = 1, PVDER_EVENTS_TABLE = 2 };
@@ -128,7 +129,7 @@ int pvder_sample_actions(uint64_t seed, int64_t step_index, int32_t* action, int
 
 /* Episode statistics (env_utilities.py:12-46) reduced over envs into 16 device doubles:
  * [0] sum return, [1] sum steps, [2] n done, [3] n failed, [4..8] action histogram,
- * [9] windup sub-steps, [10] n_envs. */
+ * [9] windup sub-steps, [10] n_envs, [11] sub-steps redone with library transcendentals. */
 int pvder_stats_reduce(const double* sd, const int32_t* si, int64_t ld, int phases, int64_t n_envs,
                        double* out16, void* stream);
 

@@ -32,6 +32,7 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
     r.status = si[(int64_t)PVDER_SI_STATUS * ld + e];
     r.done = si[(int64_t)PVDER_SI_DONE * ld + e];
     r.windup = si[(int64_t)PVDER_SI_WINDUP * ld + e];
+    r.exact = si[(int64_t)PVDER_SI_EXACT * ld + e];
     Outputs o;
     int done_out, hist_inc;
     bool hist_clear;
@@ -53,6 +54,7 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
       si[(int64_t)PVDER_SI_EPISODE * ld + e] = r.episode;
       si[(int64_t)PVDER_SI_DONE * ld + e] = r.done;
       si[(int64_t)PVDER_SI_WINDUP * ld + e] = r.windup;
+      si[(int64_t)PVDER_SI_EXACT * ld + e] = r.exact;
       if (hist_inc >= 0) si[(int64_t)(PVDER_SI_HIST + hist_inc) * ld + e] += 1;
       if (hist_clear)
         for (int h = 0; h < PVDER_N_ACTIONS; ++h) si[(int64_t)(PVDER_SI_HIST + h) * ld + e] = 0;
