@@ -23,7 +23,7 @@ N_ACTIONS = 5
 SI_K, SI_STEPS, SI_EPISODE, SI_STATUS, SI_DONE, SI_HIST, SI_WINDUP, SI_EXACT, SI_FIELDS = 0, 1, 2, 3, 4, 5, 10, 11, 12
 GOALS = {"voltage_regulation": 0, "Q_regulation": 1, "power_regulation": 2}
 EVENT_MODES = {"none": 0, "philox": 1, "table": 2}
-STATUS_OK, STATUS_BAD_ACTION, STATUS_NONFINITE = 0, 1, 2
+STATUS_OK, STATUS_BAD_ACTION, STATUS_NONFINITE, STATUS_UNBALANCED = 0, 1, 2, 3
 
 
 def sd_fields(ns):
@@ -47,7 +47,7 @@ class EnvConfigC(C.Structure):
         ("phases", C.c_int32), ("n_sub_per_step", C.c_int32), ("micro", C.c_int32), ("done_substep", C.c_int32),
         ("discrete_reward", C.c_int32), ("goal", C.c_int32), ("auto_reset", C.c_int32), ("event_mode", C.c_int32),
         ("ev_start_k", C.c_int32), ("ev_step_k", C.c_int32), ("ev_count", C.c_int32),
-        ("ev_voltage_enable", C.c_int32), ("ev_insol_enable", C.c_int32),
+        ("ev_voltage_enable", C.c_int32), ("ev_insol_enable", C.c_int32), ("balanced3", C.c_int32),
         ("ev_v_min", C.c_double), ("ev_v_max", C.c_double), ("ev_s_min", C.c_double), ("ev_s_max", C.c_double),
         ("delQ_pu", C.c_double), ("delVdc_pu", C.c_double), ("max_sim_time", C.c_double),
         ("substeps_per_sec", C.c_double), ("seed", C.c_uint64), ("Q_ref0", C.c_double), ("Vdc_ref0", C.c_double),

@@ -206,7 +206,7 @@ PVDER_DEV void phase_rot(int P, int k, double& rr, double& ri) {
 // Anti-windup mode, sampled once per half-cycle sub-step.  Bit order = M::NFRZ
 // rows: per phase xR,xI,uR,uI ; then xDC, xQ.
 template <class M>
-PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, const Inputs& in) {
+PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, const Inputs& in, bool& m_over_out) {
   constexpr int P = M::PHASES;
   constexpr int B = 6 * P;
   double Q = 0.0;
@@ -219,8 +219,9 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
     const double mR = fma(par.Kp_GCC, y[6 * k + 4], y[6 * k + 2]);
     const double mI = fma(par.Kp_GCC, y[6 * k + 5], y[6 * k + 3]);
     m_over |= (mR * mR + mI * mI) > par.m_limit10 * par.m_limit10;
-    Q += 0.5 * ((in.vg * ri) * iR - (in.vg * rr) * iI + par.Xt * (iR * iR + iI * iI));
+    Q += M::PMULT * 0.5 * ((in.vg * ri) * iR - (in.vg * rr) * iI + par.Xt * (iR * iR + iI * iI));
   }
+  m_over_out = m_over;
   const double Vdc = y[B], xDC = y[B + 1], xQ = y[B + 2];
   const double irefR = xDC + par.Kp_DC * (in.Vdcref - Vdc);
   const double irefI = xQ - par.Kp_Q * (in.Qref - Q);
@@ -283,10 +284,33 @@ struct Outputs {
   int reward_i;
 };
 
-template <class M>
-PVDER_DEV void compute_outputs(const pvder_env_config& cfg, const double (&y)[M::NS], double Qref,
-                                                double Vdcref, double Vgrid, double Sinsol, int k, Outputs& o) {
-  constexpr int P = M::PHASES;
+// Balanced three-phase set carried by phase a -> full 23-state vector (phases b, c are phase a
+// rotated by -/+120 degrees).  Individually rounded ops: the stored state and the outputs computed
+// from it are reproducible bit for bit.
+PVDER_DEV void expand_balanced(const double (&y)[11], double (&z)[23]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double rr, ri;
+    phase_rot(3, k, rr, ri);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double a = y[2 * j], b = y[2 * j + 1];
+      if (k == 0) {
+        z[2 * j] = a;
+        z[2 * j + 1] = b;
+      } else {
+        z[6 * k + 2 * j] = __dadd_rn(__dmul_rn(a, rr), -__dmul_rn(b, ri));
+        z[6 * k + 2 * j + 1] = __dadd_rn(__dmul_rn(a, ri), __dmul_rn(b, rr));
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) z[18 + j] = y[6 + j];
+}
+
+template <int P>
+PVDER_DEV void compute_outputs_p(const pvder_env_config& cfg, const double (&y)[6 * P + 5], double Qref,
+                                 double Vdcref, double Vgrid, double Sinsol, int k, Outputs& o) {
   constexpr int B = 6 * P;
   const Params& par = cfg.par;
   const double vg = __dmul_rn(Vgrid, par.vgs);
@@ -327,6 +351,46 @@ PVDER_DEV void compute_outputs(const pvder_env_config& cfg, const double (&y)[M:
   }
 }
 
+template <class M>
+PVDER_DEV void compute_outputs(const pvder_env_config& cfg, const double (&y)[M::NS], double Qref, double Vdcref,
+                               double Vgrid, double Sinsol, int k, Outputs& o) {
+  if constexpr (M::BALANCED3) {
+    double z[23];
+    expand_balanced(y, z);
+    compute_outputs_p<3>(cfg, z, Qref, Vdcref, Vgrid, Sinsol, k, o);
+  } else {
+    compute_outputs_p<M::PHASES>(cfg, y, Qref, Vdcref, Vgrid, Sinsol, k, o);
+  }
+}
+
+// Stored state (sd rows 0..NS_STORE-1) <-> registers.  The balanced model reads phase a and the
+// shared rows only and writes all 23 rows back.
+template <class M>
+PVDER_DEV void load_state(const double* sd, int64_t ld, int64_t e, double (&y)[M::NS]) {
+  if constexpr (M::BALANCED3) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y[i] = sd[(int64_t)i * ld + e];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) y[6 + i] = sd[(int64_t)(18 + i) * ld + e];
+  } else {
+#pragma unroll
+    for (int i = 0; i < M::NS; ++i) y[i] = sd[(int64_t)i * ld + e];
+  }
+}
+
+template <class M>
+PVDER_DEV void store_state(double* sd, int64_t ld, int64_t e, const double (&y)[M::NS]) {
+  if constexpr (M::BALANCED3) {
+    double z[23];
+    expand_balanced(y, z);
+#pragma unroll
+    for (int i = 0; i < 23; ++i) sd[(int64_t)i * ld + e] = z[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < M::NS; ++i) sd[(int64_t)i * ld + e] = y[i];
+  }
+}
+
 
 // Registers of one environment.
 template <class M>
@@ -339,8 +403,15 @@ struct EnvRegs {
 template <class M>
 PVDER_DEV void init_env(const pvder_env_config& cfg, double (&y)[M::NS], double& Qref, double& Vdcref,
                         double& Vgrid, double& Sinsol) {
+  if constexpr (M::BALANCED3) {
 #pragma unroll
-  for (int i = 0; i < M::NS; ++i) y[i] = cfg.y0[i];
+    for (int i = 0; i < 6; ++i) y[i] = cfg.y0[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) y[6 + i] = cfg.y0[18 + i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < M::NS; ++i) y[i] = cfg.y0[i];
+  }
   Qref = cfg.Q_ref0;
   Vdcref = cfg.Vdc_ref0;
   Vgrid = 1.0;
@@ -381,8 +452,12 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
     for (int s = 0; s < cfg.n_sub_per_step; ++s) {
       Inputs in{__dmul_rn(r.Vgrid, par.vgs), r.Qref, r.Vdcref,
                 __dmul_rn(par.np_iph100, __ddiv_rn(r.Sinsol, 100.0))};
-      const unsigned frz = freeze_bits<M>(r.y, par, in);
+      bool m_over;
+      const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
       if (frz) r.windup += 1;
+      // the duty-cycle clamp acts on Re/Im parts per phase and would break the symmetry the
+      // balanced representation relies on: report instead of integrating something else
+      if (M::BALANCED3 && m_over) r.status = PVDER_STATUS_UNBALANCED;
       for (int m = 0; m < cfg.micro; ++m)
         if (!rodas4_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
       r.k += 1;
@@ -401,7 +476,7 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
   compute_outputs<M>(cfg, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o);
   done_out = r.done;
   if (run) {
-    if (r.status == PVDER_STATUS_NONFINITE) {   // PVDER_env.py:170-172: intended -100 penalty, episode ends
+    if (r.status == PVDER_STATUS_NONFINITE || r.status == PVDER_STATUS_UNBALANCED) {   // PVDER_env.py:170-172: -100, episode ends
       o.reward = -100.0;
       o.reward_i = -100;
       done_out = 1;

@@ -23,6 +23,7 @@
 #include "pvder_common.cuh"
 #include "pvder_model_1ph.cuh"
 #include "pvder_model_3ph.cuh"
+#include "pvder_model_3ph_bal.cuh"
 #include "pvder_env_step.cuh"
 
 namespace pvder {
@@ -67,7 +68,7 @@ __device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const O
 template <class M>
 __global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS) step_kernel(const __grid_constant__ pvder_env_config cfg,
                                                      const __grid_constant__ RodasTab tab, const StepArgs a) {
-  constexpr int NS = M::NS;
+  constexpr int NS = M::NS_STORE;   // rows of the stored state (the balanced model integrates 11 of 23)
   __shared__ float stage[BLOCK * PVDER_OBS_DIM];
   const int64_t block_first = (int64_t)blockIdx.x * BLOCK;
   const int64_t e = block_first + threadIdx.x;
@@ -75,8 +76,7 @@ __global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS) step_kernel(const __gr
   const int64_t ec = active ? e : (a.n - 1);   // inactive lanes shadow the last env and never store
 
   EnvRegs<M> r;
-#pragma unroll
-  for (int i = 0; i < NS; ++i) r.y[i] = a.sd[(int64_t)i * a.ld + ec];
+  load_state<M>(a.sd, a.ld, ec, r.y);
   r.Qref = a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + ec];
   r.Vdcref = a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + ec];
   r.Vgrid = a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + ec];
@@ -104,8 +104,7 @@ __global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS) step_kernel(const __gr
     if (a.done) a.done[e] = (uint8_t)done_out;
   }
   if (run) {
-#pragma unroll
-    for (int i = 0; i < NS; ++i) a.sd[(int64_t)i * a.ld + e] = r.y[i];
+    store_state<M>(a.sd, a.ld, e, r.y);
     a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + e] = r.Qref;
     a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + e] = r.Vdcref;
     a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + e] = r.Vgrid;
@@ -381,6 +380,7 @@ int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld,
   cudaStream_t st = (cudaStream_t)stream;
   const RodasTab tab = make_rodas_tab(cfg->substeps_per_sec * (double)cfg->micro);
   if (cfg->phases == 1) step_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, tab, a);
+  else if (cfg->balanced3) step_kernel<Model3phBal><<<grid, BLOCK, 0, st>>>(*cfg, tab, a);
   else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, tab, a);
   CK(cudaGetLastError());
   return PVDER_OK;

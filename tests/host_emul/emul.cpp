@@ -7,6 +7,7 @@
 #include "../../gym-solarpvder-environment_b200/csrc/pvder_common.cuh"
 #include "../../gym-solarpvder-environment_b200/csrc/pvder_model_1ph.cuh"
 #include "../../gym-solarpvder-environment_b200/csrc/pvder_model_3ph.cuh"
+#include "../../gym-solarpvder-environment_b200/csrc/pvder_model_3ph_bal.cuh"
 #include "../../gym-solarpvder-environment_b200/csrc/pvder_env_step.cuh"
 
 using namespace pvder;
@@ -15,11 +16,11 @@ template <class M>
 static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
                      const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
                      uint8_t* done, int64_t n, int64_t off) {
-  constexpr int NS = M::NS;
+  constexpr int NS = M::NS_STORE;
   const RodasTab tab = make_rodas_tab(cfg.substeps_per_sec * (double)cfg.micro);
   for (int64_t e = 0; e < n; ++e) {
     EnvRegs<M> r;
-    for (int i = 0; i < NS; ++i) r.y[i] = sd[(int64_t)i * ld + e];
+    load_state<M>(sd, ld, e, r.y);
     r.Qref = sd[(int64_t)PVDER_SD_QREF(NS) * ld + e];
     r.Vdcref = sd[(int64_t)PVDER_SD_VDCREF(NS) * ld + e];
     r.Vgrid = sd[(int64_t)PVDER_SD_VGRID(NS) * ld + e];
@@ -42,7 +43,7 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
     if (reward_i) reward_i[e] = o.reward_i;
     if (done) done[e] = (uint8_t)done_out;
     if (run) {
-      for (int i = 0; i < NS; ++i) sd[(int64_t)i * ld + e] = r.y[i];
+      store_state<M>(sd, ld, e, r.y);
       sd[(int64_t)PVDER_SD_QREF(NS) * ld + e] = r.Qref;
       sd[(int64_t)PVDER_SD_VDCREF(NS) * ld + e] = r.Vdcref;
       sd[(int64_t)PVDER_SD_VGRID(NS) * ld + e] = r.Vgrid;
@@ -123,7 +124,8 @@ static unsigned frz_one(const pvder_env_config& cfg, const double* yin, const do
   double y[M::NS];
   for (int i = 0; i < M::NS; ++i) y[i] = yin[i];
   Inputs in{inp4[0], inp4[1], inp4[2], inp4[3]};
-  return freeze_bits<M>(y, cfg.par, in);
+  bool m_over;
+  return freeze_bits<M>(y, cfg.par, in, m_over);
 }
 
 extern "C" {
@@ -132,6 +134,7 @@ int emul_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, 
               const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i, uint8_t* done,
               int64_t n, int64_t off) {
   if (cfg->phases == 1) step_all<Model1ph>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
+  else if (cfg->balanced3) step_all<Model3phBal>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   else step_all<Model3ph>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   return 0;
 }

@@ -124,6 +124,45 @@ def test_golden_fixture(model_type):
             H.assert_state_close(em.sd[:em.ns, i], gold["state"][i, s], em.cfg.phases, what=f"env{i} step{s}")
 
 
+def test_balanced_reduction_equals_general_three_phase():
+    """model_2 default integrates the balanced set on phase a; the general 23-state path must give
+    the same trajectory (and both are checked against the oracle above / in the golden test)."""
+    kw = dict(model_type="model_2", events_spec=H.SAG_SPEC, seed=4, DISCRETE_REWARD=True)
+    bal = E.EmulVecEnv(6, balanced_three_phase=True, **kw)
+    gen = E.EmulVecEnv(6, balanced_three_phase=False, **kw)
+    assert bal.cfg.c.balanced3 == 1 and gen.cfg.c.balanced3 == 0
+    np.testing.assert_array_equal(bal.reset(), gen.reset())
+    for s in range(8):
+        a = twin.sample_actions_twin(4, s, 6, 0)
+        ob, rb, db, _ = bal.step(a)
+        og, rg, dg, _ = gen.step(a)
+        np.testing.assert_allclose(bal.sd, gen.sd, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(ob, og, rtol=1e-9, atol=1e-11)
+        np.testing.assert_array_equal(rb, rg)
+        np.testing.assert_array_equal(bal.si, gen.si)
+    # phases b, c of the stored state are exact rotations of phase a
+    ia = bal.sd[0] + 1j * bal.sd[1]
+    ib = bal.sd[6] + 1j * bal.sd[7]
+    np.testing.assert_allclose(ib, ia * np.exp(-2j * math.pi / 3), rtol=1e-15, atol=1e-16)
+
+
+@pytest.mark.parametrize("balanced", [True, False])
+def test_golden_fixture_three_phase_modes(balanced):
+    gold = np.load("tests/golden/golden_model_2.npz")
+    acts = gold["actions"]
+    n, nsteps = acts.shape
+    em = E.EmulVecEnv(n, model_type="model_2", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True,
+                      balanced_three_phase=balanced)
+    em.set_event_tables(gold["vgrid_tab"], gold["sinsol_tab"])
+    em.reset()
+    for s in range(nsteps):
+        obs, rew, done, _ = em.step(acts[:, s])
+        np.testing.assert_allclose(obs, gold["obs"][:, s], rtol=H.RTOL, atol=H.ATOL)
+        np.testing.assert_array_equal(rew, gold["reward"][:, s])
+        for i in range(n):
+            H.assert_state_close(em.sd[:em.ns, i], gold["state"][i, s], 3, what=f"env{i} step{s}")
+
+
 def test_event_tables_bit_exact_vs_twin():
     em = E.EmulVecEnv(4096, env_offset=11, model_type="model_1", events_spec=H.SAG_SPEC, seed=1234)
     em.reset()

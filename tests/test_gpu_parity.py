@@ -23,13 +23,14 @@ def _venv(cuda, n, **kw):
     return G.PVDERVecEnv(n, device=cuda, obs_f64=True, **kw)
 
 
-@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
-def test_matches_cpp_emulation(cuda, model_type):
+@pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", False)])
+def test_matches_cpp_emulation(cuda, model_type, balanced):
     import torch
     import emul_harness as E
 
     n = 300   # not a multiple of the block size
-    kw = dict(model_type=model_type, events_spec=H.SAG_SPEC, seed=1234, DISCRETE_REWARD=True)
+    kw = dict(model_type=model_type, events_spec=H.SAG_SPEC, seed=1234, DISCRETE_REWARD=True,
+              balanced_three_phase=balanced)
     g = _venv(cuda, n, env_offset=17, **kw)
     e = E.EmulVecEnv(n, env_offset=17, **kw)
     og = g.reset().cpu().numpy()
@@ -53,14 +54,15 @@ def test_matches_cpp_emulation(cuda, model_type):
     assert int(g.si[10, :n].sum()) == int(e.si[10].sum())
 
 
-@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
-def test_trajectory_vs_tight_oracle(cuda, model_type):
+@pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", False)])
+def test_trajectory_vs_tight_oracle(cuda, model_type, balanced):
     """Same y0, parameters, actions and event sequence as the oracle's tight LSODA path."""
     import torch
 
     schedules = [[0] * 6, [1, 2, 0, 3, 4, 1], [3, 3, 4, 1, 2, 0], [4, 1, 1, 2, 3, 0]]
     n = len(schedules)
-    g = _venv(cuda, n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False)
+    g = _venv(cuda, n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False,
+              balanced_three_phase=balanced)
     c = g.cfg.c
     evs = [H.random_events(100 + i) for i in range(n)]
     vt = np.concatenate([H.oracle_tables(ev, c)[0] for ev in evs], axis=1)
@@ -84,15 +86,16 @@ def test_trajectory_vs_tight_oracle(cuda, model_type):
             assert bool(done[i]) == od
 
 
-@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
-def test_golden_fixture(cuda, model_type):
+@pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", False)])
+def test_golden_fixture(cuda, model_type, balanced):
     """Committed golden vectors (oracle tight path, tests/golden/make_golden.py)."""
     import torch
 
     gold = np.load(f"tests/golden/golden_{model_type}.npz")
     acts, vt, st = gold["actions"], gold["vgrid_tab"], gold["sinsol_tab"]
     n, nsteps = acts.shape
-    g = _venv(cuda, n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True)
+    g = _venv(cuda, n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True,
+              balanced_three_phase=balanced)
     g.set_event_tables(vt, st)
     g.reset()
     bad = 0
@@ -131,7 +134,7 @@ def test_events_bit_exact_65536(cuda):
                                                       ("model_2", "power_regulation", True),
                                                       ("model_1", "Q_regulation", True),
                                                       ("model_2", "voltage_regulation", False)])
-def test_rewards_bit_exact_given_state_65536(cuda, model_type, goal, discrete):
+def test_rewards_bit_exact_given_state_65536(cuda, model_type, goal, discrete):  # model_2: balanced mode (default)
     """Integer outputs are bit-exact: reward/obs recomputed by the numpy twin from the fp64 state the
     kernel wrote must equal what the kernel emitted (same state => same integer)."""
     import torch

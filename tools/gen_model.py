@@ -34,7 +34,9 @@ PAR = ["Rf", "Rt", "Xt", "inv_Lf", "inv_wb", "Kp_GCC", "Ki_GCC", "Kp_DC", "Ki_DC
 INP = ["vg", "Qref", "Vdcref", "Ppv", "dPpv"]
 
 
-def build(P):
+def build(P, mult=1):
+    """P phases integrated explicitly; mult > 1: balanced three-phase set represented by phase a
+    (phases b, c are rotated copies, so every sum over phases is mult * the phase-a term)."""
     par = {n: sp.Symbol("p_" + n) for n in PAR}
     inp = {n: sp.Symbol("in_" + n) for n in INP}
     names = []
@@ -67,8 +69,8 @@ def build(P):
         vI.append(inp["vg"] * ri + p["Xt"] * iR + p["Rt"] * iI)
         mR.append(p["Kp_GCC"] * uR + xR)
         mI.append(p["Kp_GCC"] * uI + xI)
-        Q += sp.Rational(1, 2) * (vI[k] * iR - vR[k] * iI)
-        Pinv += sp.Rational(1, 4) * Vdc * (mR[k] * iR + mI[k] * iI)
+        Q += mult * sp.Rational(1, 2) * (vI[k] * iR - vR[k] * iI)
+        Pinv += mult * sp.Rational(1, 4) * Vdc * (mR[k] * iR + mI[k] * iI)
         ca, sa = alpha[k]
         ck = cs * ca + sn * sa       # cos(dl - a_k)
         sk = sn * ca - cs * sa       # sin(dl - a_k)
@@ -116,7 +118,7 @@ def build(P):
     for k in range(P):
         frozen_rows += [6 * k + 2, 6 * k + 3, 6 * k + 4, 6 * k + 5]
     frozen_rows += [base + 1, base + 2]
-    return dict(P=P, n=n, names=names, y=y, f=f, J=J, par=par, inp=inp, frozen=frozen_rows,
+    return dict(P=P, mult=mult, n=n, names=names, y=y, f=f, J=J, par=par, inp=inp, frozen=frozen_rows,
                 helpers=(sn, cs, inv_Vdc))
 
 
@@ -173,15 +175,15 @@ def elimination_order(n, pattern, P):
     return order
 
 
-def generate(P):
-    m = build(P)
+def generate(P, mult=1):
+    m = build(P, mult)
     n, y, f, J = m["n"], m["y"], m["f"], m["J"]
-    tag = f"{P}ph"
-    cls = f"Model{P}ph"
+    tag = f"{P}ph" if mult == 1 else f"{mult}ph_bal"
+    cls = f"Model{P}ph" if mult == 1 else f"Model{mult}phBal"
     L = []
     A = L.append
     A("// GENERATED by tools/gen_model.py -- do not edit by hand.")
-    A(f"// PV-DER model, {P} phase(s), {n} states: " + " ".join(m["names"]))
+    A(f"// PV-DER model, {P * mult} phase(s){' (balanced set carried by phase a)' if mult > 1 else ''}, {n} states: " + " ".join(m["names"]))
     A("// Equations: SURVEY.md Appendix A.2-A.4 (restated from the un-vendored pvder package that")
     A("// reference gym_PVDER/envs/PVDER_env.py:26-35 imports); PLL angle stored as delta = wte - w*t.")
     A("#pragma once")
@@ -191,7 +193,11 @@ def generate(P):
     A("")
     A(f"struct {cls} {{")
     A(f"  static constexpr int NS = {n};")
-    A(f"  static constexpr int PHASES = {P};")
+    A(f"  static constexpr int PHASES = {P};            // phases integrated explicitly")
+    A(f"  static constexpr int PHASES_OUT = {P * mult};        // phases of the physical model / stored state")
+    A(f"  static constexpr int NS_STORE = {6 * P * mult + 5};       // rows of the stored state")
+    A(f"  static constexpr bool BALANCED3 = {'true' if mult > 1 else 'false'};")
+    A(f"  static constexpr double PMULT = {float(mult)};         // sum over phases = PMULT * explicit phases")
     A(f"  static constexpr int NNZ_J = {len(J)};")
     nf = len(m["frozen"])
     A(f"  static constexpr int NFRZ = {nf};   // freeze-mask bits (rows: " +
@@ -334,5 +340,6 @@ def generate(P):
 
 
 if __name__ == "__main__":
-    for P in ([1, 3] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:]]):
-        generate(P)
+    generate(1)
+    generate(3)
+    generate(1, mult=3)      # balanced three-phase set on phase a (balanced reduction)
