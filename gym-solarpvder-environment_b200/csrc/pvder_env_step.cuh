@@ -20,9 +20,12 @@ struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant 
   double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54;
   double c21, c31, c32, c41, c42, c43, c51, c52, c53, c54, c61, c62, c63, c64, c65;
   double ghinv;     // 1/(h*gamma)
+  double luc[16];   // launch-constant reciprocal pivots of the symbolic LU (M::lu_consts)
 };
 
-inline RodasTab make_rodas_tab(double hinv) {
+template <class M>
+inline RodasTab make_rodas_tab(const Params& par, double hinv) {
+  static_assert(M::N_LUC <= 16, "luc table too small");
   RodasTab t;
   t.a21 = 0.1544000000000000e+01;
   t.a31 = 0.9466785280815826e+00; t.a32 = 0.2557011698983284e+00;
@@ -37,6 +40,8 @@ inline RodasTab make_rodas_tab(double hinv) {
   t.c61 = 0.8083246795921522e+01 * hinv; t.c62 = -0.7981132988064893e+01 * hinv; t.c63 = -0.3152159432874371e+02 * hinv;
   t.c64 = 0.1631930543123136e+02 * hinv; t.c65 = -0.6058818238834054e+01 * hinv;
   t.ghinv = hinv * (1.0 / RG);
+  for (int i = 0; i < 16; ++i) t.luc[i] = 0.0;
+  M::lu_consts(par, t.ghinv, t.luc);
   return t;
 }
 
@@ -110,7 +115,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
   ppv_from_exp(par, in, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
   typename M::LU lu;
-  M::template factor<FRZ>(y, par, in, base, frz, tab.ghinv, lu);
+  M::template factor<FRZ>(y, par, in, base, frz, tab.ghinv, tab.luc, lu);
   double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], Y[NS];
   Aux ax;
   // stage 1

@@ -378,10 +378,11 @@ int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld,
   StepArgs a{sd, si, ld, action, vgrid_tab, sinsol_tab, obs_f32, obs_f64, reward_f64, reward_i32, done, n_envs, env_offset};
   const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
-  const RodasTab tab = make_rodas_tab(cfg->substeps_per_sec * (double)cfg->micro);
-  if (cfg->phases == 1) step_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, tab, a);
-  else if (cfg->balanced3) step_kernel<Model3phBal><<<grid, BLOCK, 0, st>>>(*cfg, tab, a);
-  else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, tab, a);
+  const double hinv = cfg->substeps_per_sec * (double)cfg->micro;
+  if (cfg->phases == 1) step_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model1ph>(cfg->par, hinv), a);
+  else if (cfg->balanced3)
+    step_kernel<Model3phBal><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3phBal>(cfg->par, hinv), a);
+  else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3ph>(cfg->par, hinv), a);
   CK(cudaGetLastError());
   return PVDER_OK;
 }

@@ -17,7 +17,7 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
                      const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
                      uint8_t* done, int64_t n, int64_t off) {
   constexpr int NS = M::NS_STORE;
-  const RodasTab tab = make_rodas_tab(cfg.substeps_per_sec * (double)cfg.micro);
+  const RodasTab tab = make_rodas_tab<M>(cfg.par, cfg.substeps_per_sec * (double)cfg.micro);
   for (int64_t e = 0; e < n; ++e) {
     EnvRegs<M> r;
     load_state<M>(sd, ld, e, r.y);
@@ -113,8 +113,10 @@ static void wsolve_one(const pvder_env_config& cfg, const double* yin, const dou
   typename M::LU lu;
   Aux ax;
   aux_exact<M>(cfg.par, in, y, ax);
-  if (frz) M::template factor<true>(y, cfg.par, in, ax, frz, ghinv, lu);
-  else M::template factor<false>(y, cfg.par, in, ax, 0u, ghinv, lu);
+  double luc[16];
+  M::lu_consts(cfg.par, ghinv, luc);
+  if (frz) M::template factor<true>(y, cfg.par, in, ax, frz, ghinv, luc, lu);
+  else M::template factor<false>(y, cfg.par, in, ax, 0u, ghinv, luc, lu);
   M::solve(lu, bb);
   for (int i = 0; i < M::NS; ++i) b[i] = bb[i];
 }

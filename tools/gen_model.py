@@ -112,6 +112,9 @@ def build(P, mult=1):
             d = d.subs(1 / Vdc, inv_Vdc)
             d = sp.simplify(d) if P == 1 else d
             d = d.subs(1 / Vdc, inv_Vdc).subs(Vdc ** -2, inv_Vdc ** 2)
+            # never emit a division: sympy may have rewritten Vdc as 1/inv_Vdc
+            d = d.replace(lambda e: e.is_Pow and e.base == inv_Vdc and e.exp.is_negative,
+                          lambda e: Vdc ** (-e.exp))
             if d != 0:
                 J[(r, c)] = d
     frozen_rows = []
@@ -253,6 +256,33 @@ def generate(P, mult=1):
                     pat.add((r, c))
                     ops.append(("new", r, c, k))
     members = sorted(pat)
+    # Launch-constant pivots: w_kk is still its initial value ghinv - J_kk when row k is pivoted and
+    # J_kk depends on parameters only.  Their reciprocals come from a host-filled table (and a
+    # select when the row can be frozen) instead of a division per sub-step.
+    par_syms = set(m["par"].values())
+    touched = set()
+    const_piv = {}          # k -> index into luc[]
+    luc_exprs = []          # sympy expressions of 1/(ghinv - J_kk), ghinv symbol = GH
+    GH = sp.Symbol("ghinv")
+    for op in ops:
+        if op[0] == "inv":
+            k = op[1]
+            jkk = J.get((k, k), sp.Integer(0))
+            if (k, k) not in touched and jkk.free_symbols <= par_syms:
+                const_piv[k] = len(luc_exprs)
+                luc_exprs.append(1 / (GH - jkk))
+        elif op[0] in ("fma", "new"):
+            touched.add((op[1], op[2]))
+    A(f"  static constexpr int N_LUC = {len(luc_exprs) + 1};   // launch-constant reciprocal pivots (+ 1/ghinv)")
+    A("  // luc[0] = 1/ghinv (pivot of a frozen row); luc[1 + i] = reciprocal of constant pivot i")
+    A("  static PVDER_HD void lu_consts(const Params& par, double ghinv, double* luc) {")
+    for nme in PAR:
+        A(f"    const double p_{nme} = par.{nme}; (void)p_{nme};")
+    A("    luc[0] = 1.0 / ghinv;")
+    for i, e in enumerate(luc_exprs):
+        A(f"    luc[{i + 1}] = {ccode(e)};")
+    A("  }")
+    A("")
     A("  struct LU {")
     A("    // strictly-lower entries hold multipliers, upper entries hold U, d_k = 1/pivot")
     for (r, c) in members:
@@ -266,7 +296,7 @@ def generate(P, mult=1):
     A("")
     A("  template <bool FRZ>")
     A("  static PVDER_DEV void factor(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
-    A("                               unsigned frz, double ghinv, LU& lu) {")
+    A("                               unsigned frz, double ghinv, const double* luc, LU& lu) {")
     L.extend(par_unpack)
     L.extend(unpack())
     A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
@@ -294,7 +324,14 @@ def generate(P, mult=1):
     for op in ops:
         if op[0] == "inv":
             k = op[1]
-            A(f"    const double d_{k} = 1.0 / w_{k}_{k};")
+            if k in const_piv:
+                if k in m["frozen"]:
+                    b = m["frozen"].index(k)
+                    A(f"    const double d_{k} = (FRZ && (frz & {1 << b}u)) ? luc[0] : luc[{const_piv[k] + 1}];")
+                else:
+                    A(f"    const double d_{k} = luc[{const_piv[k] + 1}];")
+            else:
+                A(f"    const double d_{k} = 1.0 / w_{k}_{k};")
         elif op[0] == "mul":
             _, r, k = op
             A(f"    {wname(r, k)} *= d_{k};")
@@ -334,6 +371,7 @@ def generate(P, mult=1):
     path = os.path.join(OUT, f"pvder_model_{tag}.cuh")
     with open(path, "w") as fh:
         fh.write("\n".join(L) + "\n")
+    print(f"{path}: const pivots {sorted(const_piv)}")
     print(f"{path}: n={n} nnz(J)={len(J)} LU entries={len(members)} order={[m['names'][k] for k in order]} "
           f"lu_flops={nflop_f} solve_flops={nflop_s}")
     return m, order
