@@ -105,66 +105,83 @@ PVDER_DEV void aux_advance(const Params& par, const Inputs& in, const Aux& b, do
   }
 }
 
+// Effective gains of the freezable rows (bit order of freeze_bits): the parameter, or 0 while the
+// row is clamped.  Computed once per sub-step; the generated RHS/Jacobian take them as inputs.
+template <class M>
+PVDER_DEV void make_gains(const Params& par, unsigned frz, double (&gn)[M::NFRZ]) {
+#pragma unroll
+  for (int k = 0; k < M::PHASES; ++k) {
+    gn[4 * k] = (frz & (1u << (4 * k))) ? 0.0 : par.Ki_GCC;
+    gn[4 * k + 1] = (frz & (1u << (4 * k + 1))) ? 0.0 : par.Ki_GCC;
+    gn[4 * k + 2] = (frz & (1u << (4 * k + 2))) ? 0.0 : par.wp;
+    gn[4 * k + 3] = (frz & (1u << (4 * k + 3))) ? 0.0 : par.wp;
+  }
+  gn[4 * M::PHASES] = (frz & (1u << (4 * M::PHASES))) ? 0.0 : par.Ki_DC;
+  gn[4 * M::PHASES + 1] = (frz & (1u << (4 * M::PHASES + 1))) ? 0.0 : par.Ki_Q;
+}
+
 // One half-cycle Rodas4 step.  `base` is the Aux record at y on entry and at the new y on exit.
 // Returns false (y, base untouched) when EXACT == false and a stage left the incremental range.
-template <class M, bool FRZ, bool EXACT>
+template <class M, bool EXACT>
 PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
                            unsigned frz, Aux& base) {
+  double gn[M::NFRZ];
+  make_gains<M>(par, frz, gn);
   constexpr int NS = M::NS;
   bool oor = false;
   const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
   ppv_from_exp(par, in, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
   typename M::LU lu;
-  M::template factor<FRZ>(y, par, in, base, frz, tab.ghinv, tab.luc, lu);
+  M::factor(y, par, in, base, gn, tab.ghinv, tab.luc, lu);
   double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], Y[NS];
   Aux ax;
   // stage 1
-  M::template rhs<FRZ>(y, par, in, base, frz, K1);
-  M::solve(lu, K1);
+  M::rhs(y, par, in, base, gn, K1);
+  M::solve(lu, tab.luc, K1);
   // stage 2
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a21, K1[i], y[i]);
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
-  M::template rhs<FRZ>(Y, par, in, ax, frz, K2);
+  M::rhs(Y, par, in, ax, gn, K2);
 #pragma unroll
   for (int i = 0; i < NS; ++i) K2[i] = fma(tab.c21, K1[i], K2[i]);
-  M::solve(lu, K2);
+  M::solve(lu, tab.luc, K2);
   // stage 3
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a32, K2[i], fma(tab.a31, K1[i], y[i]));
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
-  M::template rhs<FRZ>(Y, par, in, ax, frz, K3);
+  M::rhs(Y, par, in, ax, gn, K3);
 #pragma unroll
   for (int i = 0; i < NS; ++i) K3[i] = fma(tab.c32, K2[i], fma(tab.c31, K1[i], K3[i]));
-  M::solve(lu, K3);
+  M::solve(lu, tab.luc, K3);
   // stage 4
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a43, K3[i], fma(tab.a42, K2[i], fma(tab.a41, K1[i], y[i])));
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
-  M::template rhs<FRZ>(Y, par, in, ax, frz, K4);
+  M::rhs(Y, par, in, ax, gn, K4);
 #pragma unroll
   for (int i = 0; i < NS; ++i) K4[i] = fma(tab.c43, K3[i], fma(tab.c42, K2[i], fma(tab.c41, K1[i], K4[i])));
-  M::solve(lu, K4);
+  M::solve(lu, tab.luc, K4);
   // stage 5
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     Y[i] = fma(tab.a54, K4[i], fma(tab.a53, K3[i], fma(tab.a52, K2[i], fma(tab.a51, K1[i], y[i]))));
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
-  M::template rhs<FRZ>(Y, par, in, ax, frz, K5);
+  M::rhs(Y, par, in, ax, gn, K5);
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     K5[i] = fma(tab.c54, K4[i], fma(tab.c53, K3[i], fma(tab.c52, K2[i], fma(tab.c51, K1[i], K5[i]))));
-  M::solve(lu, K5);
+  M::solve(lu, tab.luc, K5);
   // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] += K5[i];
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
   double K6[NS];
-  M::template rhs<FRZ>(Y, par, in, ax, frz, K6);
+  M::rhs(Y, par, in, ax, gn, K6);
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     K6[i] = fma(tab.c65, K5[i], fma(tab.c64, K4[i], fma(tab.c63, K3[i], fma(tab.c62, K2[i], fma(tab.c61, K1[i], K6[i])))));
-  M::solve(lu, K6);
+  M::solve(lu, tab.luc, K6);
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] += K6[i];
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
@@ -175,21 +192,21 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   return true;
 }
 
-// Out-of-line slow paths: library transcendentals at every stage (and the anti-windup variant).
-template <class M, bool FRZ>
+// Out-of-line slow path: library transcendentals at every stage.
+template <class M>
 PVDER_NOINLINE void rodas4_exact(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
                                  unsigned frz, Aux& base) {
-  rodas4_core<M, FRZ, true>(y, par, in, tab, frz, base);
+  rodas4_core<M, true>(y, par, in, tab, frz, base);
 }
 
 template <class M>
 PVDER_DEV bool rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
                            unsigned frz, Aux& base) {
-  // One instantiation serves clamped and unclamped envs (the freeze mask is applied with selects):
-  // with a random policy a third of the warps hold a clamped lane late in an episode, so a
-  // separate divergent code path for them would cost far more than the selects.
-  if (!rodas4_core<M, true, false>(y, par, in, tab, frz, base)) {
-    rodas4_exact<M, true>(y, par, in, tab, frz, base);
+  // One instantiation serves clamped and unclamped envs (the clamp enters through the per-row
+  // effective gains): with a random policy two thirds of the warps hold a clamped lane late in an
+  // episode, so a separate divergent code path for them cost 2x there.
+  if (!rodas4_core<M, false>(y, par, in, tab, frz, base)) {
+    rodas4_exact<M>(y, par, in, tab, frz, base);
     return false;
   }
   return true;

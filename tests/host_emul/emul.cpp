@@ -99,8 +99,9 @@ static void rhs_one(const pvder_env_config& cfg, const double* yin, const double
   Inputs in{inp4[0], inp4[1], inp4[2], inp4[3]};
   Aux ax;
   aux_exact<M>(cfg.par, in, y, ax);
-  if (frz) M::template rhs<true>(y, cfg.par, in, ax, frz, ff);
-  else M::template rhs<false>(y, cfg.par, in, ax, 0u, ff);
+  double gn[M::NFRZ];
+  make_gains<M>(cfg.par, frz, gn);
+  M::rhs(y, cfg.par, in, ax, gn, ff);
   for (int i = 0; i < M::NS; ++i) f[i] = ff[i];
 }
 
@@ -115,9 +116,10 @@ static void wsolve_one(const pvder_env_config& cfg, const double* yin, const dou
   aux_exact<M>(cfg.par, in, y, ax);
   double luc[16];
   M::lu_consts(cfg.par, ghinv, luc);
-  if (frz) M::template factor<true>(y, cfg.par, in, ax, frz, ghinv, luc, lu);
-  else M::template factor<false>(y, cfg.par, in, ax, 0u, ghinv, luc, lu);
-  M::solve(lu, bb);
+  double gn[M::NFRZ];
+  make_gains<M>(cfg.par, frz, gn);
+  M::factor(y, cfg.par, in, ax, gn, ghinv, luc, lu);
+  M::solve(lu, luc, bb);
   for (int i = 0; i < M::NS; ++i) b[i] = bb[i];
 }
 

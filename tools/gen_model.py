@@ -16,8 +16,8 @@ as delta = wte - w_grid*t, A.4):
 sin/cos(delta), Ppv(Vdc) and 1/Vdc enter through an ``Aux`` record the stepper maintains
 incrementally (pvder_env_step.cuh), so the generated code is transcendental-free.
 
-The anti-windup clamp (A.3) is a per-row freeze mask sampled by the caller on the half-cycle
-grid: a frozen row has f_r = 0 and W_r = e_r/(h*gamma).
+The anti-windup clamp (A.3) is sampled by the caller on the half-cycle grid and enters as per-row
+effective gains (0 while clamped): a frozen row has f_r = 0 and W_r = e_r/(h*gamma) at no cost.
 
 Run:  python tools/gen_model.py     (sympy needed only here, never at run time)
 """
@@ -26,6 +26,7 @@ import sys
 
 import sympy as sp
 
+CONST_PIVOTS = os.environ.get("PVDER_GEN_CONST_PIVOTS", "off")   # off | reg | bank (measured slower)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
 
@@ -57,6 +58,11 @@ def build(P, mult=1):
         rot = [(sp.Integer(1), sp.Integer(0)), (-sp.Rational(1, 2), -h3), (-sp.Rational(1, 2), h3)]
         alpha = [(sp.Integer(1), sp.Integer(0)), (-sp.Rational(1, 2), h3), (-sp.Rational(1, 2), -h3)]
     p = par
+    # Freezable rows (anti-windup, A.3) are "gain x expression": their gains come in as per-row
+    # effective values g_b (= the parameter, or 0 while the row is clamped), so clamping costs
+    # nothing inside the RHS/Jacobian and a clamped row of W is automatically e_r/(h*gamma).
+    nfrz = 4 * P + 2
+    gs = [sp.Symbol(f"g_{b}") for b in range(nfrz)]
     vR, vI, mR, mI = [], [], [], []
     Q = 0
     Pinv = 0
@@ -86,14 +92,14 @@ def build(P, mult=1):
         rr, ri = rot[k]
         f[o] = p["inv_Lf"] * (-p["Rf"] * iR - vR[k] + sp.Rational(1, 2) * mR[k] * Vdc) + wr * iI
         f[o + 1] = p["inv_Lf"] * (-p["Rf"] * iI - vI[k] + sp.Rational(1, 2) * mI[k] * Vdc) - wr * iR
-        f[o + 2] = p["Ki_GCC"] * uR
-        f[o + 3] = p["Ki_GCC"] * uI
-        f[o + 4] = p["wp"] * (-uR + (rr * irefR - ri * irefI) - iR)
-        f[o + 5] = p["wp"] * (-uI + (ri * irefR + rr * irefI) - iI)
+        f[o + 2] = gs[4 * k] * uR                                                    # Ki_GCC
+        f[o + 3] = gs[4 * k + 1] * uI                                                # Ki_GCC
+        f[o + 4] = gs[4 * k + 2] * (-uR + (rr * irefR - ri * irefI) - iR)           # wp
+        f[o + 5] = gs[4 * k + 3] * (-uI + (ri * irefR + rr * irefI) - iI)           # wp
     inv_Vdc = sp.Symbol("inv_Vdc")
     f[base] = (inp["Ppv"] - Pinv) * p["inv_C"] * inv_Vdc
-    f[base + 1] = p["Ki_DC"] * (inp["Vdcref"] - Vdc)
-    f[base + 2] = -p["Ki_Q"] * (inp["Qref"] - Q)
+    f[base + 1] = gs[4 * P] * (inp["Vdcref"] - Vdc)                                  # Ki_DC
+    f[base + 2] = -gs[4 * P + 1] * (inp["Qref"] - Q)                                 # Ki_Q
     f[base + 3] = p["Ki_PLL"] * vd
     f[base + 4] = p["Kp_PLL"] * vd + xPLL + p["dw"]
     # Jacobian: chain rule through the helper symbols
@@ -121,7 +127,7 @@ def build(P, mult=1):
     for k in range(P):
         frozen_rows += [6 * k + 2, 6 * k + 3, 6 * k + 4, 6 * k + 5]
     frozen_rows += [base + 1, base + 2]
-    return dict(P=P, mult=mult, n=n, names=names, y=y, f=f, J=J, par=par, inp=inp, frozen=frozen_rows,
+    return dict(P=P, mult=mult, n=n, names=names, gs=gs, y=y, f=f, J=J, par=par, inp=inp, frozen=frozen_rows,
                 helpers=(sn, cs, inv_Vdc))
 
 
@@ -203,7 +209,7 @@ def generate(P, mult=1):
     A(f"  static constexpr double PMULT = {float(mult)};         // sum over phases = PMULT * explicit phases")
     A(f"  static constexpr int NNZ_J = {len(J)};")
     nf = len(m["frozen"])
-    A(f"  static constexpr int NFRZ = {nf};   // freeze-mask bits (rows: " +
+    A(f"  static constexpr int NFRZ = {nf};   // freezable rows / freeze-mask bits (rows: " +
       ",".join(m["names"][r] for r in m["frozen"]) + ")")
     A(f"  static constexpr int IDX_VDC = {6 * P};")
     A(f"  static constexpr int IDX_DL = {6 * P + 4};")
@@ -216,21 +222,18 @@ def generate(P, mult=1):
         return out
 
     par_unpack = [f"    const double p_{nme} = par.{nme};" for nme in PAR]
+    gain_unpack = [f"    const double g_{b} = gn[{b}];" for b in range(len(m["frozen"]))]
     # ---------- rhs
-    A("  // Autonomous right-hand side f(y).  frz: bit b set => row frozen_rows[b] is clamped (f = 0).")
-    A("  template <bool FRZ>")
+    A("  // Autonomous right-hand side f(y).  gn[b]: effective gain of freezable row b (0 while clamped).")
     A("  static PVDER_DEV void rhs(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
-    A("                            unsigned frz, double (&f)[NS]) {")
+    A("                            const double (&gn)[NFRZ], double (&f)[NS]) {")
     L.extend(par_unpack)
     L.extend(unpack())
     A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
     A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, inv_Vdc = aux.inv_Vdc;")
+    L.extend(gain_unpack)
     L.extend(emit_block([(f"f[{r}]", f[r]) for r in range(n)], "t"))
-    A("    if (FRZ) {")
-    for b, r in enumerate(m["frozen"]):
-        A(f"      if (frz & {1 << b}u) f[{r}] = 0.0;")
-    A("    }")
     A("  }")
     A("")
     # ---------- factor
@@ -268,7 +271,7 @@ def generate(P, mult=1):
         if op[0] == "inv":
             k = op[1]
             jkk = J.get((k, k), sp.Integer(0))
-            if (k, k) not in touched and jkk.free_symbols <= par_syms:
+            if CONST_PIVOTS != "off" and (k, k) not in touched and jkk.free_symbols <= par_syms:
                 const_piv[k] = len(luc_exprs)
                 luc_exprs.append(1 / (GH - jkk))
         elif op[0] in ("fma", "new"):
@@ -289,14 +292,14 @@ def generate(P, mult=1):
         if r != c:
             A(f"    double {wname(r, c)};")
     for k in range(n):
-        A(f"    double d_{k};")
+        if not (CONST_PIVOTS == "bank" and k in const_piv):
+            A(f"    double d_{k};")
     A("  };")
     nflop_f = sum(2 if o[0] in ("fma",) else 1 for o in ops)
     A(f"  static constexpr int LU_ENTRIES = {len(members)};   // incl. {len(members) - len(pattern)} fill-ins")
     A("")
-    A("  template <bool FRZ>")
     A("  static PVDER_DEV void factor(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
-    A("                               unsigned frz, double ghinv, const double* luc, LU& lu) {")
+    A("                               const double (&gn)[NFRZ], double ghinv, const double* luc, LU& lu) {")
     L.extend(par_unpack)
     L.extend(unpack())
     A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
@@ -304,14 +307,10 @@ def generate(P, mult=1):
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
     A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, in_dPpv = aux.dPpv, inv_Vdc = aux.inv_Vdc;")
     keys = sorted(J.keys())
+    L.extend(gain_unpack)
     for (r, c) in keys:
         A(f"    double j_{r}_{c};")
     L.extend(emit_block([(f"j_{r}_{c}", J[(r, c)]) for (r, c) in keys], "q"))
-    A("    if (FRZ) {")
-    for b, r in enumerate(m["frozen"]):
-        ent = [f"j_{rr}_{cc} = 0.0;" for (rr, cc) in keys if rr == r]
-        A(f"      if (frz & {1 << b}u) {{ " + " ".join(ent) + " }")
-    A("    }")
     # W entries
     for i in range(n):
         if (i, i) in J:
@@ -325,11 +324,7 @@ def generate(P, mult=1):
         if op[0] == "inv":
             k = op[1]
             if k in const_piv:
-                if k in m["frozen"]:
-                    b = m["frozen"].index(k)
-                    A(f"    const double d_{k} = (FRZ && (frz & {1 << b}u)) ? luc[0] : luc[{const_piv[k] + 1}];")
-                else:
-                    A(f"    const double d_{k} = luc[{const_piv[k] + 1}];")
+                A(f"    const double d_{k} = luc[{const_piv[k] + 1}];")
             else:
                 A(f"    const double d_{k} = 1.0 / w_{k}_{k};")
         elif op[0] == "mul":
@@ -345,11 +340,13 @@ def generate(P, mult=1):
         if r != c:
             A(f"    lu.{wname(r, c)} = {wname(r, c)};")
     for k in range(n):
-        A(f"    lu.d_{k} = d_{k};")
+        if not (CONST_PIVOTS == "bank" and k in const_piv):
+            A(f"    lu.d_{k} = d_{k};")
     A("  }")
     A("")
     # ---------- solve
-    A("  static PVDER_DEV void solve(const LU& lu, double (&b)[NS]) {")
+    A("  static PVDER_DEV void solve(const LU& lu, const double* luc, double (&b)[NS]) {")
+    A("    (void)luc;")
     nflop_s = 0
     for k in order:
         for r in sorted(r for r in range(n) if pos[r] > pos[k] and (r, k) in pat):
@@ -359,7 +356,10 @@ def generate(P, mult=1):
         for c in sorted(c for c in range(n) if pos[c] > pos[k] and (k, c) in pat):
             A(f"    b[{k}] = fma(-lu.{wname(k, c)}, b[{c}], b[{k}]);")
             nflop_s += 2
-        A(f"    b[{k}] *= lu.d_{k};")
+        if CONST_PIVOTS == "bank" and k in const_piv:
+            A(f"    b[{k}] *= luc[{const_piv[k] + 1}];")
+        else:
+            A(f"    b[{k}] *= lu.d_{k};")
         nflop_s += 1
     A("  }")
     A("")
