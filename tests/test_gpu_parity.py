@@ -309,3 +309,26 @@ def test_fp64_peak_microbenchmark(cuda):
     tf, ms = C.c_double(), C.c_double()
     _cabi.check(_cabi.load().pvder_fp64_peak(2000, C.byref(tf), C.byref(ms)))
     assert 5.0 < tf.value < 80.0, tf.value
+
+
+def test_dqn_rollout_loop_config5(cuda):
+    """Policy-in-the-loop collect (config 5): CUDA-graph replay equals the eager loop (greedy policy)."""
+    import torch
+    import gym_pvder_b200 as G
+    from gym_pvder_b200.rollout import DQNRollout, make_qnet
+
+    torch.manual_seed(0)
+    qnet = make_qnet(device=cuda)
+    res = []
+    for graph in (False, True):
+        venv = G.PVDERVecEnv(2048, device=cuda, model_type="model_2", auto_reset=True, seed=3)
+        venv.reset()
+        ro = DQNRollout(venv, qnet=qnet, epsilon=0.0, replay_steps=4, use_cuda_graph=graph)
+        stats = ro.collect(5, warmup=2)
+        assert stats["cuda_graph"] == graph and stats["env_steps_per_s"] > 0
+        res.append((venv.sd.clone(), ro.rb_act.clone(), ro.rb_rew.clone(), ro.rb_next.clone()))
+        assert int(ro.rb_act.min()) >= 0 and int(ro.rb_act.max()) <= 4
+        assert bool((venv.steps == 7).all())       # 2 warm-up + 5 timed (graph capture does not execute)
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
+    assert res[0][1].shape == (4, 2048)
