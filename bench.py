@@ -32,7 +32,9 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
     os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version there)
 
-F_ALGO = {"model_1": 2.2e3, "model_2": 12.5e3}   # algorithmic flop per half-cycle sub-step
+# algorithmic flop per half-cycle sub-step: n = 11 -> 2.2 kflop, n = 23 -> 12.5 kflop.  The
+# balanced three-phase reduction integrates 11 states, so it is measured with the n = 11 yardstick.
+F_ALGO = {"model_1": 2.2e3, "model_2": 12.5e3, "model_2_balanced": 2.2e3}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -144,6 +146,8 @@ def main():
     ap.add_argument("--model", default="model_1", choices=["model_1", "model_2"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--n-sim", type=int, default=15)
+    ap.add_argument("--three-phase-mode", default="balanced", choices=["balanced", "general"],
+                    help="model_2 only: balanced reduction on phase a (default) or general 23-state integration")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0: min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -152,7 +156,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     metric, unit = "env-steps/sec", "env-steps/s"
     workload = (f"{args.envs_per_gpu} PVDER-v0 envs per GPU ({args.model}: "
-                f"{'single-phase derId 10, 11 states' if args.model == 'model_1' else 'three-phase derId 50, 23 states'}), "
+                f"{'single-phase derId 10, 11 states' if args.model == 'model_1' else 'three-phase derId 50, 23 states, ' + args.three_phase_mode + ' integration'}), "
                 f"n_sim_time_steps_per_env_step={args.n_sim} ({2 * args.n_sim} half-cycle sub-steps per env step), continuous reward, "
                 f"default voltage events (Philox per-env streams), random actions, auto-reset at 40 s (160 steps/episode)")
     config = {"workload": workload, "envs_per_gpu": args.envs_per_gpu, "total_envs": args.envs_per_gpu * world,
@@ -196,7 +200,8 @@ def main():
     K, Wm = args.steps, args.warmup
     cfg = G.EnvConfig(model_type=args.model, n_sim_time_steps_per_env_step=args.n_sim, max_sim_time=40.0,
                       DISCRETE_REWARD=False, goals_list=["voltage_regulation"], event_mode="philox", seed=2026,
-                      auto_reset=True)
+                      auto_reset=True, balanced_three_phase=(args.three_phase_mode == "balanced"))
+    fkey = "model_2_balanced" if (args.model == "model_2" and args.three_phase_mode == "balanced") else args.model
     env = G.PVDERVecEnv(n, device=dev, env_offset=rank * n, config=cfg)
     env.reset()
     acts = torch.empty((K + Wm, n), dtype=torch.int32, device=dev)
@@ -270,10 +275,10 @@ def main():
     tf, pms = C.c_double(), C.c_double()
     _cabi.check(lib.pvder_fp64_peak(4000, C.byref(tf), C.byref(pms)))
     sub_per_launch = n * 2 * args.n_sim
-    achieved = sub_per_launch * F_ALGO[args.model] / (kernel_ms * 1e-3) * 1e-12
+    achieved = sub_per_launch * F_ALGO[fkey] / (kernel_ms * 1e-3) * 1e-12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
-                "traffic": None, "kernel": f"pvder::step_kernel<Model{'1' if args.model == 'model_1' else '3'}ph>",
-                "kernel_ms": kernel_ms, "flop_per_sub_step": F_ALGO[args.model],
+                "traffic": None, "kernel": "pvder::step_kernel<%s>" % {"model_1": "Model1ph", "model_2": "Model3ph", "model_2_balanced": "Model3phBal"}[fkey],
+                "kernel_ms": kernel_ms, "flop_per_sub_step": F_ALGO[fkey],
                 "peak_source": "FP64 FMA micro-benchmark pvder_fp64_peak run in this process (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm_algorithmic_bytes_per_launch": n * (2 * 8 * _cabi.sd_fields(cfg.n_state) + 4 * 8 + 4 + 44 + 8 + 1),
                 "note": "SURVEY.md 8d: the path is FP64-compute bound, not HBM/tensor; the contract's enum has no fp64 "

@@ -34,7 +34,17 @@ namespace pvder {
 #ifndef PVDER_MINBLOCKS
 #define PVDER_MINBLOCKS 2
 #endif
+#ifndef PVDER_MINBLOCKS_3PH
+#define PVDER_MINBLOCKS_3PH 2
+#endif
 constexpr int BLOCK = PVDER_BLOCK;
+
+// The general three-phase model (23 states, 174 LU entries, five stage vectors) cannot be register
+// resident; it trades registers for occupancy (launch-bounds sweep in profiles/).
+template <class M>
+constexpr int min_blocks() {
+  return (M::NS > 11) ? PVDER_MINBLOCKS_3PH : PVDER_MINBLOCKS;
+}
 
 struct StepArgs {
   double* sd;
@@ -66,7 +76,7 @@ __device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const O
 }
 
 template <class M>
-__global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS) step_kernel(const __grid_constant__ pvder_env_config cfg,
+__global__ void __launch_bounds__(BLOCK, min_blocks<M>()) step_kernel(const __grid_constant__ pvder_env_config cfg,
                                                      const __grid_constant__ RodasTab tab, const StepArgs a) {
   constexpr int NS = M::NS_STORE;   // rows of the stored state (the balanced model integrates 11 of 23)
   __shared__ float stage[BLOCK * PVDER_OBS_DIM];
