@@ -237,6 +237,33 @@ class PVDER(Utilities):
         self.env_events_spec.clear()
         self.env_events_spec.update(current)
 
+    def calc_returns(self, n_episodes=2, action_specs=("random", "inc", "dec", "no_change")):
+        """Average return of fixed policies for every goal (reference PVDER_env.py:458-497, same
+        action mapping: 'inc' -> action 0, 'dec' -> 1, 'no_change' -> 2)."""
+        self.env_average_return = {}
+        saved = self.goals_list
+        for goal in self.env_goal_spec:
+            self.env_average_return[goal] = {}
+            self.goals_list = [goal]
+            for spec in action_specs:
+                total = 0.0
+                for _ in range(n_episodes):
+                    self.reset()
+                    done, ret = False, 0.0
+                    while not done:
+                        action = {"random": None, "inc": 0, "dec": 1, "no_change": 2}[spec]
+                        if action is None:
+                            action = self.action_space.sample()
+                        _, reward, done, _ = self.step(action)
+                        ret += reward
+                    total += ret
+                pv = self.sim.PV_model
+                self.env_average_return[goal][spec] = {"return": total / n_episodes,
+                                                       "ref": [pv.Vdc_ref * self.sim.Vbase, pv.Q_ref * self.sim.Sbase]}
+        self.goals_list = saved
+        self.pp.pprint(self.env_average_return)
+        return self.env_average_return
+
     def seed(self, seed=None):
         self._seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
         return [self._seed]

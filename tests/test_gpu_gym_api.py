@@ -120,3 +120,13 @@ def test_single_env_matches_vector_env(gym, cuda):
     with pytest.raises(AssertionError):
         env.step(9)
     env.close()
+
+
+def test_calc_returns(gym, capsys):                   # reference PVDER_env.py:458-497
+    env = gym.PVDER(goals_list=["voltage_regulation"], n_sim_time_steps_per_env_step=60, max_sim_time=3.0,
+                    DISCRETE_REWARD=True, model_type="model_2", seed=2)
+    res = env.calc_returns(n_episodes=1)
+    assert set(res) == {"voltage_regulation", "power_regulation", "Q_regulation"}
+    assert set(res["Q_regulation"]) == {"random", "inc", "dec", "no_change"}
+    assert res["Q_regulation"]["no_change"]["return"] == -15.0      # 3 steps x (-5): Q is far from 5.5 kVAR
+    env.close()

@@ -332,3 +332,42 @@ def test_dqn_rollout_loop_config5(cuda):
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b)
     assert res[0][1].shape == (4, 2048)
+
+
+def test_full_size_properties_1M(cuda):
+    """BASELINE.json full size (1,048,576 envs): size-independent properties -- determinism,
+    bit-exact integer outputs given the state, Box membership, counters, checkpoint/resume."""
+    import torch
+    from gym_pvder_b200 import _cabi
+
+    n = 1 << 20
+    kw = dict(model_type="model_1", events_spec=H.SAG_SPEC, seed=77, DISCRETE_REWARD=True)
+    a = _venv(cuda, n, **kw)
+    a.reset()
+    for s in range(3):
+        a.step(a.sample_actions())
+    ckpt = (a.sd.clone(), a.si.clone(), a._step_index)          # the state tensors ARE the checkpoint
+    for s in range(3):
+        obs, rew, done, _ = a.step(a.sample_actions())
+    assert bool((obs.abs() <= 10).all()) and bool(torch.isfinite(a.sd).all())
+    assert bool((a.k == 180).all()) and bool((a.steps == 6).all()) and int(a.status.sum()) == 0
+    hist = a.si[_cabi.SI_HIST:_cabi.SI_HIST + 5, :n].sum(0)
+    assert bool((hist == 6).all())
+    # action frequencies ~ uniform over 5 (6 Mi draws)
+    freq = a.si[_cabi.SI_HIST:_cabi.SI_HIST + 5, :n].sum(1).double() / (6 * n)
+    assert float((freq - 0.2).abs().max()) < 2e-3
+    # bit-exact integer reward given the fp64 state, at full size
+    o, r, _ = twin.outputs_twin(a.cfg.par, 1, a.y.cpu().numpy(), a.field("Q_ref").cpu().numpy(),
+                                a.field("Vdc_ref").cpu().numpy(), a.field("Vgrid").cpu().numpy(),
+                                a.field("Sinsol").cpu().numpy(), a.k.cpu().numpy(), a.cfg.max_sim_time, 0, True)
+    np.testing.assert_array_equal(rew.cpu().numpy().astype(np.float64), r)
+    assert set(np.unique(r)) == {1.0, -1.0, -5.0}
+    # resume from the checkpoint in a fresh env object: identical continuation
+    b = _venv(cuda, n, **kw)
+    b.reset()
+    b.sd.copy_(ckpt[0])
+    b.si.copy_(ckpt[1])
+    b._step_index = ckpt[2]
+    for s in range(3):
+        b.step(b.sample_actions())
+    assert torch.equal(a.sd, b.sd) and torch.equal(a.si, b.si) and torch.equal(a.obs, b.obs)
