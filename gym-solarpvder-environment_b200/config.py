@@ -164,9 +164,10 @@ class EnvConfig:
     auto_reset: bool = False
     max_episode_steps: int = 500
     micro: int = 1
-    # three-phase only: integrate the balanced set on phase a (exact for every state the env can
-    # reach: balanced grid, symmetric reset); False = general 23-state integration
-    balanced_three_phase: bool = True
+    # three-phase only.  "auto" (default): each env whose stored state is a balanced set -- the only
+    # kind the env itself creates (balanced grid, symmetric reset) -- is integrated on phase a alone,
+    # any other state by the general 23-state model.  True: always balanced; False: always general.
+    balanced_three_phase: bool | str = "auto"
     config_file: str | None = None
 
     def __post_init__(self):
@@ -227,7 +228,10 @@ class EnvConfig:
         stop_k = _grid_index(v["t_events_stop"], "t_events_stop")
         c.ev_count = max(0, -(-(stop_k - c.ev_start_k) // c.ev_step_k)) if c.event_mode else 0
         c.ev_voltage_enable, c.ev_insol_enable = int(bool(v["ENABLE"])), int(bool(s["ENABLE"]))
-        c.balanced3 = int(bool(self.balanced_three_phase) and self.phases == 3)
+        if self.balanced_three_phase not in (True, False, "auto"):
+            raise ValueError("balanced_three_phase must be True, False or 'auto'")
+        mode = 2 if self.balanced_three_phase == "auto" else int(bool(self.balanced_three_phase))
+        c.balanced3 = mode if self.phases == 3 else 0
         c.ev_v_min, c.ev_v_max = float(v["min"]), float(v["max"])
         c.ev_s_min, c.ev_s_max = float(s["min"]), float(s["max"])
         c.delQ_pu = self.delQref / self.extras["Sbase"]                   # PVDER_env.py:225

@@ -330,6 +330,25 @@ PVDER_DEV void expand_balanced(const double (&y)[11], double (&z)[23]) {
   for (int j = 0; j < 5; ++j) z[18 + j] = y[6 + j];
 }
 
+// True when phases b, c of a stored 23-state vector are phase a rotated by -/+120 degrees (to
+// rounding): the state can then be integrated on phase a alone (Model3phBal).
+PVDER_DEV bool is_balanced(const double (&z)[23]) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 1; k < 3; ++k) {
+    double rr, ri;
+    phase_rot(3, k, rr, ri);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double a = z[2 * j], b = z[2 * j + 1];
+      const double tol = 1e-12 * (fabs(a) + fabs(b)) + 1e-300;
+      ok &= fabs(z[6 * k + 2 * j] - (a * rr - b * ri)) <= tol;
+      ok &= fabs(z[6 * k + 2 * j + 1] - (a * ri + b * rr)) <= tol;
+    }
+  }
+  return ok;
+}
+
 template <int P>
 PVDER_DEV void compute_outputs_p(const pvder_env_config& cfg, const double (&y)[6 * P + 5], double Qref,
                                  double Vdcref, double Vgrid, double Sinsol, int k, Outputs& o) {
@@ -527,6 +546,32 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
     hist_clear = true;
   }
   return run;
+}
+
+
+// Three-phase "auto" mode: a balanced state (the only kind the env itself creates) is integrated by
+// the 11-state balanced model, anything else by the general 23-state model.
+PVDER_DEV bool advance_env_auto3(const pvder_env_config& cfg, const RodasTab& tab, EnvRegs<Model3ph>& r, int act,
+                                 bool active, const double* vtab, const double* stab, int64_t ld, int64_t e,
+                                 uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear) {
+  if (is_balanced(r.y)) {
+    EnvRegs<Model3phBal> b;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) b.y[i] = r.y[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) b.y[6 + i] = r.y[18 + i];
+    b.Qref = r.Qref; b.Vdcref = r.Vdcref; b.Vgrid = r.Vgrid; b.Sinsol = r.Sinsol; b.ret = r.ret;
+    b.last_reward = r.last_reward; b.k = r.k; b.steps = r.steps; b.episode = r.episode; b.status = r.status;
+    b.done = r.done; b.windup = r.windup; b.exact = r.exact;
+    const bool run = advance_env<Model3phBal>(cfg, tab, b, act, active, vtab, stab, ld, e, env_glob, o, done_out,
+                                              hist_inc, hist_clear);
+    expand_balanced(b.y, r.y);
+    r.Qref = b.Qref; r.Vdcref = b.Vdcref; r.Vgrid = b.Vgrid; r.Sinsol = b.Sinsol; r.ret = b.ret;
+    r.last_reward = b.last_reward; r.k = b.k; r.steps = b.steps; r.episode = b.episode; r.status = b.status;
+    r.done = b.done; r.windup = b.windup; r.exact = b.exact;
+    return run;
+  }
+  return advance_env<Model3ph>(cfg, tab, r, act, active, vtab, stab, ld, e, env_glob, o, done_out, hist_inc, hist_clear);
 }
 
 }  // namespace pvder

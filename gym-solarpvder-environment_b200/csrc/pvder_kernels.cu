@@ -75,7 +75,7 @@ __device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const O
   for (int idx = t; idx < total; idx += BLOCK) dst[idx] = stage[idx];
 }
 
-template <class M>
+template <class M, bool AUTO3 = false>
 __global__ void __launch_bounds__(BLOCK, min_blocks<M>()) step_kernel(const __grid_constant__ pvder_env_config cfg,
                                                      const __grid_constant__ RodasTab tab, const StepArgs a) {
   constexpr int NS = M::NS_STORE;   // rows of the stored state (the balanced model integrates 11 of 23)
@@ -105,8 +105,13 @@ __global__ void __launch_bounds__(BLOCK, min_blocks<M>()) step_kernel(const __gr
   Outputs o;
   int done_out, hist_inc;
   bool hist_clear;
-  const bool run = advance_env<M>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
-                                  done_out, hist_inc, hist_clear);
+  bool run;
+  if constexpr (AUTO3)
+    run = advance_env_auto3(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o, done_out,
+                            hist_inc, hist_clear);
+  else
+    run = advance_env<M>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o, done_out,
+                         hist_inc, hist_clear);
 
   if (active) {
     if (a.reward_f64) a.reward_f64[e] = o.reward;
@@ -276,6 +281,7 @@ static int check_cfg(const pvder_env_config* c) {
   if (c->phases != 1 && c->phases != 3) return PVDER_ERR_INVALID;
   if (c->n_sub_per_step < 1 || c->micro < 1 || c->ev_step_k < 1 || c->ev_count < 0) return PVDER_ERR_INVALID;
   if (c->goal < 0 || c->goal > 2) return PVDER_ERR_INVALID;
+  if (c->balanced3 < 0 || c->balanced3 > 2) return PVDER_ERR_INVALID;
   if (c->event_mode < 0 || c->event_mode > 2) return PVDER_ERR_INVALID;
   return PVDER_OK;
 }
@@ -390,8 +396,10 @@ int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld,
   cudaStream_t st = (cudaStream_t)stream;
   const double hinv = cfg->substeps_per_sec * (double)cfg->micro;
   if (cfg->phases == 1) step_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model1ph>(cfg->par, hinv), a);
-  else if (cfg->balanced3)
+  else if (cfg->balanced3 == PVDER_3PH_BALANCED)
     step_kernel<Model3phBal><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3phBal>(cfg->par, hinv), a);
+  else if (cfg->balanced3 == PVDER_3PH_AUTO)
+    step_kernel<Model3ph, true><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3ph>(cfg->par, hinv), a);
   else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3ph>(cfg->par, hinv), a);
   CK(cudaGetLastError());
   return PVDER_OK;

@@ -28,7 +28,7 @@ class PVDERVecEnv:
     def __init__(self, num_envs, device="cuda", seed=0, env_offset=0, model_type="model_2",
                  n_sim_time_steps_per_env_step=15, max_sim_time=40.0, DISCRETE_REWARD=True,
                  goals_list=("voltage_regulation",), events_spec=None, event_mode="philox", auto_reset=False,
-                 obs_f64=False, micro=1, balanced_three_phase=True, config=None):
+                 obs_f64=False, micro=1, balanced_three_phase="auto", config=None):
         import torch
 
         self.torch = torch

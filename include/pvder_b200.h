@@ -50,6 +50,8 @@ enum { PVDER_GOAL_VOLTAGE = 0, PVDER_GOAL_Q = 1, PVDER_GOAL_POWER = 2 };      /*
 enum { PVDER_EVENTS_NONE = 0, PVDER_EVENTS_PHILOX = 1, PVDER_EVENTS_TABLE = 2 };
 enum { PVDER_STATUS_OK = 0, PVDER_STATUS_BAD_ACTION = 1, PVDER_STATUS_NONFINITE = 2,
        PVDER_STATUS_UNBALANCED = 3 /* balanced3 mode met a per-phase duty-cycle clamp */ };
+/* three-phase integration mode (pvder_env_config.balanced3) */
+enum { PVDER_3PH_GENERAL = 0, PVDER_3PH_BALANCED = 1, PVDER_3PH_AUTO = 2 };
 enum { PVDER_OK = 0, PVDER_ERR_INVALID = -1, PVDER_ERR_CUDA = -2, PVDER_ERR_NOMEM = -3 };
 
 /* Per-unit DER parameters (values from config_der.json:2-21 / :66-84). */
@@ -82,7 +84,8 @@ typedef struct pvder_env_config {
   int32_t event_mode;        /* PVDER_EVENTS_* */
   int32_t ev_start_k, ev_step_k, ev_count;   /* event instants on the 1/120 s grid (PVDER_env.py:60-61) */
   int32_t ev_voltage_enable, ev_insol_enable;
-  int32_t balanced3;         /* phases == 3: integrate the balanced set on phase a (b, c = rotated copies) */
+  int32_t balanced3;         /* phases == 3: PVDER_3PH_*: general 23-state integration, balanced set on phase a
+                                (b, c = rotated copies), or per-env auto-detection */
   double ev_v_min, ev_v_max, ev_s_min, ev_s_max;
   double delQ_pu, delVdc_pu; /* per-step reference increments (PVDER_env.py:617-618, :225, :229) */
   double max_sim_time;       /* PVDER_env.py:561-575 */

@@ -12,7 +12,7 @@
 
 using namespace pvder;
 
-template <class M>
+template <class M, bool AUTO3 = false>
 static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
                      const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
                      uint8_t* done, int64_t n, int64_t off) {
@@ -37,8 +37,13 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
     Outputs o;
     int done_out, hist_inc;
     bool hist_clear;
-    const bool run = advance_env<M>(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out,
-                                    hist_inc, hist_clear);
+    bool run;
+    if constexpr (AUTO3)
+      run = advance_env_auto3(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out, hist_inc,
+                              hist_clear);
+    else
+      run = advance_env<M>(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out, hist_inc,
+                           hist_clear);
     if (reward) reward[e] = o.reward;
     if (reward_i) reward_i[e] = o.reward_i;
     if (done) done[e] = (uint8_t)done_out;
@@ -138,7 +143,10 @@ int emul_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, 
               const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i, uint8_t* done,
               int64_t n, int64_t off) {
   if (cfg->phases == 1) step_all<Model1ph>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
-  else if (cfg->balanced3) step_all<Model3phBal>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
+  else if (cfg->balanced3 == PVDER_3PH_BALANCED)
+    step_all<Model3phBal>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
+  else if (cfg->balanced3 == PVDER_3PH_AUTO)
+    step_all<Model3ph, true>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   else step_all<Model3ph>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   return 0;
 }

@@ -146,7 +146,35 @@ def test_balanced_reduction_equals_general_three_phase():
     np.testing.assert_allclose(ib, ia * np.exp(-2j * math.pi / 3), rtol=1e-15, atol=1e-16)
 
 
-@pytest.mark.parametrize("balanced", [True, False])
+def test_three_phase_auto_mode_dispatch():
+    """auto: balanced envs take the phase-a reduction, an unbalanced env the general 23-state model."""
+    kw = dict(model_type="model_2", events_spec=H.SAG_SPEC, seed=4, DISCRETE_REWARD=False)
+    auto = E.EmulVecEnv(4, balanced_three_phase="auto", **kw)
+    gen = E.EmulVecEnv(4, balanced_three_phase=False, **kw)
+    bal = E.EmulVecEnv(4, balanced_three_phase=True, **kw)
+    assert (auto.cfg.c.balanced3, gen.cfg.c.balanced3, bal.cfg.c.balanced3) == (2, 0, 1)
+    for env in (auto, gen, bal):
+        env.reset()
+    # knock env 2 off the balanced manifold (phase b current +1 %)
+    for env in (auto, gen):
+        env.sd[6, 2] *= 1.01
+    for s in range(5):
+        a = twin.sample_actions_twin(4, s, 4, 0)
+        oa, _, _, _ = auto.step(a)
+        og, _, _, _ = gen.step(a)
+        ob, _, _, _ = bal.step(a)
+    # unbalanced env: identical to the general path bit for bit
+    np.testing.assert_array_equal(auto.sd[:, 2], gen.sd[:, 2])
+    assert not np.array_equal(auto.sd[:, 2], bal.sd[:, 2])
+    # balanced envs: identical to the balanced path bit for bit, and equal to the general path to rounding
+    for e in (0, 1, 3):
+        np.testing.assert_array_equal(auto.sd[:, e], bal.sd[:, e])
+        np.testing.assert_allclose(auto.sd[:, e], gen.sd[:, e], rtol=1e-9, atol=1e-11)
+    with pytest.raises(ValueError):
+        G.EnvConfig(model_type="model_2", balanced_three_phase="maybe")
+
+
+@pytest.mark.parametrize("balanced", [True, False, "auto"])
 def test_golden_fixture_three_phase_modes(balanced):
     gold = np.load("tests/golden/golden_model_2.npz")
     acts = gold["actions"]
