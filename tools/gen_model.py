@@ -26,6 +26,10 @@ import sys
 
 import sympy as sp
 
+# explicit inverse of the dense core (currents, Vdc, delta) instead of its LU: same flops per solve,
+# but a 4x4 mat-vec has a 3-deep dependency chain where the triangular solves have ~16.  Measured
+# on B200: 4 % SLOWER (register pressure), hence off by default.  Only for cores of <= 4 unknowns.
+CORE_INVERSE = os.environ.get("PVDER_GEN_CORE_INVERSE", "0") == "1"
 CONST_PIVOTS = os.environ.get("PVDER_GEN_CONST_PIVOTS", "off")   # off | reg | bank (measured slower)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
@@ -372,6 +376,9 @@ def generate(P, mult=1):
                     pat.add((r, c))
                     ops.append(("new", r, c, k))
     members = sorted(pat)
+    nc = 2 * P + 2
+    core = order[-nc:] if (CORE_INVERSE and nc <= 4) else []
+    coreset = set(core)
     # Launch-constant pivots: w_kk is still its initial value ghinv - J_kk when row k is pivoted and
     # J_kk depends on parameters only.  Their reciprocals come from a host-filled table (and a
     # select when the row can be frozen) instead of a division per sub-step.
@@ -402,11 +409,14 @@ def generate(P, mult=1):
     A("  struct LU {")
     A("    // strictly-lower entries hold multipliers, upper entries hold U, d_k = 1/pivot")
     for (r, c) in members:
-        if r != c:
+        if r != c and not (r in coreset and c in coreset):
             A(f"    double {wname(r, c)};")
     for k in range(n):
-        if not (CONST_PIVOTS == "bank" and k in const_piv):
+        if not (CONST_PIVOTS == "bank" and k in const_piv) and k not in coreset:
             A(f"    double d_{k};")
+    for r in core:
+        for c in core:
+            A(f"    double ci_{r}_{c};   // explicit inverse of the dense core")
     A("  };")
     nflop_f = sum(2 if o[0] in ("fma",) else 1 for o in ops)
     A(f"  static constexpr int LU_ENTRIES = {len(members)};   // incl. {len(members) - len(pattern)} fill-ins")
@@ -449,11 +459,45 @@ def generate(P, mult=1):
         else:
             _, r, c, k = op
             A(f"    double {wname(r, c)} = -{wname(r, k)} * {wname(k, c)};")
+    if core:
+        # inverse of the core from its LU (unit-lower multipliers w_r_k, upper w_k_c, d_k = 1/u_kk)
+        cpos = {k: i for i, k in enumerate(core)}
+        has = lambda r, c: (r, c) in pat
+        # Linv (unit lower)
+        for ci_, c in enumerate(core):
+            for r in core[ci_ + 1:]:
+                terms = []
+                if has(r, c):
+                    terms.append(f"{wname(r, c)}")
+                for k in core[ci_ + 1:cpos[r]]:
+                    if has(r, k):
+                        terms.append(f"{wname(r, k)} * li_{k}_{c}")
+                A(f"    const double li_{r}_{c} = -(" + (" + ".join(terms) if terms else "0.0") + ");")
+        # Uinv (upper)
+        for ci_ in range(len(core) - 1, -1, -1):
+            k = core[ci_]
+            A(f"    const double ui_{k}_{k} = d_{k};")
+        for cj in range(len(core)):
+            c = core[cj]
+            for ci_ in range(cj - 1, -1, -1):
+                k = core[ci_]
+                terms = []
+                for j in core[ci_ + 1:cj + 1]:
+                    if has(k, j):
+                        terms.append(f"{wname(k, j)} * ui_{j}_{c}")
+                A(f"    const double ui_{k}_{c} = -d_{k} * (" + (" + ".join(terms) if terms else "0.0") + ");")
+        for r in core:
+            for c in core:
+                terms = []
+                for j in core[max(cpos[r], cpos[c]):]:
+                    li = "1.0" if j == c else f"li_{j}_{c}"
+                    terms.append(f"ui_{r}_{j}" if li == "1.0" else f"ui_{r}_{j} * {li}")
+                A(f"    lu.ci_{r}_{c} = " + " + ".join(terms) + ";")
     for (r, c) in members:
-        if r != c:
+        if r != c and not (r in coreset and c in coreset):
             A(f"    lu.{wname(r, c)} = {wname(r, c)};")
     for k in range(n):
-        if not (CONST_PIVOTS == "bank" and k in const_piv):
+        if not (CONST_PIVOTS == "bank" and k in const_piv) and k not in coreset:
             A(f"    lu.d_{k} = d_{k};")
     A("  }")
     A("")
@@ -462,10 +506,25 @@ def generate(P, mult=1):
     A("    (void)luc;")
     nflop_s = 0
     for k in order:
+        if k in coreset:
+            continue
         for r in sorted(r for r in range(n) if pos[r] > pos[k] and (r, k) in pat):
             A(f"    b[{r}] = fma(-lu.{wname(r, k)}, b[{k}], b[{r}]);")
             nflop_s += 2
+    if core:
+        # core unknowns by a dense mat-vec with the explicit inverse (pairwise sums: depth 3)
+        for r in core:
+            t = [f"lu.ci_{r}_{c} * b[{c}]" for c in core]
+            if len(t) == 4:
+                A(f"    const double cx_{r} = fma(lu.ci_{r}_{core[0]}, b[{core[0]}], {t[1]}) + fma(lu.ci_{r}_{core[2]}, b[{core[2]}], {t[3]});")
+            else:
+                A(f"    const double cx_{r} = " + " + ".join(t) + ";")
+            nflop_s += 2 * len(core) - 1
+        for r in core:
+            A(f"    b[{r}] = cx_{r};")
     for k in reversed(order):
+        if k in coreset:
+            continue
         for c in sorted(c for c in range(n) if pos[c] > pos[k] and (k, c) in pat):
             A(f"    b[{k}] = fma(-lu.{wname(k, c)}, b[{c}], b[{k}]);")
             nflop_s += 2
