@@ -40,6 +40,9 @@ F_ALGO = {"model_1": 2.2e3, "model_2": 12.5e3, "model_2_balanced": 2.2e3}
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm / cpu_baseline: oracle O2 on the host cores
 # ------------------------------------------------------------------------------------------------
+REF_ENV_STEPS_PER_STEP = 64   # reference arm: one bench "step" = this many env steps on every host core
+
+
 def _cpu_worker(args):
     model_type, n_sim, steps, warmup, seed = args
     import random
@@ -166,9 +169,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        v, cores, sample = cpu_reference(args.model, args.n_sim, args.steps, args.warmup)
+        # a "step" of this arm is a bounded sample of the workload: REF_ENV_STEPS_PER_STEP env steps on every core
+        v, cores, sample = cpu_reference(args.model, args.n_sim, args.steps * REF_ENV_STEPS_PER_STEP,
+                                         args.warmup * REF_ENV_STEPS_PER_STEP)
         line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * cores / v, "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": 1e3 * cores * REF_ENV_STEPS_PER_STEP / v, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
                                  "note": "restated reference path (pvder unavailable): oracle O2"},
@@ -238,15 +243,16 @@ def main():
     Ke = args.e2e_steps or min(K, 40)
     h = C.c_void_p()
     _cabi.check(lib.pvder_env_create(C.byref(cfg.c), n, rank * n, C.byref(h)))
-    h_act = torch.empty((8, n), dtype=torch.int32).pin_memory()
-    h_act.copy_(acts[:8].cpu())
+    n_act = min(8, K + Wm)
+    h_act = torch.empty((n_act, n), dtype=torch.int32).pin_memory()
+    h_act.copy_(acts[:n_act].cpu())
     h_obs = torch.empty((n, 11), dtype=torch.float32).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float64).pin_memory()
     h_done = torch.empty(n, dtype=torch.uint8).pin_memory()
     _cabi.check(lib.pvder_env_reset_host(h, C.c_void_p(h_obs.data_ptr()), None))
 
     def host_step(s):
-        _cabi.check(lib.pvder_env_step_host(h, C.c_void_p(h_act[s % 8].data_ptr()), C.c_void_p(h_obs.data_ptr()), None,
+        _cabi.check(lib.pvder_env_step_host(h, C.c_void_p(h_act[s % n_act].data_ptr()), C.c_void_p(h_obs.data_ptr()), None,
                                             C.c_void_p(h_rew.data_ptr()), C.c_void_p(h_done.data_ptr())))
 
     for s in range(3):
@@ -292,9 +298,18 @@ def main():
     except Exception:
         pass
 
+    try:   # DRAM bytes of one launch from the committed ncu --set full capture (not measured in this run)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tr = json.load(fh)
+        tkey = "model_2_general" if (args.model == "model_2" and args.three_phase_mode == "general") else "model_1"
+        roofline["traffic"] = tr[tkey]["bytes"] * (n / tr["envs"])
+        roofline["traffic_source"] = tr[tkey]["source"] + " (ncu dram__bytes_read+write per launch, scaled by envs)"
+    except Exception:
+        pass
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_reference(args.model, args.n_sim, 160, 2, envs_per_core=1)
+        v, cores, sample = cpu_reference(args.model, args.n_sim, 160 * 30, 2, envs_per_core=1)   # ~10-20 s of CPU work
         cpu = {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
                "note": "restated reference path (pvder unavailable): oracle O2"}
 
