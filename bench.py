@@ -149,8 +149,11 @@ def main():
     ap.add_argument("--model", default="model_1", choices=["model_1", "model_2"])
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--n-sim", type=int, default=15)
-    ap.add_argument("--three-phase-mode", default="auto", choices=["auto", "balanced", "general"],
-                    help="model_2 only: balanced reduction on phase a (default) or general 23-state integration")
+    ap.add_argument("--three-phase-mode", default="auto", choices=["auto", "balanced", "general", "split"],
+                    help="model_2 only: auto/balanced reduction on phase a (default), general 23-state integration "
+                         "with one thread per env, or split = general with three lanes per env")
+    ap.add_argument("--grid-unbalance", type=float, nargs=2, default=(1.0, 1.0), metavar=("RB", "RC"),
+                    help="model_2 general/split only: grid magnitude of phases b, c relative to phase a")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0: min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -205,8 +208,8 @@ def main():
     K, Wm = args.steps, args.warmup
     cfg = G.EnvConfig(model_type=args.model, n_sim_time_steps_per_env_step=args.n_sim, max_sim_time=40.0,
                       DISCRETE_REWARD=False, goals_list=["voltage_regulation"], event_mode="philox", seed=2026,
-                      auto_reset=True, balanced_three_phase={"auto": "auto", "balanced": True, "general": False}[args.three_phase_mode])
-    fkey = "model_2_balanced" if (args.model == "model_2" and args.three_phase_mode != "general") else args.model
+                      auto_reset=True, balanced_three_phase=args.three_phase_mode, grid_unbalance_ratio=tuple(args.grid_unbalance))
+    fkey = "model_2_balanced" if (args.model == "model_2" and args.three_phase_mode in ("auto", "balanced")) else args.model
     env = G.PVDERVecEnv(n, device=dev, env_offset=rank * n, config=cfg)
     env.reset()
     acts = torch.empty((K + Wm, n), dtype=torch.int32, device=dev)
@@ -283,7 +286,8 @@ def main():
     sub_per_launch = n * 2 * args.n_sim
     achieved = sub_per_launch * F_ALGO[fkey] / (kernel_ms * 1e-3) * 1e-12
     roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s", "frac": achieved / tf.value,
-                "traffic": None, "kernel": "pvder::step_kernel<%s>" % {"model_1": "Model1ph", "model_2": "Model3ph", "model_2_balanced": "Model3phBal" if args.three_phase_mode == "balanced" else "Model3ph,auto"}[fkey],
+                "traffic": None, "kernel": ("pvder::step_kernel_split3" if (args.model == "model_2" and args.three_phase_mode == "split") else
+                           "pvder::step_kernel<%s>" % {"model_1": "Model1ph", "model_2": "Model3ph", "model_2_balanced": "Model3phBal" if args.three_phase_mode == "balanced" else "Model3ph,auto"}[fkey]),
                 "kernel_ms": kernel_ms, "flop_per_sub_step": F_ALGO[fkey],
                 "peak_source": "FP64 FMA micro-benchmark pvder_fp64_peak run in this process (MEASURED_PEAKS.json has no FP64 entry)",
                 "hbm_algorithmic_bytes_per_launch": n * (2 * 8 * _cabi.sd_fields(cfg.n_state) + 4 * 8 + 4 + 44 + 8 + 1),
@@ -301,7 +305,7 @@ def main():
     try:   # DRAM bytes of one launch from the committed ncu --set full capture (not measured in this run)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             tr = json.load(fh)
-        tkey = "model_2_general" if (args.model == "model_2" and args.three_phase_mode == "general") else "model_1"
+        tkey = args.model if args.model == "model_1" else "model_2_" + args.three_phase_mode   # absent key -> traffic stays null
         roofline["traffic"] = tr[tkey]["bytes"] * (n / tr["envs"])
         roofline["traffic_source"] = tr[tkey]["source"] + " (ncu dram__bytes_read+write per launch, scaled by envs)"
     except Exception:

@@ -17,6 +17,7 @@ SOURCES = ["pvder_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-diag-suppress", "177", "-shared", "-Xcompiler", "-fPIC"]
 
+ABI_VERSION = 2
 MAX_STATES = 23
 OBS_DIM = 11
 N_ACTIONS = 5
@@ -24,6 +25,7 @@ SI_K, SI_STEPS, SI_EPISODE, SI_STATUS, SI_DONE, SI_HIST, SI_WINDUP, SI_EXACT, SI
 GOALS = {"voltage_regulation": 0, "Q_regulation": 1, "power_regulation": 2}
 EVENT_MODES = {"none": 0, "philox": 1, "table": 2}
 STATUS_OK, STATUS_BAD_ACTION, STATUS_NONFINITE, STATUS_UNBALANCED = 0, 1, 2, 3
+THREE_PHASE_MODES = {"general": 0, "balanced": 1, "auto": 2, "split": 3}
 
 
 def sd_fields(ns):
@@ -52,6 +54,7 @@ class EnvConfigC(C.Structure):
         ("delQ_pu", C.c_double), ("delVdc_pu", C.c_double), ("max_sim_time", C.c_double),
         ("substeps_per_sec", C.c_double), ("seed", C.c_uint64), ("Q_ref0", C.c_double), ("Vdc_ref0", C.c_double),
         ("y0", C.c_double * MAX_STATES),
+        ("vg_ratio_b", C.c_double), ("vg_ratio_c", C.c_double),
     ]
 
 
@@ -64,6 +67,7 @@ SIGNATURES = {
     "pvder_error_string": (C.c_char_p, [C.c_int]),
     "pvder_sd_fields": (C.c_size_t, [C.c_int]),
     "pvder_si_fields": (C.c_size_t, []),
+    "pvder_config_size": (C.c_size_t, []),
     "pvder_steady_state": (C.c_int, [C.POINTER(Params), C.c_int, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "pvder_reset": (C.c_int, [_cfgp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _i64, _i64, _vp]),
     "pvder_step": (C.c_int, [_cfgp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
@@ -118,8 +122,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.pvder_abi_version() != 1:
+    if lib.pvder_abi_version() != ABI_VERSION:
         raise RuntimeError("libpvder_b200.so ABI version mismatch; rebuild")
+    if lib.pvder_config_size() != C.sizeof(EnvConfigC):
+        raise RuntimeError("pvder_env_config layout differs between libpvder_b200.so and _cabi.EnvConfigC; rebuild")
     _lib = lib
     return lib
 

@@ -166,8 +166,13 @@ class EnvConfig:
     micro: int = 1
     # three-phase only.  "auto" (default): each env whose stored state is a balanced set -- the only
     # kind the env itself creates (balanced grid, symmetric reset) -- is integrated on phase a alone,
-    # any other state by the general 23-state model.  True: always balanced; False: always general.
+    # any other state by the general 23-state model.  True / "balanced": always balanced; False /
+    # "general": always the general model, one thread per env; "split": the general model with three
+    # lanes per env (one per phase) -- the fast path for unbalanced work.
     balanced_three_phase: bool | str = "auto"
+    # pvder Grid(unbalance_ratio_b, unbalance_ratio_c): magnitude of the phase-b/c grid voltage relative
+    # to phase a.  The reference env always builds Grid(events=...) with 1.0 (PVDER_env.py:372).
+    grid_unbalance_ratio: tuple = (1.0, 1.0)
     config_file: str | None = None
 
     def __post_init__(self):
@@ -228,10 +233,24 @@ class EnvConfig:
         stop_k = _grid_index(v["t_events_stop"], "t_events_stop")
         c.ev_count = max(0, -(-(stop_k - c.ev_start_k) // c.ev_step_k)) if c.event_mode else 0
         c.ev_voltage_enable, c.ev_insol_enable = int(bool(v["ENABLE"])), int(bool(s["ENABLE"]))
-        if self.balanced_three_phase not in (True, False, "auto"):
-            raise ValueError("balanced_three_phase must be True, False or 'auto'")
-        mode = 2 if self.balanced_three_phase == "auto" else int(bool(self.balanced_three_phase))
-        c.balanced3 = mode if self.phases == 3 else 0
+        b3 = self.balanced_three_phase
+        if isinstance(b3, bool):
+            b3 = "balanced" if b3 else "general"
+        if b3 not in _cabi.THREE_PHASE_MODES:
+            raise ValueError("balanced_three_phase must be True, False, 'auto', 'balanced', 'general' or 'split'")
+        rb, rc = (float(r) for r in self.grid_unbalance_ratio)
+        if not (rb > 0.0 and rc > 0.0):
+            raise ValueError("grid_unbalance_ratio entries must be positive")
+        if (rb, rc) != (1.0, 1.0):
+            if self.phases != 3:
+                raise ValueError("grid_unbalance_ratio needs the three-phase model (model_2)")
+            if b3 == "balanced":
+                raise ValueError("an unbalanced grid cannot be integrated by the balanced reduction")
+            if b3 == "auto":
+                b3 = "split"          # every env is unbalanced: all of them take the general model
+        self.three_phase_mode = b3 if self.phases == 3 else "single_phase"
+        c.balanced3 = _cabi.THREE_PHASE_MODES[b3] if self.phases == 3 else 0
+        c.vg_ratio_b, c.vg_ratio_c = rb, rc
         c.ev_v_min, c.ev_v_max = float(v["min"]), float(v["max"])
         c.ev_s_min, c.ev_s_max = float(s["min"]), float(s["max"])
         c.delQ_pu = self.delQref / self.extras["Sbase"]                   # PVDER_env.py:225

@@ -33,11 +33,28 @@ using Params = ::pvder_params;
 
 // Exogenous inputs held constant over one half-cycle sub-step (events frozen per sub-step, A.8).
 struct Inputs {
-  double vg;       // LV-side grid phasor magnitude  = Vgrid_event * par.vgs
+  double vg;       // LV-side grid phasor magnitude  = Vgrid_event * par.vgs  (phase a)
   double Qref;     // external reactive power reference (pu), changed only by actions
   double Vdcref;   // external DC-link reference (pu), changed only by actions
   double np_iph;   // Np * Iph(Sinsol)  (A)
+  double vgb, vgc; // phase b / c magnitudes = vg * grid unbalance ratio (explicit three-phase models only)
 };
+
+// Inputs in force for one sub-step.  Individually rounded ops: vg feeds the discrete reward.
+PVDER_DEV Inputs make_inputs(const pvder_env_config& cfg, double Vgrid, double Qref, double Vdcref, double Sinsol) {
+  Inputs in;
+  in.vg = __dmul_rn(Vgrid, cfg.par.vgs);
+  in.Qref = Qref;
+  in.Vdcref = Vdcref;
+  in.np_iph = __dmul_rn(cfg.par.np_iph100, __ddiv_rn(Sinsol, 100.0));
+  in.vgb = __dmul_rn(in.vg, cfg.vg_ratio_b);
+  in.vgc = __dmul_rn(in.vg, cfg.vg_ratio_c);
+  return in;
+}
+
+PVDER_DEV double vg_of_phase(const Inputs& in, int phases, int k) {
+  return (phases == 1 || k == 0) ? in.vg : ((k == 1) ? in.vgb : in.vgc);
+}
 
 // Transcendental side-inputs of the model at one state: sin/cos of the PLL angle delta, the PV
 // array power and slope (which need exp(kappa*Vdc)) and 1/Vdc.  E = exp(kappa*Vdc) is kept so the

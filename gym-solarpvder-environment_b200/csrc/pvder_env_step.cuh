@@ -45,31 +45,34 @@ inline RodasTab make_rodas_tab(const Params& par, double hinv) {
   return t;
 }
 
-// Aux record at state y with full-accuracy library functions (once per env step, and whenever a
-// stage leaves the incremental range).
-template <class M>
-PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[M::NS], Aux& a) {
-  sincos(y[M::IDX_DL], &a.sn, &a.cs);
-  a.E = exp(par.kappa * y[M::IDX_VDC]);
-  a.inv_Vdc = 1.0 / y[M::IDX_VDC];
-  ppv_from_exp(par, in, y[M::IDX_VDC], a.E, a.Ppv, a.dPpv);
+// Aux record at PLL angle dl and DC voltage V with full-accuracy library functions (once per env
+// step, and whenever a stage leaves the incremental range).
+PVDER_DEV void aux_exact_sv(const Params& par, const Inputs& in, double dl, double V, Aux& a) {
+  sincos(dl, &a.sn, &a.cs);
+  a.E = exp(par.kappa * V);
+  a.inv_Vdc = 1.0 / V;
+  ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
 }
 
-// Aux record at a state Y close to the base state (angle dl0, DC voltage V0, record b):
+template <class M>
+PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[M::NS], Aux& a) {
+  aux_exact_sv(par, in, y[M::IDX_DL], y[M::IDX_VDC], a);
+}
+
+// Aux record at (dl, V) close to the base point (angle dl0, DC voltage V0, record b):
 //   sin/cos(dl0 + d) by rotating (sn0, cs0) through d,  exp(kappa (V0 + dv)) = E0 * exp(kappa dv),
 //   1/V by three Newton steps from 1/V0 -- short polynomials (|d|, |kappa dv| < 2^-4: truncation
 //   below 3e-19) instead of 3 library calls per Rodas stage.  Outside that range (PLL pull-in right
 //   after reset) the step is redone by the EXACT instantiation, which is kept out of line so the
 //   hot loop stays small.
-template <class M, bool EXACT>
-PVDER_DEV void aux_advance(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0,
-                           const double (&Y)[M::NS], Aux& a, bool& out_of_range) {
+template <bool EXACT>
+PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0, double dl,
+                              double V, Aux& a, bool& out_of_range) {
   if (EXACT) {
-    aux_exact<M>(par, in, Y, a);
+    aux_exact_sv(par, in, dl, V, a);
     return;
   }
-  const double d = Y[M::IDX_DL] - dl0;
-  const double V = Y[M::IDX_VDC];
+  const double d = dl - dl0;
   const double dv = V - V0;
   const double x = par.kappa * dv;
   // outside the polynomial range the caller discards this step and redoes it with EXACT = true
@@ -103,6 +106,12 @@ PVDER_DEV void aux_advance(const Params& par, const Inputs& in, const Aux& b, do
     a.inv_Vdc = r;
     ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
   }
+}
+
+template <class M, bool EXACT>
+PVDER_DEV void aux_advance(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0,
+                           const double (&Y)[M::NS], Aux& a, bool& out_of_range) {
+  aux_advance_sv<EXACT>(par, in, b, dl0, V0, Y[M::IDX_DL], Y[M::IDX_VDC], a, out_of_range);
 }
 
 // Effective gains of the freezable rows (bit order of freeze_bits): the parameter, or 0 while the
@@ -241,7 +250,8 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
     const double mR = fma(par.Kp_GCC, y[6 * k + 4], y[6 * k + 2]);
     const double mI = fma(par.Kp_GCC, y[6 * k + 5], y[6 * k + 3]);
     m_over |= (mR * mR + mI * mI) > par.m_limit10 * par.m_limit10;
-    Q += M::PMULT * 0.5 * ((in.vg * ri) * iR - (in.vg * rr) * iI + par.Xt * (iR * iR + iI * iI));
+    const double vgk = M::BALANCED3 ? in.vg : vg_of_phase(in, P, k);
+    Q += M::PMULT * 0.5 * ((vgk * ri) * iR - (vgk * rr) * iI + par.Xt * (iR * iR + iI * iI));
   }
   m_over_out = m_over;
   const double Vdc = y[B], xDC = y[B + 1], xQ = y[B + 2];
@@ -349,32 +359,19 @@ PVDER_DEV bool is_balanced(const double (&z)[23]) {
   return ok;
 }
 
+// Tail of the output computation from the phase sums (shared by the one-thread and the
+// three-lane kernels, so both produce the same bits from the same sums).
 template <int P>
-PVDER_DEV void compute_outputs_p(const pvder_env_config& cfg, const double (&y)[6 * P + 5], double Qref,
-                                 double Vdcref, double Vgrid, double Sinsol, int k, Outputs& o) {
-  constexpr int B = 6 * P;
+PVDER_DEV void finish_outputs(const pvder_env_config& cfg, const Inputs& in, double iaR, double iaI, double vaR,
+                              double vaI, double Ppcc, double Qpcc, double v2, double Vdc, double Qref,
+                              double Vdcref, int k, Outputs& o) {
   const Params& par = cfg.par;
-  const double vg = __dmul_rn(Vgrid, par.vgs);
-  double Ppcc = 0.0, Qpcc = 0.0, v2 = 0.0, vaR = 0.0, vaI = 0.0;
-#pragma unroll
-  for (int ph = 0; ph < P; ++ph) {
-    double rr, ri;
-    phase_rot(P, ph, rr, ri);
-    const double jR = y[6 * ph], jI = y[6 * ph + 1];
-    const double vkR = __dadd_rn(__dmul_rn(vg, rr), __dadd_rn(__dmul_rn(par.Rt, jR), -__dmul_rn(par.Xt, jI)));
-    const double vkI = __dadd_rn(__dmul_rn(vg, ri), __dadd_rn(__dmul_rn(par.Xt, jR), __dmul_rn(par.Rt, jI)));
-    Ppcc = __dadd_rn(Ppcc, __dmul_rn(0.5, __dadd_rn(__dmul_rn(vkR, jR), __dmul_rn(vkI, jI))));
-    Qpcc = __dadd_rn(Qpcc, __dmul_rn(0.5, __dadd_rn(__dmul_rn(vkI, jR), -__dmul_rn(vkR, jI))));
-    v2 = __dadd_rn(v2, __dadd_rn(__dmul_rn(vkR, vkR), __dmul_rn(vkI, vkI)));
-    if (ph == 0) { vaR = vkR; vaI = vkI; }
-  }
   const double SQRT2 = 1.4142135623730951;
   const double Vrms = (P == 1) ? __ddiv_rn(__dsqrt_rn(v2), SQRT2) : __ddiv_rn(__dsqrt_rn(__ddiv_rn(v2, 3.0)), SQRT2);
-  Inputs in{vg, Qref, Vdcref, __dmul_rn(par.np_iph100, __ddiv_rn(Sinsol, 100.0))};
   double Ppv, dPpv;
-  ppv_eval(par, in, y[B], Ppv, dPpv);
-  o.obs[0] = y[0]; o.obs[1] = y[1]; o.obs[2] = vaR; o.obs[3] = vaI; o.obs[4] = Ppcc; o.obs[5] = Qpcc;
-  o.obs[6] = y[B]; o.obs[7] = Ppv; o.obs[8] = Vdcref; o.obs[9] = Qref;
+  ppv_eval(par, in, Vdc, Ppv, dPpv);
+  o.obs[0] = iaR; o.obs[1] = iaI; o.obs[2] = vaR; o.obs[3] = vaI; o.obs[4] = Ppcc; o.obs[5] = Qpcc;
+  o.obs[6] = Vdc; o.obs[7] = Ppv; o.obs[8] = Vdcref; o.obs[9] = Qref;
   o.obs[10] = __ddiv_rn(__ddiv_rn((double)k, cfg.substeps_per_sec), cfg.max_sim_time);
   double x, target, hi;
   if (cfg.goal == PVDER_GOAL_VOLTAGE) { x = Vrms; target = par.Vrms_ref; hi = 0.05; }
@@ -392,13 +389,36 @@ PVDER_DEV void compute_outputs_p(const pvder_env_config& cfg, const double (&y)[
   }
 }
 
+template <int P, bool UNBAL = true>
+PVDER_DEV void compute_outputs_p(const pvder_env_config& cfg, const double (&y)[6 * P + 5], double Qref,
+                                 double Vdcref, double Vgrid, double Sinsol, int k, Outputs& o) {
+  constexpr int B = 6 * P;
+  const Params& par = cfg.par;
+  const Inputs in = make_inputs(cfg, Vgrid, Qref, Vdcref, Sinsol);
+  double Ppcc = 0.0, Qpcc = 0.0, v2 = 0.0, vaR = 0.0, vaI = 0.0;
+#pragma unroll
+  for (int ph = 0; ph < P; ++ph) {
+    double rr, ri;
+    phase_rot(P, ph, rr, ri);
+    const double jR = y[6 * ph], jI = y[6 * ph + 1];
+    const double vg = UNBAL ? vg_of_phase(in, P, ph) : in.vg;   // the balanced reduction carries a balanced grid
+    const double vkR = __dadd_rn(__dmul_rn(vg, rr), __dadd_rn(__dmul_rn(par.Rt, jR), -__dmul_rn(par.Xt, jI)));
+    const double vkI = __dadd_rn(__dmul_rn(vg, ri), __dadd_rn(__dmul_rn(par.Xt, jR), __dmul_rn(par.Rt, jI)));
+    Ppcc = __dadd_rn(Ppcc, __dmul_rn(0.5, __dadd_rn(__dmul_rn(vkR, jR), __dmul_rn(vkI, jI))));
+    Qpcc = __dadd_rn(Qpcc, __dmul_rn(0.5, __dadd_rn(__dmul_rn(vkI, jR), -__dmul_rn(vkR, jI))));
+    v2 = __dadd_rn(v2, __dadd_rn(__dmul_rn(vkR, vkR), __dmul_rn(vkI, vkI)));
+    if (ph == 0) { vaR = vkR; vaI = vkI; }
+  }
+  finish_outputs<P>(cfg, in, y[0], y[1], vaR, vaI, Ppcc, Qpcc, v2, y[B], Qref, Vdcref, k, o);
+}
+
 template <class M>
 PVDER_DEV void compute_outputs(const pvder_env_config& cfg, const double (&y)[M::NS], double Qref, double Vdcref,
                                double Vgrid, double Sinsol, int k, Outputs& o) {
   if constexpr (M::BALANCED3) {
     double z[23];
     expand_balanced(y, z);
-    compute_outputs_p<3>(cfg, z, Qref, Vdcref, Vgrid, Sinsol, k, o);
+    compute_outputs_p<3, false>(cfg, z, Qref, Vdcref, Vgrid, Sinsol, k, o);
   } else {
     compute_outputs_p<M::PHASES>(cfg, y, Qref, Vdcref, Vgrid, Sinsol, k, o);
   }
@@ -486,13 +506,11 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
     int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
     Aux base;
     {
-      Inputs in0{__dmul_rn(r.Vgrid, par.vgs), r.Qref, r.Vdcref,
-                 __dmul_rn(par.np_iph100, __ddiv_rn(r.Sinsol, 100.0))};
+      const Inputs in0 = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
       aux_exact<M>(par, in0, r.y, base);      // library sincos/exp/div once per env step, then incremental
     }
     for (int s = 0; s < cfg.n_sub_per_step; ++s) {
-      Inputs in{__dmul_rn(r.Vgrid, par.vgs), r.Qref, r.Vdcref,
-                __dmul_rn(par.np_iph100, __ddiv_rn(r.Sinsol, 100.0))};
+      const Inputs in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
       bool m_over;
       const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
       if (frz) r.windup += 1;

@@ -25,6 +25,7 @@
 #include "pvder_model_3ph.cuh"
 #include "pvder_model_3ph_bal.cuh"
 #include "pvder_env_step.cuh"
+#include "pvder_split3.cuh"
 
 namespace pvder {
 
@@ -144,6 +145,108 @@ __global__ void __launch_bounds__(BLOCK, min_blocks<M>()) step_kernel(const __gr
     for (int j = 0; j < PVDER_OBS_DIM; ++j) a.obs_f64[e * PVDER_OBS_DIM + j] = o.obs[j];
   }
   if (a.obs_f32) store_obs_block(a.obs_f32, o, block_first, a.n, stage);
+}
+
+
+// Three lanes per environment (pvder_split3.cuh): lanes 3g..3g+2 of a warp integrate phases a, b, c of
+// env g (10 envs per warp; lanes 30 and 31 shadow lanes 27 and 28 and never store).  Each lane loads
+// and stores the six SoA rows of its phase; lane a also owns the shared rows, the counters and the
+// outputs.
+#ifndef PVDER_MINBLOCKS_SPLIT
+#define PVDER_MINBLOCKS_SPLIT 2
+#endif
+constexpr int SPLIT_ENVS_PER_WARP = 10;
+constexpr int SPLIT_ENVS_PER_BLOCK = SPLIT_ENVS_PER_WARP * (BLOCK / 32);
+
+__global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS_SPLIT)
+    step_kernel_split3(const __grid_constant__ pvder_env_config cfg, const __grid_constant__ RodasTab tab, const StepArgs a) {
+  constexpr int NS = 23;
+  __shared__ float stage[SPLIT_ENVS_PER_BLOCK * PVDER_OBS_DIM];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane < 30 ? lane / 3 : SPLIT_ENVS_PER_WARP - 1;
+  const int p = lane < 30 ? lane - 3 * g : lane - 30;
+  const Lanes3 ln{0xffffffffu, 3 * g, p};
+  const int64_t block_first = (int64_t)blockIdx.x * SPLIT_ENVS_PER_BLOCK;
+  const int slot = warp * SPLIT_ENVS_PER_WARP + g;
+  const int64_t e = block_first + slot;
+  const bool active = e < a.n;
+  const int64_t ec = active ? e : (a.n - 1);   // inactive groups shadow the last env and never store
+  const bool writer = active && lane < 30;
+  const bool owner = writer && p == 0;
+
+  EnvRegsSplit r;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) r.y.p[i] = a.sd[(int64_t)(6 * p + i) * a.ld + ec];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r.y.s[i] = a.sd[(int64_t)(18 + i) * a.ld + ec];
+  r.Qref = a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + ec];
+  r.Vdcref = a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + ec];
+  r.Vgrid = a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + ec];
+  r.Sinsol = a.sd[(int64_t)PVDER_SD_SINSOL(NS) * a.ld + ec];
+  r.ret = a.sd[(int64_t)PVDER_SD_RETURN(NS) * a.ld + ec];
+  r.last_reward = a.sd[(int64_t)PVDER_SD_REWARD(NS) * a.ld + ec];
+  r.k = a.si[(int64_t)PVDER_SI_K * a.ld + ec];
+  r.steps = a.si[(int64_t)PVDER_SI_STEPS * a.ld + ec];
+  r.episode = a.si[(int64_t)PVDER_SI_EPISODE * a.ld + ec];
+  r.status = a.si[(int64_t)PVDER_SI_STATUS * a.ld + ec];
+  r.done = a.si[(int64_t)PVDER_SI_DONE * a.ld + ec];
+  r.windup = a.si[(int64_t)PVDER_SI_WINDUP * a.ld + ec];
+  r.exact = a.si[(int64_t)PVDER_SI_EXACT * a.ld + ec];
+  const int act = a.action[ec];
+
+  Outputs o;
+  int done_out, hist_inc;
+  bool hist_clear;
+  // inactive groups run the shadow env too (uniform control flow for the shuffles); they never store
+  const bool run = advance_env_split(ln, cfg, tab, r, act, true, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
+                                     done_out, hist_inc, hist_clear);
+
+  if (owner) {
+    if (a.reward_f64) a.reward_f64[e] = o.reward;
+    if (a.reward_i32) a.reward_i32[e] = o.reward_i;
+    if (a.done) a.done[e] = (uint8_t)done_out;
+  }
+  if (run && writer) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a.sd[(int64_t)(6 * p + i) * a.ld + e] = r.y.p[i];
+  }
+  if (run && owner) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) a.sd[(int64_t)(18 + i) * a.ld + e] = r.y.s[i];
+    a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + e] = r.Qref;
+    a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + e] = r.Vdcref;
+    a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + e] = r.Vgrid;
+    a.sd[(int64_t)PVDER_SD_SINSOL(NS) * a.ld + e] = r.Sinsol;
+    a.sd[(int64_t)PVDER_SD_RETURN(NS) * a.ld + e] = r.ret;
+    a.sd[(int64_t)PVDER_SD_REWARD(NS) * a.ld + e] = r.last_reward;
+    a.si[(int64_t)PVDER_SI_K * a.ld + e] = r.k;
+    a.si[(int64_t)PVDER_SI_STEPS * a.ld + e] = r.steps;
+    a.si[(int64_t)PVDER_SI_EPISODE * a.ld + e] = r.episode;
+    a.si[(int64_t)PVDER_SI_DONE * a.ld + e] = r.done;
+    a.si[(int64_t)PVDER_SI_WINDUP * a.ld + e] = r.windup;
+    a.si[(int64_t)PVDER_SI_EXACT * a.ld + e] = r.exact;
+    if (hist_inc >= 0) a.si[(int64_t)(PVDER_SI_HIST + hist_inc) * a.ld + e] += 1;
+    if (hist_clear) {
+#pragma unroll
+      for (int h = 0; h < PVDER_N_ACTIONS; ++h) a.si[(int64_t)(PVDER_SI_HIST + h) * a.ld + e] = 0;
+    }
+  }
+  if (owner) a.si[(int64_t)PVDER_SI_STATUS * a.ld + e] = r.status;
+  if (a.obs_f64 && owner) {
+#pragma unroll
+    for (int j = 0; j < PVDER_OBS_DIM; ++j) a.obs_f64[e * PVDER_OBS_DIM + j] = o.obs[j];
+  }
+  if (a.obs_f32) {   // coalesced store of the block's obs rows through shared memory
+    if (lane < 30 && p == 0) {
+#pragma unroll
+      for (int j = 0; j < PVDER_OBS_DIM; ++j) stage[slot * PVDER_OBS_DIM + j] = (float)o.obs[j];
+    }
+    __syncthreads();
+    const int64_t rows = min((int64_t)SPLIT_ENVS_PER_BLOCK, a.n - block_first);
+    const int total = (int)rows * PVDER_OBS_DIM;
+    float* dst = a.obs_f32 + block_first * PVDER_OBS_DIM;
+    for (int idx = threadIdx.x; idx < total; idx += BLOCK) dst[idx] = stage[idx];
+  }
 }
 
 struct ResetArgs {
@@ -281,7 +384,11 @@ static int check_cfg(const pvder_env_config* c) {
   if (c->phases != 1 && c->phases != 3) return PVDER_ERR_INVALID;
   if (c->n_sub_per_step < 1 || c->micro < 1 || c->ev_step_k < 1 || c->ev_count < 0) return PVDER_ERR_INVALID;
   if (c->goal < 0 || c->goal > 2) return PVDER_ERR_INVALID;
-  if (c->balanced3 < 0 || c->balanced3 > 2) return PVDER_ERR_INVALID;
+  if (c->balanced3 < 0 || c->balanced3 > 3) return PVDER_ERR_INVALID;
+  if (!(c->vg_ratio_b > 0.0) || !(c->vg_ratio_c > 0.0)) return PVDER_ERR_INVALID;
+  if ((c->vg_ratio_b != 1.0 || c->vg_ratio_c != 1.0) &&
+      (c->phases != 3 || c->balanced3 == PVDER_3PH_BALANCED || c->balanced3 == PVDER_3PH_AUTO))
+    return PVDER_ERR_INVALID;   /* an unbalanced grid needs the general or the split three-phase mode */
   if (c->event_mode < 0 || c->event_mode > 2) return PVDER_ERR_INVALID;
   return PVDER_OK;
 }
@@ -302,6 +409,7 @@ const char* pvder_error_string(int code) {
 
 size_t pvder_sd_fields(int phases) { return PVDER_SD_FIELDS(6 * phases + 5); }
 size_t pvder_si_fields(void) { return PVDER_SI_FIELDS; }
+size_t pvder_config_size(void) { return sizeof(pvder_env_config); }
 
 int pvder_steady_state(const pvder_params* par, int phases, double Vdc, double Vgrid, double Sinsol, double Q_ref,
                        double wte0, double* y0, double* ma0, double* ia0) {
@@ -400,6 +508,10 @@ int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld,
     step_kernel<Model3phBal><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3phBal>(cfg->par, hinv), a);
   else if (cfg->balanced3 == PVDER_3PH_AUTO)
     step_kernel<Model3ph, true><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3ph>(cfg->par, hinv), a);
+  else if (cfg->balanced3 == PVDER_3PH_SPLIT) {
+    const unsigned grid3 = (unsigned)((n_envs + SPLIT_ENVS_PER_BLOCK - 1) / SPLIT_ENVS_PER_BLOCK);
+    step_kernel_split3<<<grid3, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Split3>(cfg->par, hinv), a);
+  }
   else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3ph>(cfg->par, hinv), a);
   CK(cudaGetLastError());
   return PVDER_OK;

@@ -1,0 +1,649 @@
+// General three-phase PV-DER model (23 states) integrated by THREE LANES PER
+// ENVIRONMENT: lane p of a group owns phase p (i, x, u: 6 states) and a replicated copy of the
+// shared tail (Vdc, xDC, xQ, xPLL, delta); the three phases couple only through three sums
+// (reactive power, inverter power, PLL d-axis voltage) that are formed with warp shuffles.
+//
+// Why: one thread cannot hold the 23-state Rodas4 working set (23 states, 174 LU entries, five stage
+// vectors) in 255 registers -- the one-thread kernel moves 160 GB of spill traffic per 1 Mi-env launch
+// (profiles/r1d_step_kernel_3ph_general_ncu_full.csv).  Split by phase, a lane carries the same 11
+// values per vector as the single-phase kernel and no dense LU at all:
+//
+//   W K = b,  W = I/(h g) - J  is block-arrow: per phase a 6x6 block that reduces by hand to a 2x2
+//   system in (KiR, KiI) [x and u rows are eliminated in closed form], bordered by the shared tail.
+//   The phase blocks respond to the border only through beta = (d wr, K_Vdc, d irefR, d irefI); the
+//   border closes on u = (dQ, d vd, K_Vdc), a 3x3 system whose matrix needs 13 three-lane sums per
+//   factorisation and whose right-hand side needs 3 per stage.  Everything else is local FMAs.
+//
+// The same source is the CUDA kernel body (V = double, one lane per phase, shuffles) and -- built as
+// plain C++ for tests/host_emul -- a three-wide value type (V = V3, sums over its elements).
+//
+//   advance_env_split <- PVDER.step  reference gym_PVDER/envs/PVDER_env.py:138-196 (same semantics as
+//                        advance_env in pvder_env_step.cuh; the integrator state is lane-split)
+#pragma once
+#include "pvder_env_step.cuh"
+
+namespace pvder {
+
+// ---------------------------------------------------------------------------------------------
+// Lane abstraction
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+struct Lanes3 {
+  using V = double;   // per-phase value: this lane's phase
+  using B = bool;
+  unsigned mask;      // lanes executing the current (possibly divergent) region
+  int base;           // first lane of the group (phase a)
+  int p;              // phase of this lane
+
+  // sum over the three phases in the fixed order (a + b) + c: identical bits in all three lanes
+  PVDER_DEV double sum3(double v) const {
+    const double a = __shfl_sync(mask, v, base), b = __shfl_sync(mask, v, base + 1), c = __shfl_sync(mask, v, base + 2);
+    return __dadd_rn(__dadd_rn(a, b), c);
+  }
+  PVDER_DEV bool any3(bool b) const { return ((__ballot_sync(mask, b) >> base) & 7u) != 0u; }
+  PVDER_DEV double from_a(double v) const { return __shfl_sync(mask, v, base); }
+  PVDER_DEV double pc(double a, double b, double c) const { return p == 0 ? a : (p == 1 ? b : c); }
+  // the lanes of this region for which pred holds (pred must be uniform within a group)
+  PVDER_DEV Lanes3 sub(bool pred) const {
+    Lanes3 l = *this;
+    l.mask = __ballot_sync(mask, pred);
+    return l;
+  }
+};
+PVDER_DEV double vfma(double a, double b, double c) { return fma(a, b, c); }
+PVDER_DEV double vsel(bool c, double a, double b) { return c ? a : b; }
+PVDER_DEV bool vgt(double a, double b) { return a > b; }
+PVDER_DEV bool vor(bool a, bool b) { return a || b; }
+PVDER_DEV bool vnonfinite(double a) { return !(bool)isfinite(a); }
+PVDER_DEV double vmul_rn(double a, double b) { return __dmul_rn(a, b); }
+PVDER_DEV double vadd_rn(double a, double b) { return __dadd_rn(a, b); }
+#else
+// Host emulation (tests/host_emul only): the three lanes of a group as one three-wide value.
+struct V3 {
+  double v[3];
+  V3() : v{0.0, 0.0, 0.0} {}
+  V3(double s) : v{s, s, s} {}
+  V3(double a, double b, double c) : v{a, b, c} {}
+};
+struct B3 {
+  bool v[3];
+};
+#define PVDER_V3_BIN(op)                                                        \
+  inline V3 operator op(const V3& a, const V3& b) {                             \
+    return V3(a.v[0] op b.v[0], a.v[1] op b.v[1], a.v[2] op b.v[2]);            \
+  }
+PVDER_V3_BIN(+)
+PVDER_V3_BIN(-)
+PVDER_V3_BIN(*)
+PVDER_V3_BIN(/)
+#undef PVDER_V3_BIN
+inline V3 operator-(const V3& a) { return V3(-a.v[0], -a.v[1], -a.v[2]); }
+inline V3 vfma(const V3& a, const V3& b, const V3& c) {
+  return V3(std::fma(a.v[0], b.v[0], c.v[0]), std::fma(a.v[1], b.v[1], c.v[1]), std::fma(a.v[2], b.v[2], c.v[2]));
+}
+inline double vfma(double a, double b, double c) { return std::fma(a, b, c); }
+inline V3 vsel(const B3& c, const V3& a, const V3& b) {
+  return V3(c.v[0] ? a.v[0] : b.v[0], c.v[1] ? a.v[1] : b.v[1], c.v[2] ? a.v[2] : b.v[2]);
+}
+inline B3 vgt(const V3& a, const V3& b) { return B3{{a.v[0] > b.v[0], a.v[1] > b.v[1], a.v[2] > b.v[2]}}; }
+inline B3 vor(const B3& a, const B3& b) { return B3{{a.v[0] || b.v[0], a.v[1] || b.v[1], a.v[2] || b.v[2]}}; }
+inline B3 vnonfinite(const V3& a) { return B3{{!std::isfinite(a.v[0]), !std::isfinite(a.v[1]), !std::isfinite(a.v[2])}}; }
+inline V3 vmul_rn(const V3& a, const V3& b) { return a * b; }
+inline V3 vadd_rn(const V3& a, const V3& b) { return a + b; }
+struct Lanes3 {
+  using V = V3;
+  using B = B3;
+  double sum3(const V3& v) const { return (v.v[0] + v.v[1]) + v.v[2]; }
+  bool any3(const B3& b) const { return b.v[0] || b.v[1] || b.v[2]; }
+  double from_a(const V3& v) const { return v.v[0]; }
+  V3 pc(double a, double b, double c) const { return V3(a, b, c); }
+  Lanes3 sub(bool) const { return *this; }
+};
+#endif
+
+PVDER_DEV Lanes3::B vsame_sign(const Lanes3::V& a, const Lanes3::V& b) {
+  // np.sign(a) == np.sign(b)  (pvder's clamping test)
+  const Lanes3::V z(0.0);
+  const Lanes3::B ap = vgt(a, z), an = vgt(z, a), bp = vgt(b, z), bn = vgt(z, b);
+#ifdef __CUDACC__
+  return (ap == bp) && (an == bn);
+#else
+  return B3{{(ap.v[0] == bp.v[0]) && (an.v[0] == bn.v[0]), (ap.v[1] == bp.v[1]) && (an.v[1] == bn.v[1]),
+             (ap.v[2] == bp.v[2]) && (an.v[2] == bn.v[2])}};
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// Model
+// ---------------------------------------------------------------------------------------------
+struct Split3 {
+  using L = Lanes3;
+  using V = L::V;
+  using B = L::B;
+  static constexpr int NS = 23;
+  static constexpr int NS_STORE = 23;
+  static constexpr int PHASES = 3;
+  static constexpr int N_LUC = 2;
+
+  // luc[0] = 1/ghinv, luc[1] = 1/(ghinv + wp): reciprocal pivots of a clamped / free u row
+  static PVDER_HD void lu_consts(const Params& par, double ghinv, double* luc) {
+    luc[0] = 1.0 / ghinv;
+    luc[1] = 1.0 / (ghinv + par.wp);
+  }
+
+  // One lane's share of a 23-vector: p = (iR, iI, xR, xI, uR, uI) of its phase, s = (Vdc, xDC, xQ,
+  // xPLL, delta) replicated in the three lanes.
+  struct Vec {
+    V p[6];
+    double s[5];
+  };
+  struct Consts {     // phasor rotation of this phase and the abc->dq angle offset (cos, sin)
+    V rr, ri, ca, sa;
+  };
+  struct In {
+    V vgR, vgI;       // LV-side grid phasor of this phase (unbalance ratio and rotation applied)
+    double Qref, Vdcref;
+  };
+  struct Gains {      // effective gains of the freezable rows (0 while clamped)
+    V g0, g1, g2, g3; // xR, xI (Ki_GCC) ; uR, uI (wp)
+    V duR, duI;       // 1/(ghinv + g2), 1/(ghinv + g3)
+    double g4, g5;    // xDC (Ki_DC), xQ (Ki_Q)
+    bool any;
+  };
+  struct Pt {         // algebraic quantities at one state (A.2)
+    V vR, vI, mR, mI, ck, sk;
+    double Qp, Ps, vd, wex, wr, dV, dQ, irefR, irefI;
+  };
+
+  static PVDER_DEV Consts consts(const L& ln) {
+    constexpr double C3 = 0.86602540378443864676;
+    Consts k;
+    k.rr = ln.pc(1.0, -0.5, -0.5);
+    k.ri = ln.pc(0.0, -C3, C3);
+    k.ca = ln.pc(1.0, -0.5, -0.5);
+    k.sa = ln.pc(0.0, C3, -C3);
+    return k;
+  }
+
+  static PVDER_DEV In inputs(const L& ln, const Consts& k, const Inputs& in) {
+    In o;
+    const V vgk = ln.pc(in.vg, in.vgb, in.vgc);
+    o.vgR = vmul_rn(vgk, k.rr);
+    o.vgI = vmul_rn(vgk, k.ri);
+    o.Qref = in.Qref;
+    o.Vdcref = in.Vdcref;
+    return o;
+  }
+
+  static PVDER_DEV Pt point(const L& ln, const Params& par, const Consts& k, const In& in, const Aux& ax, const Vec& Y) {
+    Pt q;
+    const V iR = Y.p[0], iI = Y.p[1];
+    q.vR = vfma(par.Rt, iR, vfma(-par.Xt, iI, in.vgR));
+    q.vI = vfma(par.Xt, iR, vfma(par.Rt, iI, in.vgI));
+    q.mR = vfma(par.Kp_GCC, Y.p[4], Y.p[2]);
+    q.mI = vfma(par.Kp_GCC, Y.p[5], Y.p[3]);
+    const V qs = vfma(q.vI, iR, -(q.vR * iI));
+    const V ps = vfma(q.mR, iR, q.mI * iI);
+    q.ck = vfma(ax.cs, k.ca, ax.sn * k.sa);        // cos(delta - alpha_p)
+    q.sk = vfma(ax.sn, k.ca, -(ax.cs * k.sa));     // sin(delta - alpha_p)
+    const V vdk = vfma(q.vR, q.ck, q.vI * q.sk);
+    q.Qp = 0.5 * ln.sum3(qs);
+    q.Ps = ln.sum3(ps);
+    q.vd = (1.0 / 3.0) * ln.sum3(vdk);             // positive-sequence d-axis voltage (A.4)
+    q.wex = fma(par.Kp_PLL, q.vd, Y.s[3]);
+    q.wr = (q.wex + par.w0) * par.inv_wb;
+    q.dV = in.Vdcref - Y.s[0];
+    q.dQ = in.Qref - q.Qp;
+    q.irefR = fma(par.Kp_DC, q.dV, Y.s[1]);
+    q.irefI = fma(-par.Kp_Q, q.dQ, Y.s[2]);
+    return q;
+  }
+
+  // Autonomous right-hand side (A.3) from the point record.
+  static PVDER_DEV void rhs(const Params& par, const Consts& k, const Aux& ax, const Gains& g, const Vec& Y, const Pt& q,
+                            Vec& F) {
+    const double hV = 0.5 * Y.s[0];
+    const V iR = Y.p[0], iI = Y.p[1];
+    F.p[0] = vfma(q.wr, iI, par.inv_Lf * vfma(q.mR, hV, vfma(-par.Rf, iR, -q.vR)));
+    F.p[1] = vfma(-q.wr, iR, par.inv_Lf * vfma(q.mI, hV, vfma(-par.Rf, iI, -q.vI)));
+    F.p[2] = g.g0 * Y.p[4];
+    F.p[3] = g.g1 * Y.p[5];
+    const V rfR = vfma(k.rr, q.irefR, -(k.ri * q.irefI)), rfI = vfma(k.ri, q.irefR, k.rr * q.irefI);
+    F.p[4] = g.g2 * ((rfR - Y.p[4]) - iR);
+    F.p[5] = g.g3 * ((rfI - Y.p[5]) - iI);
+    F.s[0] = fma(-0.25 * Y.s[0], q.Ps, ax.Ppv) * (par.inv_C * ax.inv_Vdc);
+    F.s[1] = g.g4 * q.dV;
+    F.s[2] = -(g.g5 * q.dQ);
+    F.s[3] = par.Ki_PLL * q.vd;
+    F.s[4] = q.wex + par.dw;
+  }
+
+  // Factors of W = I/(h g) - J(y) in block-arrow form (see the file header).
+  struct Fac {
+    V n11, n22, n12;     // inverse of the 2x2 current block [[A_R, -c], [c, A_I]] = [[n11, n12], [-n12, n22]]
+    V thR, thI;          // d(m)/d(Ku): g0/ghinv + Kp_GCC
+    V kaR, kaI;          // du * g2: feedback of (iref - Ki) into Ku
+    V epR, epI;          // e * th * ka
+    V hmR, hmI;          // 0.5 inv_Lf m: response of the current rows to K_Vdc
+    V qR, qI, dR, dI, pR, pI;   // rows of dQ, d vd, d Ps with respect to (KiR, KiI)
+    V gxR, gxI;          // g0/ghinv, g1/ghinv
+    double e;            // inv_Lf Vdc / 2
+    double RQ[3], Rv[3], RP[3];   // response of the three sums to beta_1 (d wr), beta_3, beta_4 (d iref)
+    double N[9];         // inverse of the 3x3 border matrix, row-major
+    double vdd;          // d vd / d delta
+    double piw, piD, piQ, pid, g4h, g5h;
+  };
+
+  static PVDER_DEV void factor(const L& ln, const Params& par, const Consts& k, const In& in, const Aux& ax,
+                               const Gains& g, const Vec& y, const Pt& q, double ghinv, const double* luc, Fac& f) {
+    const double inv_gh = luc[0];
+    const V iR = y.p[0], iI = y.p[1];
+    f.e = par.inv_Lf * (0.5 * y.s[0]);
+    const double a = fma(par.inv_Lf, par.Rf + par.Rt, ghinv);
+    const double c = fma(par.inv_Lf, par.Xt, q.wr);
+    f.gxR = g.g0 * inv_gh;
+    f.gxI = g.g1 * inv_gh;
+    f.thR = f.gxR + par.Kp_GCC;
+    f.thI = f.gxI + par.Kp_GCC;
+    f.kaR = g.duR * g.g2;
+    f.kaI = g.duI * g.g3;
+    const V tkR = f.thR * f.kaR, tkI = f.thI * f.kaI;
+    f.epR = f.e * tkR;
+    f.epI = f.e * tkI;
+    const V AR = f.epR + a, AI = f.epI + a;
+    const V det = vfma(AR, AI, V(c * c));
+    const V idet = V(1.0) / det;
+    f.n11 = AI * idet;
+    f.n22 = AR * idet;
+    f.n12 = c * idet;
+    f.hmR = (0.5 * par.inv_Lf) * q.mR;
+    f.hmI = (0.5 * par.inv_Lf) * q.mI;
+    f.qR = vfma(par.Xt, iR, 0.5 * in.vgI);       // d Qp / d iR = 0.5 (vgI + 2 Xt iR)
+    f.qI = vfma(par.Xt, iI, -0.5 * in.vgR);
+    f.dR = (1.0 / 3.0) * vfma(par.Rt, q.ck, par.Xt * q.sk);
+    f.dI = (1.0 / 3.0) * vfma(par.Rt, q.sk, -(par.Xt * q.ck));
+    f.pR = vfma(-iR, tkR, q.mR);
+    f.pI = vfma(-iI, tkI, q.mI);
+    // response of (KiR, KiI) to the four border columns, then the three sums of each
+    const V c1R = vfma(f.n11, iI, -(f.n12 * iR)), c1I = vfma(-f.n12, iI, -(f.n22 * iR));          // d wr : (iI, -iR)
+    const V c2R = vfma(f.n11, f.hmR, f.n12 * f.hmI), c2I = vfma(-f.n12, f.hmR, f.n22 * f.hmI);    // K_Vdc : (hmR, hmI)
+    const V e3R = f.epR * k.rr, e3I = f.epI * k.ri;                                               // d irefR
+    const V c3R = vfma(f.n11, e3R, f.n12 * e3I), c3I = vfma(-f.n12, e3R, f.n22 * e3I);
+    const V e4R = -(f.epR * k.ri), e4I = f.epI * k.rr;                                            // d irefI
+    const V c4R = vfma(f.n11, e4R, f.n12 * e4I), c4I = vfma(-f.n12, e4R, f.n22 * e4I);
+    const V uR = iR * tkR, uI = iI * tkI;    // direct part of d Ps / d iref through Ku
+    const double RQ1 = ln.sum3(vfma(f.qR, c1R, f.qI * c1I)), RQ2 = ln.sum3(vfma(f.qR, c2R, f.qI * c2I));
+    const double RQ3 = ln.sum3(vfma(f.qR, c3R, f.qI * c3I)), RQ4 = ln.sum3(vfma(f.qR, c4R, f.qI * c4I));
+    const double Rv1 = ln.sum3(vfma(f.dR, c1R, f.dI * c1I)), Rv2 = ln.sum3(vfma(f.dR, c2R, f.dI * c2I));
+    const double Rv3 = ln.sum3(vfma(f.dR, c3R, f.dI * c3I)), Rv4 = ln.sum3(vfma(f.dR, c4R, f.dI * c4I));
+    const double RP1 = ln.sum3(vfma(f.pR, c1R, f.pI * c1I)), RP2 = ln.sum3(vfma(f.pR, c2R, f.pI * c2I));
+    const double RP3 = ln.sum3(vfma(f.pR, c3R, vfma(f.pI, c3I, vfma(uR, k.rr, uI * k.ri))));
+    const double RP4 = ln.sum3(vfma(f.pR, c4R, vfma(f.pI, c4I, vfma(uI, k.rr, -(uR * k.ri)))));
+    f.vdd = (1.0 / 3.0) * ln.sum3(vfma(q.vI, q.ck, -(q.vR * q.sk)));
+    f.RQ[0] = RQ1; f.RQ[1] = RQ3; f.RQ[2] = RQ4;
+    f.Rv[0] = Rv1; f.Rv[1] = Rv3; f.Rv[2] = Rv4;
+    f.RP[0] = RP1; f.RP[1] = RP3; f.RP[2] = RP4;
+    const double kpll = fma(par.Ki_PLL, inv_gh, par.Kp_PLL);
+    f.piw = par.inv_wb * kpll;
+    f.pid = kpll * inv_gh;
+    f.g4h = g.g4 * inv_gh;
+    f.g5h = g.g5 * inv_gh;
+    f.piD = f.g4h + par.Kp_DC;
+    f.piQ = f.g5h + par.Kp_Q;
+    const double qC = 0.25 * par.inv_C;
+    const double jVV = par.inv_C * ax.inv_Vdc * fma(-ax.Ppv, ax.inv_Vdc, ax.dPpv);
+    // border matrix in u = (dQ, d vd, K_Vdc)
+    const double m00 = fma(-RQ4, f.piQ, 1.0), m01 = -(RQ1 * f.piw), m02 = fma(f.piD, RQ3, -RQ2);
+    const double m10 = -(Rv4 * f.piQ), m11 = fma(-f.vdd, f.pid, fma(-Rv1, f.piw, 1.0)), m12 = fma(f.piD, Rv3, -Rv2);
+    const double m20 = qC * (RP4 * f.piQ), m21 = qC * (RP1 * f.piw), m22 = fma(qC, fma(-f.piD, RP3, RP2), ghinv - jVV);
+    const double k00 = fma(m11, m22, -(m12 * m21)), k01 = fma(m02, m21, -(m01 * m22)), k02 = fma(m01, m12, -(m02 * m11));
+    const double k10 = fma(m12, m20, -(m10 * m22)), k11 = fma(m00, m22, -(m02 * m20)), k12 = fma(m02, m10, -(m00 * m12));
+    const double k20 = fma(m10, m21, -(m11 * m20)), k21 = fma(m01, m20, -(m00 * m21)), k22 = fma(m00, m11, -(m01 * m10));
+    const double dt = fma(m00, k00, fma(m01, k10, m02 * k20));
+    const double idt = 1.0 / dt;
+    f.N[0] = k00 * idt; f.N[1] = k01 * idt; f.N[2] = k02 * idt;
+    f.N[3] = k10 * idt; f.N[4] = k11 * idt; f.N[5] = k12 * idt;
+    f.N[6] = k20 * idt; f.N[7] = k21 * idt; f.N[8] = k22 * idt;
+  }
+
+  // b <- W^-1 b
+  static PVDER_DEV void solve(const L& ln, const Params& par, const Consts& k, const Gains& g, const Fac& f,
+                              const Vec& y, double inv_gh, Vec& b) {
+    const V iR = y.p[0], iI = y.p[1];
+    const V hxR = b.p[2] * inv_gh, hxI = b.p[3] * inv_gh;
+    const V buR = g.duR * b.p[4], buI = g.duI * b.p[5];
+    const V mmR = vfma(f.thR, buR, hxR), mmI = vfma(f.thI, buI, hxI);
+    const V rR = vfma(f.e, mmR, b.p[0]), rI = vfma(f.e, mmI, b.p[1]);
+    const V tR = vfma(f.n11, rR, f.n12 * rI), tI = vfma(f.n22, rI, -(f.n12 * rR));
+    const double sQ = ln.sum3(vfma(f.qR, tR, f.qI * tI));
+    const double sv = ln.sum3(vfma(f.dR, tR, f.dI * tI));
+    const double sP = ln.sum3(vfma(f.pR, tR, vfma(f.pI, tI, vfma(iR, mmR, iI * mmI))));
+    const double b3 = inv_gh * b.s[1], b4 = inv_gh * b.s[2], hp = inv_gh * b.s[3];
+    const double b1 = par.inv_wb * hp;
+    const double kd0 = (b.s[4] + hp) * inv_gh;
+    const double r1 = fma(f.RQ[0], b1, fma(f.RQ[1], b3, fma(f.RQ[2], b4, sQ)));
+    const double r2 = fma(f.vdd, kd0, fma(f.Rv[0], b1, fma(f.Rv[1], b3, fma(f.Rv[2], b4, sv))));
+    const double cP = fma(f.RP[0], b1, fma(f.RP[1], b3, fma(f.RP[2], b4, sP)));
+    const double r3 = fma(-0.25 * par.inv_C, cP, b.s[0]);
+    const double dQ = fma(f.N[0], r1, fma(f.N[1], r2, f.N[2] * r3));
+    const double dvd = fma(f.N[3], r1, fma(f.N[4], r2, f.N[5] * r3));
+    const double KV = fma(f.N[6], r1, fma(f.N[7], r2, f.N[8] * r3));
+    const double be1 = fma(f.piw, dvd, b1);
+    const double be3 = fma(-f.piD, KV, b3);
+    const double be4 = fma(f.piQ, dQ, b4);
+    const V rfR = vfma(k.rr, be3, -(k.ri * be4)), rfI = vfma(k.ri, be3, k.rr * be4);
+    const V r2R = vfma(iI, be1, vfma(f.hmR, KV, vfma(f.epR, rfR, rR)));
+    const V r2I = vfma(-iR, be1, vfma(f.hmI, KV, vfma(f.epI, rfI, rI)));
+    const V KiR = vfma(f.n11, r2R, f.n12 * r2I), KiI = vfma(f.n22, r2I, -(f.n12 * r2R));
+    const V KuR = vfma(f.kaR, rfR - KiR, buR), KuI = vfma(f.kaI, rfI - KiI, buI);
+    b.p[0] = KiR;
+    b.p[1] = KiI;
+    b.p[2] = vfma(f.gxR, KuR, hxR);
+    b.p[3] = vfma(f.gxI, KuI, hxI);
+    b.p[4] = KuR;
+    b.p[5] = KuI;
+    b.s[0] = KV;
+    b.s[1] = fma(-f.g4h, KV, b3);
+    b.s[2] = fma(f.g5h, dQ, b4);
+    b.s[3] = fma(par.Ki_PLL * inv_gh, dvd, hp);
+    b.s[4] = fma(f.pid, dvd, kd0);
+  }
+
+  // Anti-windup mode (A.3) sampled at the sub-step start; same decisions as freeze_bits<Model3ph>.
+  static PVDER_DEV Gains gains(const L& ln, const Params& par, const Consts& k, const In& in, const Vec& y,
+                               const double* luc, bool& m_over_out) {
+    Gains g;
+    const V iR = y.p[0], iI = y.p[1];
+    const V mR = vfma(par.Kp_GCC, y.p[4], y.p[2]), mI = vfma(par.Kp_GCC, y.p[5], y.p[3]);
+    const bool m_over = ln.any3(vgt(mR * mR + mI * mI, V(par.m_limit10 * par.m_limit10)));
+    const double Q = ln.sum3(0.5 * (in.vgI * iR - in.vgR * iI + par.Xt * (iR * iR + iI * iI)));
+    const double Vdc = y.s[0], xDC = y.s[1], xQ = y.s[2];
+    const double irefR = xDC + par.Kp_DC * (in.Vdcref - Vdc);
+    const double irefI = xQ - par.Kp_Q * (in.Qref - Q);
+    const bool i_over = (irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit;
+    m_over_out = m_over;
+    const V zero(0.0), kig(par.Ki_GCC), wp(par.wp), du_free(luc[1]), du_frz(luc[0]);
+    g.g0 = kig; g.g1 = kig; g.g2 = wp; g.g3 = wp;
+    g.duR = du_free; g.duI = du_free;
+    g.g4 = par.Ki_DC; g.g5 = par.Ki_Q;
+    g.any = false;
+    if (!(m_over || i_over)) return g;
+    bool any = false;
+    if (m_over) {
+      const V uR = y.p[4], uI = y.p[5];
+      const V duR = par.wp * (-uR + (k.rr * irefR - k.ri * irefI) - iR);
+      const V duI = par.wp * (-uI + (k.ri * irefR + k.rr * irefI) - iI);
+      const B f0 = vsame_sign(par.Ki_GCC * uR, y.p[2]), f1 = vsame_sign(par.Ki_GCC * uI, y.p[3]);
+      const B f2 = vsame_sign(duR, uR), f3 = vsame_sign(duI, uI);
+      g.g0 = vsel(f0, zero, kig); g.g1 = vsel(f1, zero, kig);
+      g.g2 = vsel(f2, zero, wp); g.g3 = vsel(f3, zero, wp);
+      g.duR = vsel(f2, du_frz, du_free); g.duI = vsel(f3, du_frz, du_free);
+      any = ln.any3(vor(vor(f0, f1), vor(f2, f3)));
+    }
+    if (i_over) {
+      if (same_sign(par.Ki_DC * (in.Vdcref - Vdc), xDC)) { g.g4 = 0.0; any = true; }
+      if (same_sign(-par.Ki_Q * (in.Qref - Q), xQ)) { g.g5 = 0.0; any = true; }
+    }
+    g.any = any;
+    return g;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Rodas4 half-cycle step on the lane-split state (same scheme, coefficients and incremental
+// side-inputs as rodas4_core).  K1..K4 are folded into the stage-5/6 sums as soon as K4 exists, so
+// at most five lane-vectors are live.
+// ---------------------------------------------------------------------------------------------
+template <bool EXACT>
+PVDER_DEV bool rodas4_core_split(const Lanes3& ln, Split3::Vec& y, const pvder_env_config& cfg, const Inputs& in_s,
+                                 const Split3::In& in, const Split3::Consts& k, const RodasTab& tab,
+                                 const Split3::Gains& g, Aux& base) {
+  using S = Split3;
+  using Vec = S::Vec;
+  const Params& par = cfg.par;
+  const double inv_gh = tab.luc[0];
+  bool oor = false;
+  const double dl0 = y.s[4], V0 = y.s[0];
+  ppv_from_exp(par, in_s, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
+  Vec K1, K2, K3, K4, Y;
+  Aux ax;
+  S::Fac fac;
+  {
+    const S::Pt q = S::point(ln, par, k, in, base, y);
+    S::factor(ln, par, k, in, base, g, y, q, tab.ghinv, tab.luc, fac);
+    S::rhs(par, k, base, g, y, q, K1);
+  }
+  S::solve(ln, par, k, g, fac, y, inv_gh, K1);
+  // the same statement on the six per-phase slots (V) and the five shared slots (double)
+#define PVDER_EACH(ST)                                        \
+  _Pragma("unroll") for (int i = 0; i < 6; ++i) { ST(p) }     \
+  _Pragma("unroll") for (int i = 0; i < 5; ++i) { ST(s) }
+  // stage 2
+#define ST(m) Y.m[i] = vfma(tab.a21, K1.m[i], y.m[i]);
+  PVDER_EACH(ST)
+#undef ST
+  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K2);
+#define ST(m) K2.m[i] = vfma(tab.c21, K1.m[i], K2.m[i]);
+  PVDER_EACH(ST)
+#undef ST
+  S::solve(ln, par, k, g, fac, y, inv_gh, K2);
+  // stage 3
+#define ST(m) Y.m[i] = vfma(tab.a32, K2.m[i], vfma(tab.a31, K1.m[i], y.m[i]));
+  PVDER_EACH(ST)
+#undef ST
+  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K3);
+#define ST(m) K3.m[i] = vfma(tab.c32, K2.m[i], vfma(tab.c31, K1.m[i], K3.m[i]));
+  PVDER_EACH(ST)
+#undef ST
+  S::solve(ln, par, k, g, fac, y, inv_gh, K3);
+  // stage 4
+#define ST(m) Y.m[i] = vfma(tab.a43, K3.m[i], vfma(tab.a42, K2.m[i], vfma(tab.a41, K1.m[i], y.m[i])));
+  PVDER_EACH(ST)
+#undef ST
+  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
+#define ST(m) K4.m[i] = vfma(tab.c43, K3.m[i], vfma(tab.c42, K2.m[i], vfma(tab.c41, K1.m[i], K4.m[i])));
+  PVDER_EACH(ST)
+#undef ST
+  S::solve(ln, par, k, g, fac, y, inv_gh, K4);
+  // fold K1..K4 into Y5, C5 (-> K2) and C6 (-> K3); K1, K4 are dead afterwards
+#define ST(m)                                                                                                  \
+  {                                                                                                            \
+    const auto k1 = K1.m[i], k2 = K2.m[i], k3 = K3.m[i], k4 = K4.m[i];                                         \
+    Y.m[i] = vfma(tab.a54, k4, vfma(tab.a53, k3, vfma(tab.a52, k2, vfma(tab.a51, k1, y.m[i]))));               \
+    K2.m[i] = vfma(tab.c54, k4, vfma(tab.c53, k3, vfma(tab.c52, k2, tab.c51 * k1)));                           \
+    K3.m[i] = vfma(tab.c64, k4, vfma(tab.c63, k3, vfma(tab.c62, k2, tab.c61 * k1)));                           \
+  }
+  PVDER_EACH(ST)
+#undef ST
+  // stage 5
+  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
+#define ST(m) K2.m[i] = K2.m[i] + K4.m[i];
+  PVDER_EACH(ST)
+#undef ST
+  S::solve(ln, par, k, g, fac, y, inv_gh, K2);      // K2 = K5
+  // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
+#define ST(m)                                   \
+  Y.m[i] = Y.m[i] + K2.m[i];                    \
+  K3.m[i] = vfma(tab.c65, K2.m[i], K3.m[i]);
+  PVDER_EACH(ST)
+#undef ST
+  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
+#define ST(m) K3.m[i] = K3.m[i] + K4.m[i];
+  PVDER_EACH(ST)
+#undef ST
+  S::solve(ln, par, k, g, fac, y, inv_gh, K3);      // K3 = K6
+#define ST(m) Y.m[i] = Y.m[i] + K3.m[i];
+  PVDER_EACH(ST)
+#undef ST
+#undef PVDER_EACH
+  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  if (oor) return false;
+  y = Y;
+  base = ax;
+  return true;
+}
+
+// Out-of-line slow path (library transcendentals at every stage).  Everything travels by value so
+// that nothing in the caller's hot loop has its address taken (that would pin it to local memory).
+struct SplitStepResult {
+  Split3::Vec y;
+  Aux base;
+};
+PVDER_NOINLINE SplitStepResult rodas4_exact_split(Lanes3 ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
+                                                  Split3::In in, Split3::Consts k, const RodasTab* tab,
+                                                  Split3::Gains g, Aux base) {
+  SplitStepResult r;
+  rodas4_core_split<true>(ln, y, *cfg, in_s, in, k, *tab, g, base);
+  r.y = y;
+  r.base = base;
+  return r;
+}
+
+// Registers of one environment as seen by one of its three lanes.
+struct EnvRegsSplit {
+  Split3::Vec y;
+  double Qref, Vdcref, Vgrid, Sinsol, ret, last_reward;
+  int k, steps, episode, status, done, windup, exact;
+};
+
+// Outputs from the lane-split state: the same individually rounded operations as
+// compute_outputs_p<3>, with the three phase terms summed in the same order.
+PVDER_DEV void compute_outputs_split(const Lanes3& ln, const pvder_env_config& cfg, const Split3::Consts& kc,
+                                     const Split3::Vec& y, double Qref, double Vdcref, double Vgrid, double Sinsol,
+                                     int k, Outputs& o) {
+  using V = Split3::V;
+  const Params& par = cfg.par;
+  const Inputs in = make_inputs(cfg, Vgrid, Qref, Vdcref, Sinsol);
+  const Split3::In inp = Split3::inputs(ln, kc, in);
+  const V jR = y.p[0], jI = y.p[1];
+  const V vkR = vadd_rn(inp.vgR, vadd_rn(vmul_rn(par.Rt, jR), -vmul_rn(par.Xt, jI)));
+  const V vkI = vadd_rn(inp.vgI, vadd_rn(vmul_rn(par.Xt, jR), vmul_rn(par.Rt, jI)));
+  const double Ppcc = ln.sum3(vmul_rn(0.5, vadd_rn(vmul_rn(vkR, jR), vmul_rn(vkI, jI))));
+  const double Qpcc = ln.sum3(vmul_rn(0.5, vadd_rn(vmul_rn(vkI, jR), -vmul_rn(vkR, jI))));
+  const double v2 = ln.sum3(vadd_rn(vmul_rn(vkR, vkR), vmul_rn(vkI, vkI)));
+  finish_outputs<3>(cfg, in, ln.from_a(jR), ln.from_a(jI), ln.from_a(vkR), ln.from_a(vkI), Ppcc, Qpcc, v2, y.s[0], Qref,
+                    Vdcref, k, o);
+}
+
+PVDER_DEV void init_env_split(const Lanes3& ln, const pvder_env_config& cfg, Split3::Vec& y, double& Qref,
+                              double& Vdcref, double& Vgrid, double& Sinsol) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y.p[i] = ln.pc(cfg.y0[i], cfg.y0[6 + i], cfg.y0[12 + i]);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) y.s[i] = cfg.y0[18 + i];
+  Qref = cfg.Q_ref0;
+  Vdcref = cfg.Vdc_ref0;
+  Vgrid = 1.0;
+  Sinsol = 100.0;
+}
+
+// One env step of one env on three lanes (every lane runs the same bookkeeping; see advance_env for
+// the reference line numbers).  `ln` covers the lanes that entered; all three lanes of a group agree
+// on every branch taken here.
+PVDER_DEV bool advance_env_split(const Lanes3& ln_in, const pvder_env_config& cfg, const RodasTab& tab, EnvRegsSplit& r,
+                                 int act, bool active, const double* vtab, const double* stab, int64_t ld, int64_t e,
+                                 uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear) {
+  using S = Split3;
+  const Params& par = cfg.par;
+  const S::Consts kc = S::consts(ln_in);
+  hist_inc = -1;
+  hist_clear = false;
+  bool run = active && !r.done;                     // PVDER_env.py:145-154: step after done is a no-op
+  if (run && (unsigned)act >= (unsigned)PVDER_N_ACTIONS) {   // PVDER_env.py:201
+    r.status = PVDER_STATUS_BAD_ACTION;
+    run = false;
+  }
+  const Lanes3 ln = ln_in.sub(run);
+  if (run) {
+    hist_inc = act;                                          // env_utilities.py:25-30
+    r.steps += 1;                                            // PVDER_env.py:156
+    const double dQ = (act == 1) ? cfg.delQ_pu : ((act == 2) ? -cfg.delQ_pu : 0.0);
+    const double dV = (act == 3) ? cfg.delVdc_pu : ((act == 4) ? -cfg.delVdc_pu : 0.0);
+    r.Qref = __dadd_rn(r.Qref, dQ);                          // PVDER_env.py:225
+    r.Vdcref = __dadd_rn(r.Vdcref, dV);                      // PVDER_env.py:229
+    int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
+    int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
+    Aux base;
+    {
+      const Inputs in0 = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
+      aux_exact_sv(par, in0, r.y.s[4], r.y.s[0], base);
+    }
+    for (int s = 0; s < cfg.n_sub_per_step; ++s) {
+      const Inputs in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
+      const S::In in = S::inputs(ln, kc, in_s);
+      bool m_over;
+      const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
+      if (g.any) r.windup += 1;
+      for (int m = 0; m < cfg.micro; ++m) {
+        const bool ok = rodas4_core_split<false>(ln, r.y, cfg, in_s, in, kc, tab, g, base);
+        const Lanes3 lx = ln.sub(!ok);
+        if (!ok) {
+          const SplitStepResult res = rodas4_exact_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base);
+          r.y = res.y;
+          base = res.base;
+          r.exact += 1;
+        }
+      }
+      r.k += 1;
+      if (r.k == next_k && j_next < cfg.ev_count) {
+        apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
+        j_next += 1;
+        next_k += cfg.ev_step_k;
+      }
+    }
+    auto bad = vnonfinite(r.y.p[0]);
+#pragma unroll
+    for (int i = 1; i < 6; ++i) bad = vor(bad, vnonfinite(r.y.p[i]));
+    bool finite = !ln.any3(bad);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) finite &= (bool)isfinite(r.y.s[i]);
+    if (!finite) r.status = PVDER_STATUS_NONFINITE;
+  }
+
+  compute_outputs_split(ln_in, cfg, kc, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o);
+  done_out = r.done;
+  if (run) {
+    if (r.status == PVDER_STATUS_NONFINITE) {   // PVDER_env.py:170-172: -100, episode ends
+      o.reward = -100.0;
+      o.reward_i = -100;
+      done_out = 1;
+    }
+    if (r.k >= cfg.done_substep) done_out = 1;  // PVDER_env.py:183
+    r.last_reward = o.reward;
+    r.ret += o.reward;                          // env_utilities.py:32-38
+    r.done = done_out;
+  } else {
+    o.reward = r.last_reward;                   // cached tuple, PVDER_env.py:196
+    o.reward_i = (int)r.last_reward;
+  }
+  if (run && done_out && cfg.auto_reset) {
+    init_env_split(ln_in, cfg, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol);
+    r.episode += 1;
+    r.k = 0; r.steps = 0; r.done = 0; r.ret = 0.0; r.status = PVDER_STATUS_OK; r.windup = 0; r.exact = 0;
+    if (cfg.ev_start_k == 0 && cfg.ev_count > 0)
+      apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, 0, r.Vgrid, r.Sinsol);
+    hist_inc = -1;
+    hist_clear = true;
+  }
+  // outputs after an auto-reset are those of the new episode's first state (vector-env convention);
+  // the sums need all lanes, so the recomputation is not under the (group-uniform) reset branch
+  {
+    const bool redo = run && done_out && cfg.auto_reset;
+    const double rew = o.reward;
+    const int rew_i = o.reward_i;
+    const Lanes3 lr = ln_in.sub(redo);
+    if (redo) {
+      compute_outputs_split(lr, cfg, kc, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o);
+      o.reward = rew;
+      o.reward_i = rew_i;
+    }
+  }
+  return run;
+}
+
+}  // namespace pvder

@@ -28,7 +28,8 @@ class PVDERVecEnv:
     def __init__(self, num_envs, device="cuda", seed=0, env_offset=0, model_type="model_2",
                  n_sim_time_steps_per_env_step=15, max_sim_time=40.0, DISCRETE_REWARD=True,
                  goals_list=("voltage_regulation",), events_spec=None, event_mode="philox", auto_reset=False,
-                 obs_f64=False, micro=1, balanced_three_phase="auto", config=None):
+                 obs_f64=False, micro=1, balanced_three_phase="auto", grid_unbalance_ratio=(1.0, 1.0),
+                 config=None):
         import torch
 
         self.torch = torch
@@ -41,7 +42,8 @@ class PVDERVecEnv:
                                        max_sim_time=max_sim_time, DISCRETE_REWARD=DISCRETE_REWARD,
                                        goals_list=list(goals_list), events_spec=events_spec,
                                        event_mode=event_mode, seed=seed, auto_reset=auto_reset, micro=micro,
-                                       balanced_three_phase=balanced_three_phase)
+                                       balanced_three_phase=balanced_three_phase,
+                                       grid_unbalance_ratio=tuple(grid_unbalance_ratio))
         self.num_envs = int(num_envs)
         self.env_offset = int(env_offset)
         self.ns = self.cfg.n_state

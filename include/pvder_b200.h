@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PVDER_ABI_VERSION 1
+#define PVDER_ABI_VERSION 2
 #define PVDER_OBS_DIM 11          /* PVDER_env.py:44-51 observed_quantities */
 #define PVDER_N_ACTIONS 5         /* PVDER_env.py:50 Discrete(5) */
 #define PVDER_MAX_STATES 23
@@ -51,7 +51,10 @@ enum { PVDER_EVENTS_NONE = 0, PVDER_EVENTS_PHILOX = 1, PVDER_EVENTS_TABLE = 2 };
 enum { PVDER_STATUS_OK = 0, PVDER_STATUS_BAD_ACTION = 1, PVDER_STATUS_NONFINITE = 2,
        PVDER_STATUS_UNBALANCED = 3 /* balanced3 mode met a per-phase duty-cycle clamp */ };
 /* three-phase integration mode (pvder_env_config.balanced3) */
-enum { PVDER_3PH_GENERAL = 0, PVDER_3PH_BALANCED = 1, PVDER_3PH_AUTO = 2 };
+enum { PVDER_3PH_GENERAL = 0,   /* 23 states, one thread per env */
+       PVDER_3PH_BALANCED = 1,  /* balanced set carried by phase a (11 states) */
+       PVDER_3PH_AUTO = 2,      /* per env: balanced reduction when the stored state is balanced, else general */
+       PVDER_3PH_SPLIT = 3 };   /* 23 states, three lanes per env (one per phase, warp-shuffle reductions) */
 enum { PVDER_OK = 0, PVDER_ERR_INVALID = -1, PVDER_ERR_CUDA = -2, PVDER_ERR_NOMEM = -3 };
 
 /* Per-unit DER parameters (values from config_der.json:2-21 / :66-84). */
@@ -93,12 +96,16 @@ typedef struct pvder_env_config {
   uint64_t seed;
   double Q_ref0, Vdc_ref0;
   double y0[PVDER_MAX_STATES]; /* reset state (steady-state init, A.6), delta form */
+  double vg_ratio_b, vg_ratio_c; /* grid magnitude of phases b, c relative to phase a (pvder
+                                    Grid(unbalance_ratio_b/c); the env builds Grid(events=...) with 1.0,
+                                    PVDER_env.py:372).  != 1 needs PVDER_3PH_GENERAL or PVDER_3PH_SPLIT */
 } pvder_env_config;
 
 int pvder_abi_version(void);
 const char* pvder_error_string(int code);
 size_t pvder_sd_fields(int phases);
 size_t pvder_si_fields(void);
+size_t pvder_config_size(void);   /* sizeof(pvder_env_config): lets a binding verify its struct mirror */
 
 /* Steady-state initialisation (replaces DERModel(..., steadyStateInitialization=True),
  * PVDER_env.py:374-378).  Host-only Newton solve; y0 gets ns doubles. */

@@ -106,13 +106,15 @@ class OraclePVDEREnv:
     def __init__(self, n_sim_time_steps_per_env_step=15, max_sim_time=40.0, DISCRETE_REWARD=True,
                  goals_list=("voltage_regulation",), model_type="model_2", solver="reference",
                  events_spec=None, events: EventTable | None = None, seed=None,
-                 max_episode_steps=500):
+                 max_episode_steps=500, vg_ratio=(1.0, 1.0, 1.0), pll_mode="abc_dq0"):
         self.n = int(n_sim_time_steps_per_env_step)
         limit = max_episode_steps * self.n * TINC
         self.max_sim_time = min(max(float(max_sim_time), 1.0), limit)   # PVDER_env.py:561-575
         self.DISCRETE_REWARD = bool(DISCRETE_REWARD)
         self.goal = list(goals_list)[0]
         self.params = load_der_params(MODEL_SPEC[model_type])
+        self.params.vg_ratio = tuple(float(r) for r in vg_ratio)    # pvder Grid(unbalance_ratio_b/c); env default 1.0
+        self.params.pll_mode = pll_mode
         self.model = PVDERModel(self.params)
         self.solver = solver
         self.events_spec = events_spec or {k: dict(v) for k, v in DEFAULT_EVENTS_SPEC.items()}

@@ -73,6 +73,13 @@ class DERParams:
     m_limit: float = 1.0
     wte0: float = 6.28
     ss_guess: tuple = (0.0, 0.0, 0.0, 0.0)
+    # grid unbalance (pvder Grid(unbalance_ratio_b, unbalance_ratio_c); the env builds
+    # Grid(events=...) with the defaults 1.0, reference PVDER_env.py:372): per-phase magnitude factors
+    vg_ratio: tuple = (1.0, 1.0, 1.0)
+    # three-phase PLL input (A.4): "abc_dq0" = pvder's abc->dq0 of the time-domain voltages (carries a
+    # 2w ripple on unbalanced sets), "posseq" = its cycle average, the positive-sequence projection the
+    # half-cycle kernel integrates (identical on balanced sets)
+    pll_mode: str = "abc_dq0"
     # derived extras kept for known-answer tests
     extras: dict = field(default_factory=dict)
 
@@ -189,6 +196,17 @@ class PVDERModel:
             c, s = math.cos(psi), math.sin(psi)
             vd = vR[0] * c - vI[0] * s
             return vd, [p.Rt * c - p.Xt * s], [-p.Xt * c - p.Rt * s], vR[0] * s + vI[0] * c
+        if p.pll_mode == "posseq":
+            dl = wte - wgrid * t
+            vd, dR, dI, dw = 0.0, [], [], 0.0
+            for k in range(3):
+                ck = math.cos(dl - self.alpha[k])
+                sk = math.sin(dl - self.alpha[k])
+                vd += (vR[k] * ck + vI[k] * sk) / 3.0
+                dR.append((p.Rt * ck + p.Xt * sk) / 3.0)
+                dI.append((-p.Xt * ck + p.Rt * sk) / 3.0)
+                dw += (-vR[k] * sk + vI[k] * ck) / 3.0
+            return vd, dR, dI, dw
         cwt, swt = math.cos(wgrid * t), math.sin(wgrid * t)
         vd = 0.0
         dR, dI = [], []
@@ -244,7 +262,7 @@ class PVDERModel:
         for k in range(p.phases):
             o = 6 * k
             iR, iI = y[o], y[o + 1]
-            vg = inp.Vgrid * p.vgs * self.rot[k]
+            vg = inp.Vgrid * p.vgs * p.vg_ratio[k] * self.rot[k]
             Q += 0.5 * (vg.imag * iR - vg.real * iI + p.Xt * (iR * iR + iI * iI))
         return Q
 
@@ -260,7 +278,7 @@ class PVDERModel:
         for k in range(P_):
             o = 6 * k
             iR, iI = y[o], y[o + 1]
-            vg = inp.Vgrid * p.vgs * self.rot[k]
+            vg = inp.Vgrid * p.vgs * p.vg_ratio[k] * self.rot[k]
             vR[k] = vg.real + p.Rt * iR - p.Xt * iI
             vI[k] = vg.imag + p.Xt * iR + p.Rt * iI
             mR = p.Kp_GCC * y[o + 4] + y[o + 2]
@@ -329,7 +347,7 @@ class PVDERModel:
         for k in range(P_):
             o = 6 * k
             iR, iI = y[o], y[o + 1]
-            vg = inp.Vgrid * p.vgs * self.rot[k]
+            vg = inp.Vgrid * p.vgs * p.vg_ratio[k] * self.rot[k]
             vR[k] = vg.real + p.Rt * iR - p.Xt * iI
             vI[k] = vg.imag + p.Xt * iR + p.Rt * iI
             dQ_R[k] = 0.5 * (vg.imag + 2.0 * p.Xt * iR)
@@ -440,7 +458,7 @@ class PVDERModel:
         for k in range(p.phases):
             o = 6 * k
             jR, jI = y[o], y[o + 1]
-            vg = (inp.Vgrid * p.vgs) * self.rot[k]
+            vg = ((inp.Vgrid * p.vgs) * p.vg_ratio[k]) * self.rot[k]
             vkR = vg.real + (p.Rt * jR - p.Xt * jI)
             vkI = vg.imag + (p.Xt * jR + p.Rt * jI)
             P = P + 0.5 * (vkR * jR + vkI * jI)

@@ -100,3 +100,27 @@ def freeze_bits(cfg, y, inp4):
     i4 = np.ascontiguousarray(inp4, dtype=np.float64)
     load().emul_freeze_bits.restype = C.c_uint
     return int(load().emul_freeze_bits(C.byref(cfg.c), _p(y), _p(i4)))
+
+
+def split_rhs(cfg, y, inp4, frz=0):
+    """Right-hand side of the lane-split three-phase model (pvder_split3.cuh), lanes emulated on the host."""
+    f = np.zeros(23)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    i4 = np.ascontiguousarray(inp4, dtype=np.float64)
+    load().emul_split_rhs(C.byref(cfg.c), _p(y), _p(i4), C.c_uint(frz), _p(f))
+    return f
+
+
+def split_wsolve(cfg, y, inp4, ghinv, b, frz=0):
+    b = np.array(b, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    i4 = np.ascontiguousarray(inp4, dtype=np.float64)
+    load().emul_split_wsolve(C.byref(cfg.c), _p(y), _p(i4), C.c_uint(frz), C.c_double(ghinv), _p(b))
+    return b
+
+
+def split_freeze_bits(cfg, y, inp4):
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    i4 = np.ascontiguousarray(inp4, dtype=np.float64)
+    load().emul_split_freeze_bits.restype = C.c_uint
+    return int(load().emul_split_freeze_bits(C.byref(cfg.c), _p(y), _p(i4)))

@@ -9,6 +9,7 @@
 #include "../../gym-solarpvder-environment_b200/csrc/pvder_model_3ph.cuh"
 #include "../../gym-solarpvder-environment_b200/csrc/pvder_model_3ph_bal.cuh"
 #include "../../gym-solarpvder-environment_b200/csrc/pvder_env_step.cuh"
+#include "../../gym-solarpvder-environment_b200/csrc/pvder_split3.cuh"
 
 using namespace pvder;
 
@@ -101,7 +102,7 @@ template <class M>
 static void rhs_one(const pvder_env_config& cfg, const double* yin, const double* inp4, unsigned frz, double* f) {
   double y[M::NS], ff[M::NS];
   for (int i = 0; i < M::NS; ++i) y[i] = yin[i];
-  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3]};
+  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
   Aux ax;
   aux_exact<M>(cfg.par, in, y, ax);
   double gn[M::NFRZ];
@@ -115,7 +116,7 @@ static void wsolve_one(const pvder_env_config& cfg, const double* yin, const dou
                        double* b) {
   double y[M::NS], bb[M::NS];
   for (int i = 0; i < M::NS; ++i) { y[i] = yin[i]; bb[i] = b[i]; }
-  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3]};
+  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
   typename M::LU lu;
   Aux ax;
   aux_exact<M>(cfg.par, in, y, ax);
@@ -132,9 +133,134 @@ template <class M>
 static unsigned frz_one(const pvder_env_config& cfg, const double* yin, const double* inp4) {
   double y[M::NS];
   for (int i = 0; i < M::NS; ++i) y[i] = yin[i];
-  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3]};
+  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
   bool m_over;
   return freeze_bits<M>(y, cfg.par, in, m_over);
+}
+
+
+// ---- lane-split three-phase model (pvder_split3.cuh) with the three lanes emulated by V3 ----------
+static void load_split(const double* sd, int64_t ld, int64_t e, Split3::Vec& y) {
+  for (int i = 0; i < 6; ++i) y.p[i] = V3(sd[(int64_t)i * ld + e], sd[(int64_t)(6 + i) * ld + e], sd[(int64_t)(12 + i) * ld + e]);
+  for (int i = 0; i < 5; ++i) y.s[i] = sd[(int64_t)(18 + i) * ld + e];
+}
+
+static void store_split(double* sd, int64_t ld, int64_t e, const Split3::Vec& y) {
+  for (int i = 0; i < 6; ++i)
+    for (int k = 0; k < 3; ++k) sd[(int64_t)(6 * k + i) * ld + e] = y.p[i].v[k];
+  for (int i = 0; i < 5; ++i) sd[(int64_t)(18 + i) * ld + e] = y.s[i];
+}
+
+static void step_all_split(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+                           const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
+                           uint8_t* done, int64_t n, int64_t off) {
+  constexpr int NS = 23;
+  const RodasTab tab = make_rodas_tab<Split3>(cfg.par, cfg.substeps_per_sec * (double)cfg.micro);
+  const Lanes3 ln;
+  for (int64_t e = 0; e < n; ++e) {
+    EnvRegsSplit r;
+    load_split(sd, ld, e, r.y);
+    r.Qref = sd[(int64_t)PVDER_SD_QREF(NS) * ld + e];
+    r.Vdcref = sd[(int64_t)PVDER_SD_VDCREF(NS) * ld + e];
+    r.Vgrid = sd[(int64_t)PVDER_SD_VGRID(NS) * ld + e];
+    r.Sinsol = sd[(int64_t)PVDER_SD_SINSOL(NS) * ld + e];
+    r.ret = sd[(int64_t)PVDER_SD_RETURN(NS) * ld + e];
+    r.last_reward = sd[(int64_t)PVDER_SD_REWARD(NS) * ld + e];
+    r.k = si[(int64_t)PVDER_SI_K * ld + e];
+    r.steps = si[(int64_t)PVDER_SI_STEPS * ld + e];
+    r.episode = si[(int64_t)PVDER_SI_EPISODE * ld + e];
+    r.status = si[(int64_t)PVDER_SI_STATUS * ld + e];
+    r.done = si[(int64_t)PVDER_SI_DONE * ld + e];
+    r.windup = si[(int64_t)PVDER_SI_WINDUP * ld + e];
+    r.exact = si[(int64_t)PVDER_SI_EXACT * ld + e];
+    Outputs o;
+    int done_out, hist_inc;
+    bool hist_clear;
+    const bool run = advance_env_split(ln, cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o,
+                                       done_out, hist_inc, hist_clear);
+    if (reward) reward[e] = o.reward;
+    if (reward_i) reward_i[e] = o.reward_i;
+    if (done) done[e] = (uint8_t)done_out;
+    if (run) {
+      store_split(sd, ld, e, r.y);
+      sd[(int64_t)PVDER_SD_QREF(NS) * ld + e] = r.Qref;
+      sd[(int64_t)PVDER_SD_VDCREF(NS) * ld + e] = r.Vdcref;
+      sd[(int64_t)PVDER_SD_VGRID(NS) * ld + e] = r.Vgrid;
+      sd[(int64_t)PVDER_SD_SINSOL(NS) * ld + e] = r.Sinsol;
+      sd[(int64_t)PVDER_SD_RETURN(NS) * ld + e] = r.ret;
+      sd[(int64_t)PVDER_SD_REWARD(NS) * ld + e] = r.last_reward;
+      si[(int64_t)PVDER_SI_K * ld + e] = r.k;
+      si[(int64_t)PVDER_SI_STEPS * ld + e] = r.steps;
+      si[(int64_t)PVDER_SI_EPISODE * ld + e] = r.episode;
+      si[(int64_t)PVDER_SI_DONE * ld + e] = r.done;
+      si[(int64_t)PVDER_SI_WINDUP * ld + e] = r.windup;
+      si[(int64_t)PVDER_SI_EXACT * ld + e] = r.exact;
+      if (hist_inc >= 0) si[(int64_t)(PVDER_SI_HIST + hist_inc) * ld + e] += 1;
+      if (hist_clear)
+        for (int h = 0; h < PVDER_N_ACTIONS; ++h) si[(int64_t)(PVDER_SI_HIST + h) * ld + e] = 0;
+    }
+    si[(int64_t)PVDER_SI_STATUS * ld + e] = r.status;
+    if (obs64)
+      for (int j = 0; j < PVDER_OBS_DIM; ++j) obs64[e * PVDER_OBS_DIM + j] = o.obs[j];
+  }
+}
+
+// rhs (mode 0) or W^-1 b (mode 1) of the lane-split model at a 23-state point; frz = freeze mask bits
+// in the order of Model3ph (per phase xR,xI,uR,uI; then xDC, xQ)
+static void split_one(const pvder_env_config& cfg, const double* yin, const double* inp4, unsigned frz, double ghinv,
+                      int mode, double* out) {
+  const Lanes3 ln;
+  Split3::Vec y, b;
+  load_split(yin, 1, 0, y);
+  Inputs in_s{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
+  const Split3::Consts kc = Split3::consts(ln);
+  const Split3::In in = Split3::inputs(ln, kc, in_s);
+  Aux ax;
+  aux_exact_sv(cfg.par, in_s, y.s[4], y.s[0], ax);
+  double luc[16];
+  Split3::lu_consts(cfg.par, ghinv, luc);
+  Split3::Gains g;
+  auto bit = [&](int b_) { return (frz >> b_) & 1u; };
+  auto gv = [&](int j, double val) { return V3(bit(j) ? 0.0 : val, bit(4 + j) ? 0.0 : val, bit(8 + j) ? 0.0 : val); };
+  g.g0 = gv(0, cfg.par.Ki_GCC); g.g1 = gv(1, cfg.par.Ki_GCC); g.g2 = gv(2, cfg.par.wp); g.g3 = gv(3, cfg.par.wp);
+  g.duR = V3(1.0) / (g.g2 + V3(ghinv));
+  g.duI = V3(1.0) / (g.g3 + V3(ghinv));
+  g.g4 = bit(12) ? 0.0 : cfg.par.Ki_DC;
+  g.g5 = bit(13) ? 0.0 : cfg.par.Ki_Q;
+  g.any = frz != 0;
+  const Split3::Pt q = Split3::point(ln, cfg.par, kc, in, ax, y);
+  if (mode == 0) {
+    Split3::rhs(cfg.par, kc, ax, g, y, q, b);
+  } else {
+    load_split(out, 1, 0, b);
+    Split3::Fac fac;
+    Split3::factor(ln, cfg.par, kc, in, ax, g, y, q, ghinv, luc, fac);
+    Split3::solve(ln, cfg.par, kc, g, fac, y, luc[0], b);
+  }
+  store_split(out, 1, 0, b);
+}
+
+static unsigned split_freeze_bits(const pvder_env_config& cfg, const double* yin, const double* inp4, double ghinv) {
+  const Lanes3 ln;
+  Split3::Vec y;
+  load_split(yin, 1, 0, y);
+  Inputs in_s{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
+  const Split3::Consts kc = Split3::consts(ln);
+  const Split3::In in = Split3::inputs(ln, kc, in_s);
+  double luc[16];
+  Split3::lu_consts(cfg.par, ghinv, luc);
+  bool m_over;
+  const Split3::Gains g = Split3::gains(ln, cfg.par, kc, in, y, luc, m_over);
+  unsigned bits = 0;
+  for (int k = 0; k < 3; ++k) {
+    if (g.g0.v[k] == 0.0) bits |= 1u << (4 * k);
+    if (g.g1.v[k] == 0.0) bits |= 1u << (4 * k + 1);
+    if (g.g2.v[k] == 0.0) bits |= 1u << (4 * k + 2);
+    if (g.g3.v[k] == 0.0) bits |= 1u << (4 * k + 3);
+  }
+  if (g.g4 == 0.0) bits |= 1u << 12;
+  if (g.g5 == 0.0) bits |= 1u << 13;
+  return bits;
 }
 
 extern "C" {
@@ -147,6 +273,8 @@ int emul_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, 
     step_all<Model3phBal>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   else if (cfg->balanced3 == PVDER_3PH_AUTO)
     step_all<Model3ph, true>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
+  else if (cfg->balanced3 == PVDER_3PH_SPLIT)
+    step_all_split(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   else step_all<Model3ph>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   return 0;
 }
@@ -171,6 +299,19 @@ void emul_wsolve(const pvder_env_config* cfg, const double* y, const double* inp
 
 unsigned emul_freeze_bits(const pvder_env_config* cfg, const double* y, const double* inp4) {
   return cfg->phases == 1 ? frz_one<Model1ph>(*cfg, y, inp4) : frz_one<Model3ph>(*cfg, y, inp4);
+}
+
+void emul_split_rhs(const pvder_env_config* cfg, const double* y, const double* inp4, unsigned frz, double* f) {
+  split_one(*cfg, y, inp4, frz, 480.0, 0, f);
+}
+
+void emul_split_wsolve(const pvder_env_config* cfg, const double* y, const double* inp4, unsigned frz, double ghinv,
+                       double* b) {
+  split_one(*cfg, y, inp4, frz, ghinv, 1, b);
+}
+
+unsigned emul_split_freeze_bits(const pvder_env_config* cfg, const double* y, const double* inp4) {
+  return split_freeze_bits(*cfg, y, inp4, 480.0);
 }
 
 void emul_events(const pvder_env_config* cfg, const int32_t* episode, double* vtab, double* stab, int64_t ld,

@@ -291,3 +291,135 @@ def test_property_reference_increments_and_counters(actions, n_sim):
         assert obs[0, 9] == q and obs[0, 8] == v
         assert np.isfinite(obs).all() and (np.abs(obs) <= 10).all()
     assert em.si[_cabi.SI_K, 0] == 2 * n_sim * len(actions) and em.si[_cabi.SI_STATUS, 0] == 0
+
+
+# ---- lane-split general three-phase model (csrc/pvder_split3.cuh), lanes emulated on the host ----------
+def _unbalanced_state(cfg, rng):
+    y = np.array(cfg.y0) * (1 + 0.03 * rng.standard_normal(23))
+    y[[4, 5, 10, 11, 16, 17]] = 1e-3 * rng.standard_normal(6)
+    y[21], y[22] = 0.3 * rng.standard_normal(), 7.8 + 0.2 * rng.standard_normal()
+    return y
+
+
+@pytest.mark.parametrize("ratio", [(1.0, 1.0), (0.95, 1.03)])
+def test_split_model_rhs_and_block_solve(ratio):
+    """The hand-derived block-arrow solve of the three-lane model against (a) the generated symbolic LU of
+    the one-thread model and (b) a dense numpy solve with the oracle's analytic Jacobian (positive-sequence
+    PLL), on unbalanced states, unbalanced grids and random anti-windup masks."""
+    cfg = G.EnvConfig(model_type="model_2", balanced_three_phase="split", grid_unbalance_ratio=ratio)
+    p = load_der_params("50")
+    p.vg_ratio = (1.0,) + ratio
+    p.pll_mode = "posseq"
+    m = PVDERModel(p)
+    rng = np.random.default_rng(3)
+    for trial in range(8):
+        y = _unbalanced_state(cfg, rng)
+        frz = 0 if trial < 3 else int(rng.integers(0, 1 << 14))
+        mask = tuple(bool((frz >> b) & 1) for b in range(14))
+        inp = Inputs(Vgrid=0.96, Sinsol=90.0, Q_ref=0.03, Vdc_ref=p.Vdc_ref0 * 1.01, freeze=mask)
+        inp4 = [0.96 * cfg.par.vgs, 0.03, p.Vdc_ref0 * 1.01, cfg.par.np_iph100 * 0.9]
+        f_or = np.array(m.rhs(list(y), 0.0, inp))
+        f_or[-1] -= H.W
+        f_sp = E.split_rhs(cfg, y, inp4, frz)
+        np.testing.assert_allclose(f_sp, f_or, rtol=1e-12, atol=1e-9 * np.abs(f_or).max())
+        np.testing.assert_array_equal(f_sp, E.rhs(cfg, y, inp4, frz))          # same expressions as the generated model
+        gh = 480.0
+        b = rng.standard_normal(23)
+        x_sp = E.split_wsolve(cfg, y, inp4, gh, b, frz)
+        x_lu = E.wsolve(cfg, y, inp4, gh, b, frz)
+        x_np = np.linalg.solve(np.eye(23) * gh - m.jac(list(y), 0.0, inp), b)
+        np.testing.assert_allclose(x_sp, x_lu, rtol=0, atol=1e-12 * np.abs(x_lu).max())
+        np.testing.assert_allclose(x_sp, x_np, rtol=0, atol=1e-10 * np.abs(x_np).max())
+
+
+def test_split_freeze_mask_matches_general_model():
+    cfg = G.EnvConfig(model_type="model_2", balanced_three_phase="split", grid_unbalance_ratio=(0.97, 1.02))
+    rng = np.random.default_rng(5)
+    hits = 0
+    for trial in range(40):
+        y = _unbalanced_state(cfg, rng)
+        if trial % 2:
+            y[19] *= 1.6            # push |iref| over the limit
+        if trial % 3 == 0:
+            y[2:4] *= 12.0          # push one phase's duty cycle over 10 m_limit
+        inp4 = [0.96 * cfg.par.vgs, 0.03, cfg.extras["Vdc_ref0"], cfg.par.np_iph100]
+        a, b = E.freeze_bits(cfg, y, inp4), E.split_freeze_bits(cfg, y, inp4)
+        assert a == b
+        hits += a != 0
+    assert hits > 10
+
+
+@pytest.mark.parametrize("ratio", [(1.0, 1.0), (0.95, 1.03)])
+def test_split_stepping_equals_one_thread_general_model(ratio):
+    kw = dict(model_type="model_2", events_spec=H.SAG_SPEC, seed=4, DISCRETE_REWARD=True, grid_unbalance_ratio=ratio,
+              auto_reset=True, max_sim_time=1.5, n_sim_time_steps_per_env_step=6)
+    gen = E.EmulVecEnv(6, balanced_three_phase=False, **kw)
+    spl = E.EmulVecEnv(6, balanced_three_phase="split", **kw)
+    assert (gen.cfg.c.balanced3, spl.cfg.c.balanced3) == (0, 3)
+    np.testing.assert_array_equal(gen.reset(), spl.reset())
+    for s in range(20):                      # crosses an auto-reset (15 steps per episode)
+        a = twin.sample_actions_twin(4, s, 6, 0)
+        og, rg, dg, _ = gen.step(a)
+        os_, rs, ds, _ = spl.step(a)
+        np.testing.assert_allclose(spl.sd, gen.sd, rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(os_, og, rtol=1e-11, atol=1e-12)
+        np.testing.assert_array_equal(rs, rg)
+        np.testing.assert_array_equal(spl.si, gen.si)
+        np.testing.assert_array_equal(ds, dg)
+    assert gen.si[_cabi.SI_EPISODE].min() >= 1
+
+
+def test_split_golden_fixture():
+    gold = np.load("tests/golden/golden_model_2.npz")
+    acts = gold["actions"]
+    n, nsteps = acts.shape
+    em = E.EmulVecEnv(n, model_type="model_2", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True,
+                      balanced_three_phase="split")
+    em.set_event_tables(gold["vgrid_tab"], gold["sinsol_tab"])
+    em.reset()
+    for s in range(nsteps):
+        obs, rew, done, _ = em.step(acts[:, s])
+        np.testing.assert_allclose(obs, gold["obs"][:, s], rtol=H.RTOL, atol=H.ATOL)
+        np.testing.assert_array_equal(rew, gold["reward"][:, s])
+        for i in range(n):
+            H.assert_state_close(em.sd[:em.ns, i], gold["state"][i, s], 3, what=f"env{i} step{s}")
+
+
+def test_unbalanced_grid_vs_tight_oracle():
+    """Unbalanced grid (phase b 0.95, phase c 1.03 of phase a): split and one-thread kernels sources against
+    the oracle's tight LSODA with the same positive-sequence PLL input (the half-cycle grid cannot
+    resolve the 2w ripple of pvder's abc->dq0 transform; on balanced sets both are identical)."""
+    ratio = (0.95, 1.03)
+    ev = H.random_events(7)
+    orc = OraclePVDEREnv(model_type="model_2", solver="tight", events=ev, DISCRETE_REWARD=False,
+                         vg_ratio=(1.0,) + ratio, pll_mode="posseq")
+    orc.reset()
+    envs = []
+    for mode in ("split", False):
+        em = E.EmulVecEnv(1, model_type="model_2", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False,
+                          balanced_three_phase=mode, grid_unbalance_ratio=ratio)
+        v, s = H.oracle_tables(ev, em.cfg.c)
+        em.set_event_tables(v, s)
+        em.reset()
+        envs.append(em)
+    for step, a in enumerate([0, 1, 3]):
+        oo, orw, od, _ = orc.step(a)
+        for em in envs:
+            obs, rew, done, _ = em.step(np.array([a]))
+            H.assert_state_close(em.sd[:23, 0], H.oracle_delta_state(orc), 3, what=f"step{step}")
+            np.testing.assert_allclose(obs[0], oo, rtol=H.RTOL, atol=H.ATOL)
+    # the unbalance is real: the current loop keeps the currents (nearly) balanced, so the duty-cycle
+    # integrators of phase b are not a rotated copy of phase a's
+    xa = complex(envs[0].sd[2, 0], envs[0].sd[3, 0])
+    xb = complex(envs[0].sd[8, 0], envs[0].sd[9, 0])
+    assert abs(xb - xa * np.exp(-2j * math.pi / 3)) > 1e-2
+
+
+def test_unbalanced_grid_config_validation():
+    assert G.EnvConfig(model_type="model_2", grid_unbalance_ratio=(0.9, 1.0)).three_phase_mode == "split"   # auto -> split
+    with pytest.raises(ValueError):
+        G.EnvConfig(model_type="model_2", grid_unbalance_ratio=(0.9, 1.0), balanced_three_phase=True)
+    with pytest.raises(ValueError):
+        G.EnvConfig(model_type="model_1", grid_unbalance_ratio=(0.9, 1.0))
+    with pytest.raises(ValueError):
+        G.EnvConfig(model_type="model_2", grid_unbalance_ratio=(0.0, 1.0))

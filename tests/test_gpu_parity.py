@@ -24,7 +24,7 @@ def _venv(cuda, n, **kw):
 
 
 @pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", False),
-                                                 ("model_2", "auto")])
+                                                 ("model_2", "auto"), ("model_2", "split")])
 def test_matches_cpp_emulation(cuda, model_type, balanced):
     import torch
     import emul_harness as E
@@ -58,7 +58,8 @@ def test_matches_cpp_emulation(cuda, model_type, balanced):
     assert int(g.si[10, :n].sum()) == int(e.si[10].sum())
 
 
-@pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", False)])
+@pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", False),
+                                                 ("model_2", "split")])
 def test_trajectory_vs_tight_oracle(cuda, model_type, balanced):
     """Same y0, parameters, actions and event sequence as the oracle's tight LSODA path."""
     import torch
@@ -90,7 +91,8 @@ def test_trajectory_vs_tight_oracle(cuda, model_type, balanced):
             assert bool(done[i]) == od
 
 
-@pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", False)])
+@pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", False),
+                                                 ("model_2", "split")])
 def test_golden_fixture(cuda, model_type, balanced):
     """Committed golden vectors (oracle tight path, tests/golden/make_golden.py)."""
     import torch
@@ -375,3 +377,68 @@ def test_full_size_properties_1M(cuda):
     for s in range(3):
         b.step(b.sample_actions())
     assert torch.equal(a.sd, b.sd) and torch.equal(a.si, b.si) and torch.equal(a.obs, b.obs)
+
+
+@pytest.mark.parametrize("mode", ["split", False])
+def test_unbalanced_grid_kernels(cuda, mode):
+    """Grid unbalance ratios (pvder Grid(unbalance_ratio_b/c)): the three-lane kernel and the one-thread
+    general kernel against the C++ build of their sources (tight) and the oracle's tight LSODA with the same
+    positive-sequence PLL input, on an odd env count (partial warps / groups)."""
+    import torch
+    import emul_harness as E
+
+    ratio = (0.95, 1.03)
+    n = 47
+    kw = dict(model_type="model_2", events_spec=H.SAG_SPEC, seed=77, DISCRETE_REWARD=True, balanced_three_phase=mode,
+              grid_unbalance_ratio=ratio)
+    g = _venv(cuda, n, env_offset=3, **kw)
+    e = E.EmulVecEnv(n, env_offset=3, **kw)
+    g.reset()
+    e.reset()
+    for step in range(6):
+        a = g.sample_actions()
+        obs, rew, done, _ = g.step(a)
+        oe, re_, de, _ = e.step(a.cpu().numpy())
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(g.sd[:, :n].cpu().numpy(), e.sd, rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(g.obs64.cpu().numpy(), oe, rtol=1e-9, atol=1e-11)
+        np.testing.assert_array_equal(g.si[:, :n].cpu().numpy(), e.si)
+    # against the oracle (one env, fixed events)
+    ev = H.random_events(7)
+    orc = OraclePVDEREnv(model_type="model_2", solver="tight", events=ev, DISCRETE_REWARD=False,
+                         vg_ratio=(1.0,) + ratio, pll_mode="posseq")
+    orc.reset()
+    g1 = _venv(cuda, 1, model_type="model_2", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False,
+               balanced_three_phase=mode, grid_unbalance_ratio=ratio)
+    v, s = H.oracle_tables(ev, g1.cfg.c)
+    g1.set_event_tables(v, s)
+    g1.reset()
+    for step, act in enumerate([0, 1, 3, 2]):
+        oo, orw, od, _ = orc.step(act)
+        g1.step(torch.tensor([act], dtype=torch.int32, device=cuda))
+        H.assert_state_close(g1.y.cpu().numpy()[:, 0], H.oracle_delta_state(orc), 3, what=f"unbalanced step{step}")
+        np.testing.assert_allclose(g1.obs64.cpu().numpy()[0], oo, rtol=H.RTOL, atol=H.ATOL)
+
+
+def test_split_kernel_full_episode_with_auto_reset(cuda):
+    """Three-lane kernel over more than one episode: counters, done and auto-reset agree with the one-thread
+    general kernel env by env (partial last warp: 10 envs per warp, 40 per block)."""
+    import torch
+
+    n = 1003
+    kw = dict(model_type="model_2", events_spec=H.SAG_SPEC, seed=9, DISCRETE_REWARD=True, auto_reset=True,
+              max_sim_time=2.0, n_sim_time_steps_per_env_step=15)
+    a_env = _venv(cuda, n, balanced_three_phase="split", **kw)
+    b_env = _venv(cuda, n, balanced_three_phase=False, **kw)
+    a_env.reset()
+    b_env.reset()
+    for step in range(11):                    # 8 steps per episode
+        act = a_env.sample_actions()
+        oa, ra, da, _ = a_env.step(act)
+        ob, rb, db, _ = b_env.step(act)
+        np.testing.assert_array_equal(da.cpu().numpy(), db.cpu().numpy())
+        np.testing.assert_array_equal(a_env.si[:, :n].cpu().numpy(), b_env.si[:, :n].cpu().numpy())
+        np.testing.assert_allclose(a_env.sd[:, :n].cpu().numpy(), b_env.sd[:, :n].cpu().numpy(), rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(oa.cpu().numpy(), ob.cpu().numpy(), rtol=1e-6, atol=1e-7)
+        assert int((ra.cpu().numpy() != rb.cpu().numpy()).sum()) <= 1
+    assert int(a_env.si[2, :n].min()) >= 1    # every env went through an auto-reset

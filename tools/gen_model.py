@@ -36,7 +36,7 @@ OUT = os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
 
 PAR = ["Rf", "Rt", "Xt", "inv_Lf", "inv_wb", "Kp_GCC", "Ki_GCC", "Kp_DC", "Ki_DC", "Kp_Q", "Ki_Q",
        "wp", "Kp_PLL", "Ki_PLL", "inv_C", "w0", "dw"]
-INP = ["vg", "Qref", "Vdcref", "Ppv", "dPpv"]
+INP = ["vg", "vgb", "vgc", "Qref", "Vdcref", "Ppv", "dPpv"]
 
 
 def build(P, mult=1):
@@ -61,6 +61,9 @@ def build(P, mult=1):
         h3 = sp.Symbol("SQ3") / 2     # sqrt(3), emitted as a literal
         rot = [(sp.Integer(1), sp.Integer(0)), (-sp.Rational(1, 2), -h3), (-sp.Rational(1, 2), h3)]
         alpha = [(sp.Integer(1), sp.Integer(0)), (-sp.Rational(1, 2), h3), (-sp.Rational(1, 2), -h3)]
+    # grid phasor magnitude per phase: an explicit three-phase model takes vg, vgb, vgc (grid
+    # unbalance ratios); the single-phase / balanced models use vg only
+    vgk = [inp["vg"], inp["vgb"], inp["vgc"]] if (P == 3 and mult == 1) else [inp["vg"]] * P
     p = par
     # Freezable rows (anti-windup, A.3) are "gain x expression": their gains come in as per-row
     # effective values g_b (= the parameter, or 0 while the row is clamped), so clamping costs
@@ -75,8 +78,8 @@ def build(P, mult=1):
         o = 6 * k
         iR, iI, xR, xI, uR, uI = y[o:o + 6]
         rr, ri = rot[k]
-        vR.append(inp["vg"] * rr + p["Rt"] * iR - p["Xt"] * iI)
-        vI.append(inp["vg"] * ri + p["Xt"] * iR + p["Rt"] * iI)
+        vR.append(vgk[k] * rr + p["Rt"] * iR - p["Xt"] * iI)
+        vI.append(vgk[k] * ri + p["Xt"] * iR + p["Rt"] * iI)
         mR.append(p["Kp_GCC"] * uR + xR)
         mI.append(p["Kp_GCC"] * uI + xI)
         Q += mult * sp.Rational(1, 2) * (vI[k] * iR - vR[k] * iI)
@@ -151,8 +154,9 @@ def emit_rhs_structured(m):
     for k in range(P):
         iR, iI, xR, xI, uR, uI = ["y_" + nm[6 * k + j] for j in range(6)]
         rr, ri = rots[k]
-        vgR = "in_vg" if rr == "1" else f"({rr} * in_vg)"
-        vgI = "0.0" if ri == "0" else f"({ri} * in_vg)"
+        vgn = ["in_vg", "in_vgb", "in_vgc"][k] if (P == 3 and mult == 1) else "in_vg"
+        vgR = vgn if rr == "1" else f"({rr} * {vgn})"
+        vgI = "0.0" if ri == "0" else f"({ri} * {vgn})"
         A(f"    const double vR{k} = fma(p_Rt, {iR}, fma(-p_Xt, {iI}, {vgR}));")
         if ri == "0":
             A(f"    const double vI{k} = fma(p_Xt, {iR}, p_Rt * {iI});")
@@ -344,7 +348,8 @@ def generate(P, mult=1):
     A("                            const double (&gn)[NFRZ], double (&f)[NS]) {")
     L.extend(par_unpack)
     L.extend(unpack())
-    A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
+    A("    const double in_vg = in.vg, in_vgb = in.vgb, in_vgc = in.vgc, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
+    A("    (void)in_vgb; (void)in_vgc;")
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
     A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, inv_Vdc = aux.inv_Vdc;")
     L.extend(gain_unpack)
@@ -425,7 +430,8 @@ def generate(P, mult=1):
     A("                               const double (&gn)[NFRZ], double ghinv, const double* luc, LU& lu) {")
     L.extend(par_unpack)
     L.extend(unpack())
-    A("    const double in_vg = in.vg, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
+    A("    const double in_vg = in.vg, in_vgb = in.vgb, in_vgc = in.vgc, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
+    A("    (void)in_vgb; (void)in_vgc;")
     A("    (void)in_Qref; (void)in_Vdcref;")
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
     A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, in_dPpv = aux.dPpv, inv_Vdc = aux.inv_Vdc;")
