@@ -76,8 +76,16 @@ __device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const O
   for (int idx = t; idx < total; idx += BLOCK) dst[idx] = stage[idx];
 }
 
+// Register budget of the step kernels: __launch_bounds__(BLOCK, minBlocks) by default; building with
+// -DPVDER_MAXNREG=N pins it to N registers per thread instead (occupancy sweeps, tools/build_variant.sh).
+#ifdef PVDER_MAXNREG
+#define PVDER_STEP_BOUNDS(M) __maxnreg__(PVDER_MAXNREG)
+#else
+#define PVDER_STEP_BOUNDS(M) __launch_bounds__(BLOCK, min_blocks<M>())
+#endif
+
 template <class M, bool AUTO3 = false>
-__global__ void __launch_bounds__(BLOCK, min_blocks<M>()) step_kernel(const __grid_constant__ pvder_env_config cfg,
+__global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_env_config cfg,
                                                      const __grid_constant__ RodasTab tab, const StepArgs a) {
   constexpr int NS = M::NS_STORE;   // rows of the stored state (the balanced model integrates 11 of 23)
   __shared__ float stage[BLOCK * PVDER_OBS_DIM];
@@ -163,9 +171,8 @@ __global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS_SPLIT)
   constexpr int NS = 23;
   __shared__ float stage[SPLIT_ENVS_PER_BLOCK * PVDER_OBS_DIM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane < 30 ? lane / 3 : SPLIT_ENVS_PER_WARP - 1;
-  const int p = lane < 30 ? lane - 3 * g : lane - 30;
-  const Lanes3 ln{0xffffffffu, 3 * g, p};
+  const Lanes3 ln = make_lanes(lane);
+  const int g = ln.base / 3, p = ln.p;
   const int64_t block_first = (int64_t)blockIdx.x * SPLIT_ENVS_PER_BLOCK;
   const int slot = warp * SPLIT_ENVS_PER_WARP + g;
   const int64_t e = block_first + slot;
@@ -174,32 +181,36 @@ __global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS_SPLIT)
   const bool writer = active && lane < 30;
   const bool owner = writer && p == 0;
 
+  auto load_env = [&](EnvRegsSplit& r) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.y.p[i] = a.sd[(int64_t)(6 * p + i) * a.ld + ec];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) r.y.s[i] = a.sd[(int64_t)(18 + i) * a.ld + ec];
+    r.Qref = a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + ec];
+    r.Vdcref = a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + ec];
+    r.Vgrid = a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + ec];
+    r.Sinsol = a.sd[(int64_t)PVDER_SD_SINSOL(NS) * a.ld + ec];
+    r.ret = a.sd[(int64_t)PVDER_SD_RETURN(NS) * a.ld + ec];
+    r.last_reward = a.sd[(int64_t)PVDER_SD_REWARD(NS) * a.ld + ec];
+    r.k = a.si[(int64_t)PVDER_SI_K * a.ld + ec];
+    r.steps = a.si[(int64_t)PVDER_SI_STEPS * a.ld + ec];
+    r.episode = a.si[(int64_t)PVDER_SI_EPISODE * a.ld + ec];
+    r.status = a.si[(int64_t)PVDER_SI_STATUS * a.ld + ec];
+    r.done = a.si[(int64_t)PVDER_SI_DONE * a.ld + ec];
+    r.windup = a.si[(int64_t)PVDER_SI_WINDUP * a.ld + ec];
+    r.exact = a.si[(int64_t)PVDER_SI_EXACT * a.ld + ec];
+  };
   EnvRegsSplit r;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) r.y.p[i] = a.sd[(int64_t)(6 * p + i) * a.ld + ec];
-#pragma unroll
-  for (int i = 0; i < 5; ++i) r.y.s[i] = a.sd[(int64_t)(18 + i) * a.ld + ec];
-  r.Qref = a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + ec];
-  r.Vdcref = a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + ec];
-  r.Vgrid = a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + ec];
-  r.Sinsol = a.sd[(int64_t)PVDER_SD_SINSOL(NS) * a.ld + ec];
-  r.ret = a.sd[(int64_t)PVDER_SD_RETURN(NS) * a.ld + ec];
-  r.last_reward = a.sd[(int64_t)PVDER_SD_REWARD(NS) * a.ld + ec];
-  r.k = a.si[(int64_t)PVDER_SI_K * a.ld + ec];
-  r.steps = a.si[(int64_t)PVDER_SI_STEPS * a.ld + ec];
-  r.episode = a.si[(int64_t)PVDER_SI_EPISODE * a.ld + ec];
-  r.status = a.si[(int64_t)PVDER_SI_STATUS * a.ld + ec];
-  r.done = a.si[(int64_t)PVDER_SI_DONE * a.ld + ec];
-  r.windup = a.si[(int64_t)PVDER_SI_WINDUP * a.ld + ec];
-  r.exact = a.si[(int64_t)PVDER_SI_EXACT * a.ld + ec];
+  load_env(r);
   const int act = a.action[ec];
 
   Outputs o;
   int done_out, hist_inc;
   bool hist_clear;
-  // inactive groups run the shadow env too (uniform control flow for the shuffles); they never store
+  // padding groups step the shadow env too (they never store); an env that must not step is restored
+  // from memory after keeping its warp converged
   const bool run = advance_env_split(ln, cfg, tab, r, act, true, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
-                                     done_out, hist_inc, hist_clear);
+                                     done_out, hist_inc, hist_clear, load_env);
 
   if (owner) {
     if (a.reward_f64) a.reward_f64[e] = o.reward;

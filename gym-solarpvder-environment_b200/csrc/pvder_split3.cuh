@@ -28,32 +28,61 @@ namespace pvder {
 // Lane abstraction
 // ---------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
-struct Lanes3 {
+// DYN = false: the whole warp is converged (hot path; the member mask is the compile-time constant
+// 0xffffffff, which lets ptxas drop the destination initialisation of every SHFL).  DYN = true: a
+// divergent region (out-of-line slow path) entered by the lanes in `mask`.
+template <bool DYN>
+struct LanesT {
   using V = double;   // per-phase value: this lane's phase
   using B = bool;
-  unsigned mask;      // lanes executing the current (possibly divergent) region
+  unsigned mask;      // lanes executing the current region (DYN only)
   int base;           // first lane of the group (phase a)
   int p;              // phase of this lane
+  int n1, n2;         // lanes holding the next two phases (cyclic)
 
-  // sum over the three phases in the fixed order (a + b) + c: identical bits in all three lanes
+  PVDER_DEV unsigned m() const { return DYN ? mask : 0xffffffffu; }
+  // Sum over the three phases, two shuffles: own + next + next-next.  Lane a gets (a + b) + c; the other
+  // lanes get the same sum in a rotated order (last-bit differences), so every DECISION derived from a
+  // sum is taken group-wide (any3 / from_a) -- see gains() and the range flag of the Rodas4 core.
   PVDER_DEV double sum3(double v) const {
-    const double a = __shfl_sync(mask, v, base), b = __shfl_sync(mask, v, base + 1), c = __shfl_sync(mask, v, base + 2);
+    const double b = __shfl_sync(m(), v, n1), c = __shfl_sync(m(), v, n2);
+    return __dadd_rn(__dadd_rn(v, b), c);
+  }
+  // fixed order (a + b) + c in all three lanes (outputs: bit-identical to the one-thread kernel)
+  PVDER_DEV double sum3_ordered(double v) const {
+    const double a = __shfl_sync(m(), v, base), b = __shfl_sync(m(), v, base + 1), c = __shfl_sync(m(), v, base + 2);
     return __dadd_rn(__dadd_rn(a, b), c);
   }
-  PVDER_DEV bool any3(bool b) const { return ((__ballot_sync(mask, b) >> base) & 7u) != 0u; }
-  PVDER_DEV double from_a(double v) const { return __shfl_sync(mask, v, base); }
+  PVDER_DEV bool any3(bool b) const { return ((__ballot_sync(m(), b) >> base) & 7u) != 0u; }
+  PVDER_DEV bool any_warp(bool b) const { return __ballot_sync(m(), b) != 0u; }
+  PVDER_DEV double from_a(double v) const { return __shfl_sync(m(), v, base); }
+  PVDER_DEV int from_a(int v) const { return __shfl_sync(m(), v, base); }
   PVDER_DEV double pc(double a, double b, double c) const { return p == 0 ? a : (p == 1 ? b : c); }
   // the lanes of this region for which pred holds (pred must be uniform within a group)
-  PVDER_DEV Lanes3 sub(bool pred) const {
-    Lanes3 l = *this;
-    l.mask = __ballot_sync(mask, pred);
+  PVDER_DEV LanesT<true> sub(bool pred) const {
+    LanesT<true> l;
+    l.mask = __ballot_sync(m(), pred);
+    l.base = base; l.p = p; l.n1 = n1; l.n2 = n2;
     return l;
   }
 };
+using Lanes3 = LanesT<false>;
+PVDER_DEV Lanes3 make_lanes(int lane) {
+  // lanes 3g..3g+2 = phases a, b, c of group g; lanes 30, 31 shadow lanes 27, 28
+  Lanes3 l;
+  const int g = lane < 30 ? lane / 3 : 9;
+  l.p = lane < 30 ? lane - 3 * g : lane - 30;
+  l.base = 3 * g;
+  l.mask = 0xffffffffu;
+  l.n1 = l.base + (l.p + 1) % 3;
+  l.n2 = l.base + (l.p + 2) % 3;
+  return l;
+}
 PVDER_DEV double vfma(double a, double b, double c) { return fma(a, b, c); }
 PVDER_DEV double vsel(bool c, double a, double b) { return c ? a : b; }
 PVDER_DEV bool vgt(double a, double b) { return a > b; }
 PVDER_DEV bool vor(bool a, bool b) { return a || b; }
+PVDER_DEV bool vand(bool a, bool b) { return a && b; }
 PVDER_DEV bool vnonfinite(double a) { return !(bool)isfinite(a); }
 PVDER_DEV double vmul_rn(double a, double b) { return __dmul_rn(a, b); }
 PVDER_DEV double vadd_rn(double a, double b) { return __dadd_rn(a, b); }
@@ -86,19 +115,27 @@ inline V3 vsel(const B3& c, const V3& a, const V3& b) {
   return V3(c.v[0] ? a.v[0] : b.v[0], c.v[1] ? a.v[1] : b.v[1], c.v[2] ? a.v[2] : b.v[2]);
 }
 inline B3 vgt(const V3& a, const V3& b) { return B3{{a.v[0] > b.v[0], a.v[1] > b.v[1], a.v[2] > b.v[2]}}; }
+inline B3 vand(const B3& a, bool b) { return B3{{a.v[0] && b, a.v[1] && b, a.v[2] && b}}; }
 inline B3 vor(const B3& a, const B3& b) { return B3{{a.v[0] || b.v[0], a.v[1] || b.v[1], a.v[2] || b.v[2]}}; }
 inline B3 vnonfinite(const V3& a) { return B3{{!std::isfinite(a.v[0]), !std::isfinite(a.v[1]), !std::isfinite(a.v[2])}}; }
 inline V3 vmul_rn(const V3& a, const V3& b) { return a * b; }
 inline V3 vadd_rn(const V3& a, const V3& b) { return a + b; }
-struct Lanes3 {
+template <bool DYN>
+struct LanesT {
   using V = V3;
   using B = B3;
   double sum3(const V3& v) const { return (v.v[0] + v.v[1]) + v.v[2]; }
+  double sum3_ordered(const V3& v) const { return (v.v[0] + v.v[1]) + v.v[2]; }
   bool any3(const B3& b) const { return b.v[0] || b.v[1] || b.v[2]; }
+  bool any3(bool b) const { return b; }
+  bool any_warp(bool b) const { return b; }
   double from_a(const V3& v) const { return v.v[0]; }
+  double from_a(double v) const { return v; }
+  int from_a(int v) const { return v; }
   V3 pc(double a, double b, double c) const { return V3(a, b, c); }
-  Lanes3 sub(bool) const { return *this; }
+  LanesT<true> sub(bool) const { return LanesT<true>(); }
 };
+using Lanes3 = LanesT<false>;
 #endif
 
 PVDER_DEV Lanes3::B vsame_sign(const Lanes3::V& a, const Lanes3::V& b) {
@@ -117,9 +154,8 @@ PVDER_DEV Lanes3::B vsame_sign(const Lanes3::V& a, const Lanes3::V& b) {
 // Model
 // ---------------------------------------------------------------------------------------------
 struct Split3 {
-  using L = Lanes3;
-  using V = L::V;
-  using B = L::B;
+  using V = Lanes3::V;
+  using B = Lanes3::B;
   static constexpr int NS = 23;
   static constexpr int NS_STORE = 23;
   static constexpr int PHASES = 3;
@@ -155,6 +191,7 @@ struct Split3 {
     double Qp, Ps, vd, wex, wr, dV, dQ, irefR, irefI;
   };
 
+  template <class L>
   static PVDER_DEV Consts consts(const L& ln) {
     constexpr double C3 = 0.86602540378443864676;
     Consts k;
@@ -165,6 +202,7 @@ struct Split3 {
     return k;
   }
 
+  template <class L>
   static PVDER_DEV In inputs(const L& ln, const Consts& k, const Inputs& in) {
     In o;
     const V vgk = ln.pc(in.vg, in.vgb, in.vgc);
@@ -175,6 +213,7 @@ struct Split3 {
     return o;
   }
 
+  template <class L>
   static PVDER_DEV Pt point(const L& ln, const Params& par, const Consts& k, const In& in, const Aux& ax, const Vec& Y) {
     Pt q;
     const V iR = Y.p[0], iI = Y.p[1];
@@ -234,6 +273,7 @@ struct Split3 {
     double piw, piD, piQ, pid, g4h, g5h;
   };
 
+  template <class L>
   static PVDER_DEV void factor(const L& ln, const Params& par, const Consts& k, const In& in, const Aux& ax,
                                const Gains& g, const Vec& y, const Pt& q, double ghinv, const double* luc, Fac& f) {
     const double inv_gh = luc[0];
@@ -307,6 +347,7 @@ struct Split3 {
   }
 
   // b <- W^-1 b
+  template <class L>
   static PVDER_DEV void solve(const L& ln, const Params& par, const Consts& k, const Gains& g, const Fac& f,
                               const Vec& y, double inv_gh, Vec& b) {
     const V iR = y.p[0], iI = y.p[1];
@@ -350,6 +391,7 @@ struct Split3 {
   }
 
   // Anti-windup mode (A.3) sampled at the sub-step start; same decisions as freeze_bits<Model3ph>.
+  template <class L>
   static PVDER_DEV Gains gains(const L& ln, const Params& par, const Consts& k, const In& in, const Vec& y,
                                const double* luc, bool& m_over_out) {
     Gains g;
@@ -360,31 +402,27 @@ struct Split3 {
     const double Vdc = y.s[0], xDC = y.s[1], xQ = y.s[2];
     const double irefR = xDC + par.Kp_DC * (in.Vdcref - Vdc);
     const double irefI = xQ - par.Kp_Q * (in.Qref - Q);
-    const bool i_over = (irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit;
+    // decisions on the shared rows come from sums: take lane a's so the three lanes agree
+    const int sbits = ln.from_a(((irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit ? 1 : 0) |
+                                (same_sign(par.Ki_DC * (in.Vdcref - Vdc), xDC) ? 2 : 0) |
+                                (same_sign(-par.Ki_Q * (in.Qref - Q), xQ) ? 4 : 0));
+    const bool i_over = (sbits & 1) != 0;
     m_over_out = m_over;
+    // branch-free (the warp stays converged for the group votes): flags are masked by the group-wide
+    // over-limit conditions instead of being computed under them
     const V zero(0.0), kig(par.Ki_GCC), wp(par.wp), du_free(luc[1]), du_frz(luc[0]);
-    g.g0 = kig; g.g1 = kig; g.g2 = wp; g.g3 = wp;
-    g.duR = du_free; g.duI = du_free;
-    g.g4 = par.Ki_DC; g.g5 = par.Ki_Q;
-    g.any = false;
-    if (!(m_over || i_over)) return g;
-    bool any = false;
-    if (m_over) {
-      const V uR = y.p[4], uI = y.p[5];
-      const V duR = par.wp * (-uR + (k.rr * irefR - k.ri * irefI) - iR);
-      const V duI = par.wp * (-uI + (k.ri * irefR + k.rr * irefI) - iI);
-      const B f0 = vsame_sign(par.Ki_GCC * uR, y.p[2]), f1 = vsame_sign(par.Ki_GCC * uI, y.p[3]);
-      const B f2 = vsame_sign(duR, uR), f3 = vsame_sign(duI, uI);
-      g.g0 = vsel(f0, zero, kig); g.g1 = vsel(f1, zero, kig);
-      g.g2 = vsel(f2, zero, wp); g.g3 = vsel(f3, zero, wp);
-      g.duR = vsel(f2, du_frz, du_free); g.duI = vsel(f3, du_frz, du_free);
-      any = ln.any3(vor(vor(f0, f1), vor(f2, f3)));
-    }
-    if (i_over) {
-      if (same_sign(par.Ki_DC * (in.Vdcref - Vdc), xDC)) { g.g4 = 0.0; any = true; }
-      if (same_sign(-par.Ki_Q * (in.Qref - Q), xQ)) { g.g5 = 0.0; any = true; }
-    }
-    g.any = any;
+    const V uR = y.p[4], uI = y.p[5];
+    const V duR = par.wp * (-uR + (k.rr * irefR - k.ri * irefI) - iR);
+    const V duI = par.wp * (-uI + (k.ri * irefR + k.rr * irefI) - iI);
+    const B f0 = vand(vsame_sign(par.Ki_GCC * uR, y.p[2]), m_over), f1 = vand(vsame_sign(par.Ki_GCC * uI, y.p[3]), m_over);
+    const B f2 = vand(vsame_sign(duR, uR), m_over), f3 = vand(vsame_sign(duI, uI), m_over);
+    g.g0 = vsel(f0, zero, kig); g.g1 = vsel(f1, zero, kig);
+    g.g2 = vsel(f2, zero, wp); g.g3 = vsel(f3, zero, wp);
+    g.duR = vsel(f2, du_frz, du_free); g.duI = vsel(f3, du_frz, du_free);
+    const bool fdc = i_over && (sbits & 2), fq = i_over && (sbits & 4);
+    g.g4 = fdc ? 0.0 : par.Ki_DC;
+    g.g5 = fq ? 0.0 : par.Ki_Q;
+    g.any = ln.any3(vor(vor(f0, f1), vor(f2, f3))) || fdc || fq;
     return g;
   }
 };
@@ -394,8 +432,8 @@ struct Split3 {
 // side-inputs as rodas4_core).  K1..K4 are folded into the stage-5/6 sums as soon as K4 exists, so
 // at most five lane-vectors are live.
 // ---------------------------------------------------------------------------------------------
-template <bool EXACT>
-PVDER_DEV bool rodas4_core_split(const Lanes3& ln, Split3::Vec& y, const pvder_env_config& cfg, const Inputs& in_s,
+template <bool EXACT, class LN>
+PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_config& cfg, const Inputs& in_s,
                                  const Split3::In& in, const Split3::Consts& k, const RodasTab& tab,
                                  const Split3::Gains& g, Aux& base) {
   using S = Split3;
@@ -482,7 +520,7 @@ PVDER_DEV bool rodas4_core_split(const Lanes3& ln, Split3::Vec& y, const pvder_e
 #undef ST
 #undef PVDER_EACH
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  if (oor) return false;
+  if (!EXACT && ln.any3(oor)) return false;   // group-wide: the three lanes must agree on the redo
   y = Y;
   base = ax;
   return true;
@@ -494,7 +532,7 @@ struct SplitStepResult {
   Split3::Vec y;
   Aux base;
 };
-PVDER_NOINLINE SplitStepResult rodas4_exact_split(Lanes3 ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
+PVDER_NOINLINE SplitStepResult rodas4_exact_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
                                                   Split3::In in, Split3::Consts k, const RodasTab* tab,
                                                   Split3::Gains g, Aux base) {
   SplitStepResult r;
@@ -513,7 +551,8 @@ struct EnvRegsSplit {
 
 // Outputs from the lane-split state: the same individually rounded operations as
 // compute_outputs_p<3>, with the three phase terms summed in the same order.
-PVDER_DEV void compute_outputs_split(const Lanes3& ln, const pvder_env_config& cfg, const Split3::Consts& kc,
+template <class LN>
+PVDER_DEV void compute_outputs_split(const LN& ln, const pvder_env_config& cfg, const Split3::Consts& kc,
                                      const Split3::Vec& y, double Qref, double Vdcref, double Vgrid, double Sinsol,
                                      int k, Outputs& o) {
   using V = Split3::V;
@@ -523,14 +562,15 @@ PVDER_DEV void compute_outputs_split(const Lanes3& ln, const pvder_env_config& c
   const V jR = y.p[0], jI = y.p[1];
   const V vkR = vadd_rn(inp.vgR, vadd_rn(vmul_rn(par.Rt, jR), -vmul_rn(par.Xt, jI)));
   const V vkI = vadd_rn(inp.vgI, vadd_rn(vmul_rn(par.Xt, jR), vmul_rn(par.Rt, jI)));
-  const double Ppcc = ln.sum3(vmul_rn(0.5, vadd_rn(vmul_rn(vkR, jR), vmul_rn(vkI, jI))));
-  const double Qpcc = ln.sum3(vmul_rn(0.5, vadd_rn(vmul_rn(vkI, jR), -vmul_rn(vkR, jI))));
-  const double v2 = ln.sum3(vadd_rn(vmul_rn(vkR, vkR), vmul_rn(vkI, vkI)));
+  const double Ppcc = ln.sum3_ordered(vmul_rn(0.5, vadd_rn(vmul_rn(vkR, jR), vmul_rn(vkI, jI))));
+  const double Qpcc = ln.sum3_ordered(vmul_rn(0.5, vadd_rn(vmul_rn(vkI, jR), -vmul_rn(vkR, jI))));
+  const double v2 = ln.sum3_ordered(vadd_rn(vmul_rn(vkR, vkR), vmul_rn(vkI, vkI)));
   finish_outputs<3>(cfg, in, ln.from_a(jR), ln.from_a(jI), ln.from_a(vkR), ln.from_a(vkI), Ppcc, Qpcc, v2, y.s[0], Qref,
                     Vdcref, k, o);
 }
 
-PVDER_DEV void init_env_split(const Lanes3& ln, const pvder_env_config& cfg, Split3::Vec& y, double& Qref,
+template <class LN>
+PVDER_DEV void init_env_split(const LN& ln, const pvder_env_config& cfg, Split3::Vec& y, double& Qref,
                               double& Vdcref, double& Vgrid, double& Sinsol) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) y.p[i] = ln.pc(cfg.y0[i], cfg.y0[6 + i], cfg.y0[12 + i]);
@@ -543,14 +583,18 @@ PVDER_DEV void init_env_split(const Lanes3& ln, const pvder_env_config& cfg, Spl
 }
 
 // One env step of one env on three lanes (every lane runs the same bookkeeping; see advance_env for
-// the reference line numbers).  `ln` covers the lanes that entered; all three lanes of a group agree
-// on every branch taken here.
-PVDER_DEV bool advance_env_split(const Lanes3& ln_in, const pvder_env_config& cfg, const RodasTab& tab, EnvRegsSplit& r,
+// the reference line numbers).  The warp stays converged through the integration: when at least one env
+// of the warp steps, ALL its lanes integrate -- an env that must not step (done, bad action, padding)
+// works on values that `restore(r)` afterwards reloads from memory (rare, cold).  That keeps every
+// shuffle on the compile-time full mask; only the out-of-line slow path runs under a ballot mask.
+template <class Restore>
+PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, const RodasTab& tab, EnvRegsSplit& r,
                                  int act, bool active, const double* vtab, const double* stab, int64_t ld, int64_t e,
-                                 uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear) {
+                                 uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear,
+                                 Restore restore) {
   using S = Split3;
   const Params& par = cfg.par;
-  const S::Consts kc = S::consts(ln_in);
+  const S::Consts kc = S::consts(ln);
   hist_inc = -1;
   hist_clear = false;
   bool run = active && !r.done;                     // PVDER_env.py:145-154: step after done is a no-op
@@ -558,7 +602,6 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln_in, const pvder_env_config& cf
     r.status = PVDER_STATUS_BAD_ACTION;
     run = false;
   }
-  const Lanes3 ln = ln_in.sub(run);
   if (run) {
     hist_inc = act;                                          // env_utilities.py:25-30
     r.steps += 1;                                            // PVDER_env.py:156
@@ -566,6 +609,10 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln_in, const pvder_env_config& cf
     const double dV = (act == 3) ? cfg.delVdc_pu : ((act == 4) ? -cfg.delVdc_pu : 0.0);
     r.Qref = __dadd_rn(r.Qref, dQ);                          // PVDER_env.py:225
     r.Vdcref = __dadd_rn(r.Vdcref, dV);                      // PVDER_env.py:229
+  }
+  const bool any_run = ln.any_warp(run);                     // warp-uniform
+  if (any_run) {
+    const int status_in = r.status;
     int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
     int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
     Aux base;
@@ -581,7 +628,7 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln_in, const pvder_env_config& cf
       if (g.any) r.windup += 1;
       for (int m = 0; m < cfg.micro; ++m) {
         const bool ok = rodas4_core_split<false>(ln, r.y, cfg, in_s, in, kc, tab, g, base);
-        const Lanes3 lx = ln.sub(!ok);
+        const LanesT<true> lx = ln.sub(!ok);
         if (!ok) {
           const SplitStepResult res = rodas4_exact_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base);
           r.y = res.y;
@@ -599,13 +646,18 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln_in, const pvder_env_config& cf
     auto bad = vnonfinite(r.y.p[0]);
 #pragma unroll
     for (int i = 1; i < 6; ++i) bad = vor(bad, vnonfinite(r.y.p[i]));
-    bool finite = !ln.any3(bad);
+    bool nonfinite = false;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) finite &= (bool)isfinite(r.y.s[i]);
-    if (!finite) r.status = PVDER_STATUS_NONFINITE;
+    for (int i = 0; i < 5; ++i) nonfinite |= !(bool)isfinite(r.y.s[i]);
+    nonfinite = ln.any3(bad) || ln.any3(nonfinite);
+    if (nonfinite) r.status = PVDER_STATUS_NONFINITE;
+    if (!run) {            // this env was only keeping the warp converged: undo
+      restore(r);
+      r.status = status_in;
+    }
   }
 
-  compute_outputs_split(ln_in, cfg, kc, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o);
+  compute_outputs_split(ln, cfg, kc, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o);
   done_out = r.done;
   if (run) {
     if (r.status == PVDER_STATUS_NONFINITE) {   // PVDER_env.py:170-172: -100, episode ends
@@ -621,8 +673,9 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln_in, const pvder_env_config& cf
     o.reward = r.last_reward;                   // cached tuple, PVDER_env.py:196
     o.reward_i = (int)r.last_reward;
   }
-  if (run && done_out && cfg.auto_reset) {
-    init_env_split(ln_in, cfg, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol);
+  const bool reset_now = run && done_out && cfg.auto_reset;
+  if (reset_now) {
+    init_env_split(ln, cfg, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol);
     r.episode += 1;
     r.k = 0; r.steps = 0; r.done = 0; r.ret = 0.0; r.status = PVDER_STATUS_OK; r.windup = 0; r.exact = 0;
     if (cfg.ev_start_k == 0 && cfg.ev_count > 0)
@@ -630,17 +683,15 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln_in, const pvder_env_config& cf
     hist_inc = -1;
     hist_clear = true;
   }
-  // outputs after an auto-reset are those of the new episode's first state (vector-env convention);
-  // the sums need all lanes, so the recomputation is not under the (group-uniform) reset branch
-  {
-    const bool redo = run && done_out && cfg.auto_reset;
-    const double rew = o.reward;
-    const int rew_i = o.reward_i;
-    const Lanes3 lr = ln_in.sub(redo);
-    if (redo) {
-      compute_outputs_split(lr, cfg, kc, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o);
-      o.reward = rew;
-      o.reward_i = rew_i;
+  // Vector-env convention: after an auto-reset the observation is the first of the new episode, the
+  // reward/done are the final ones.  The output sums need the whole warp, so they are recomputed
+  // under a warp-uniform condition and selected per env.
+  if (ln.any_warp(reset_now)) {
+    Outputs o2;
+    compute_outputs_split(ln, cfg, kc, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o2);
+    if (reset_now) {
+#pragma unroll
+      for (int j = 0; j < PVDER_OBS_DIM; ++j) o.obs[j] = o2.obs[j];
     }
   }
   return run;

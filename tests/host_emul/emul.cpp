@@ -177,7 +177,7 @@ static void step_all_split(const pvder_env_config& cfg, double* sd, int32_t* si,
     int done_out, hist_inc;
     bool hist_clear;
     const bool run = advance_env_split(ln, cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o,
-                                       done_out, hist_inc, hist_clear);
+                                       done_out, hist_inc, hist_clear, [](EnvRegsSplit&) {});
     if (reward) reward[e] = o.reward;
     if (reward_i) reward_i[e] = o.reward_i;
     if (done) done[e] = (uint8_t)done_out;

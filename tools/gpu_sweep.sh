@@ -1,0 +1,11 @@
+#!/bin/bash
+# Dev tool: kernel-variant sweep on the GPU (build/variants/*.so) + split kernel bench.
+TAG=${1:-sweep}
+O=gpurun_out/$TAG
+mkdir -p $O
+STEPS=40 bash tools/variant_sweep.sh 2>&1 | tee $O/sweep_1ph.txt
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "split or unbalanced or emulation" > $O/pytest_split.log 2>&1; echo "pytest rc=$?" | tee -a $O/summary.txt; tail -3 $O/pytest_split.log | tee -a $O/summary.txt
+python bench.py --model model_2 --three-phase-mode split --steps 40 --no-cpu-baseline > $O/bench_split.json 2> $O/bench_split.err
+python -c "
+import json
+d=json.load(open('$O/bench_split.json')); print('split value=%.4g ms/step=%.4g frac=%.3f' % (d['value'], d['ms_per_step'], d['roofline']['frac']))" | tee -a $O/summary.txt
