@@ -71,6 +71,7 @@ SIGNATURES = {
     "pvder_steady_state": (C.c_int, [C.POINTER(Params), C.c_int, _dbl, _dbl, _dbl, _dbl, _dbl, _vp, _vp, _vp]),
     "pvder_reset": (C.c_int, [_cfgp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _i64, _i64, _vp]),
     "pvder_step": (C.c_int, [_cfgp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "pvder_step_record": (C.c_int, [_cfgp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
     "pvder_generate_events": (C.c_int, [_cfgp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "pvder_sample_actions": (C.c_int, [_u64, _i64, _vp, _i64, _i64, _vp]),
     "pvder_stats_reduce": (C.c_int, [_vp, _vp, _i64, C.c_int, _i64, _vp, _vp]),

@@ -494,6 +494,26 @@ PVDER_DEV void store_state(double* sd, int64_t ld, int64_t e, const double (&y)[
 }
 
 
+// Trajectory recording (what the reference's SimulationResults plots, PVDER_env.py:358-364): the
+// stored-layout state after half-cycle sub-step s of this env step, then the event values that were in
+// force during it.  traj is this env's column of a [n_sub_per_step][NS_STORE + 2][traj_ld] array.
+template <class M>
+PVDER_DEV void record_substep(double* traj, int64_t traj_ld, int s, const double (&y)[M::NS], double Vgrid, double Sinsol) {
+  constexpr int ROWS = M::NS_STORE + 2;
+  double* row = traj + (int64_t)s * ROWS * traj_ld;
+  if constexpr (M::BALANCED3) {
+    double z[23];
+    expand_balanced(y, z);
+#pragma unroll
+    for (int i = 0; i < 23; ++i) row[(int64_t)i * traj_ld] = z[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < M::NS; ++i) row[(int64_t)i * traj_ld] = y[i];
+  }
+  row[(int64_t)M::NS_STORE * traj_ld] = Vgrid;
+  row[(int64_t)(M::NS_STORE + 1) * traj_ld] = Sinsol;
+}
+
 // Registers of one environment.
 template <class M>
 struct EnvRegs {
@@ -526,7 +546,7 @@ PVDER_DEV void init_env(const pvder_env_config& cfg, double (&y)[M::NS], double&
 template <class M>
 PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, EnvRegs<M>& r, int act, bool active, const double* vtab,
                            const double* stab, int64_t ld, int64_t e, uint32_t env_glob, Outputs& o, int& done_out,
-                           int& hist_inc, bool& hist_clear) {
+                           int& hist_inc, bool& hist_clear, double* traj = nullptr, int64_t traj_ld = 0) {
   constexpr int NS = M::NS;
   const Params& par = cfg.par;
   hist_inc = -1;
@@ -560,6 +580,7 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
       if (M::BALANCED3 && m_over) r.status = PVDER_STATUS_UNBALANCED;
       for (int m = 0; m < cfg.micro; ++m)
         if (!rodas4_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
+      if (traj) record_substep<M>(traj, traj_ld, s, r.y, r.Vgrid, r.Sinsol);
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
@@ -612,7 +633,8 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
 // the 11-state balanced model, anything else by the general 23-state model.
 PVDER_DEV bool advance_env_auto3(const pvder_env_config& cfg, const RodasTab& tab, EnvRegs<Model3ph>& r, int act,
                                  bool active, const double* vtab, const double* stab, int64_t ld, int64_t e,
-                                 uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear) {
+                                 uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear,
+                                 double* traj = nullptr, int64_t traj_ld = 0) {
   if (is_balanced(r.y)) {
     EnvRegs<Model3phBal> b;
 #pragma unroll
@@ -623,14 +645,15 @@ PVDER_DEV bool advance_env_auto3(const pvder_env_config& cfg, const RodasTab& ta
     b.last_reward = r.last_reward; b.k = r.k; b.steps = r.steps; b.episode = r.episode; b.status = r.status;
     b.done = r.done; b.windup = r.windup; b.exact = r.exact;
     const bool run = advance_env<Model3phBal>(cfg, tab, b, act, active, vtab, stab, ld, e, env_glob, o, done_out,
-                                              hist_inc, hist_clear);
+                                              hist_inc, hist_clear, traj, traj_ld);
     expand_balanced(b.y, r.y);
     r.Qref = b.Qref; r.Vdcref = b.Vdcref; r.Vgrid = b.Vgrid; r.Sinsol = b.Sinsol; r.ret = b.ret;
     r.last_reward = b.last_reward; r.k = b.k; r.steps = b.steps; r.episode = b.episode; r.status = b.status;
     r.done = b.done; r.windup = b.windup; r.exact = b.exact;
     return run;
   }
-  return advance_env<Model3ph>(cfg, tab, r, act, active, vtab, stab, ld, e, env_glob, o, done_out, hist_inc, hist_clear);
+  return advance_env<Model3ph>(cfg, tab, r, act, active, vtab, stab, ld, e, env_glob, o, done_out, hist_inc, hist_clear,
+                               traj, traj_ld);
 }
 
 }  // namespace pvder

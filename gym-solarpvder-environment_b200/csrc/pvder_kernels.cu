@@ -61,7 +61,15 @@ struct StepArgs {
   uint8_t* done;
   int64_t n;
   int64_t env_offset;
+  double* traj;          // optional [n_sub_per_step][NS_STORE + 2][traj_n]: envs e = j * traj_stride, j < traj_n
+  int64_t traj_n;
+  int64_t traj_stride;
 };
+
+__device__ __forceinline__ double* traj_column(const StepArgs& a, int64_t e, bool active) {
+  if (!a.traj || !active || (e % a.traj_stride) != 0 || e / a.traj_stride >= a.traj_n) return nullptr;
+  return a.traj + e / a.traj_stride;
+}
 
 // Coalesced store of a block's obs rows ([BLOCK][11] contiguous in HBM) through shared memory.
 __device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const Outputs& o, int64_t block_first,
@@ -115,12 +123,13 @@ __global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_e
   int done_out, hist_inc;
   bool hist_clear;
   bool run;
+  double* traj = traj_column(a, e, active);
   if constexpr (AUTO3)
     run = advance_env_auto3(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o, done_out,
-                            hist_inc, hist_clear);
+                            hist_inc, hist_clear, traj, a.traj_n);
   else
     run = advance_env<M>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o, done_out,
-                         hist_inc, hist_clear);
+                         hist_inc, hist_clear, traj, a.traj_n);
 
   if (active) {
     if (a.reward_f64) a.reward_f64[e] = o.reward;
@@ -209,8 +218,9 @@ __global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS_SPLIT)
   bool hist_clear;
   // padding groups step the shadow env too (they never store); an env that must not step is restored
   // from memory after keeping its warp converged
+  double* traj = traj_column(a, e, writer);
   const bool run = advance_env_split(ln, cfg, tab, r, act, true, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
-                                     done_out, hist_inc, hist_clear, load_env);
+                                     done_out, hist_inc, hist_clear, load_env, traj, a.traj_n);
 
   if (owner) {
     if (a.reward_f64) a.reward_f64[e] = o.reward;
@@ -502,15 +512,18 @@ int pvder_reset(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld
                       (cudaStream_t)stream);
 }
 
-int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
-               const double* vgrid_tab, const double* sinsol_tab, float* obs_f32, double* obs_f64, double* reward_f64,
-               int32_t* reward_i32, uint8_t* done, int64_t n_envs, int64_t env_offset, void* stream) {
+static int launch_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+                       const double* vgrid_tab, const double* sinsol_tab, float* obs_f32, double* obs_f64, double* reward_f64,
+                       int32_t* reward_i32, uint8_t* done, int64_t n_envs, int64_t env_offset, double* traj, int64_t traj_n,
+                       int64_t traj_stride, void* stream) {
   int rc = check_cfg(cfg);
   if (rc) return rc;
   if (!sd || !si || !action || n_envs < 0 || ld < n_envs) return PVDER_ERR_INVALID;
   if (cfg->event_mode == PVDER_EVENTS_TABLE && cfg->ev_count > 0 && (!vgrid_tab || !sinsol_tab)) return PVDER_ERR_INVALID;
   if (n_envs == 0) return PVDER_OK;
-  StepArgs a{sd, si, ld, action, vgrid_tab, sinsol_tab, obs_f32, obs_f64, reward_f64, reward_i32, done, n_envs, env_offset};
+  if (traj && (traj_n < 1 || traj_stride < 1)) return PVDER_ERR_INVALID;
+  StepArgs a{sd, si, ld, action, vgrid_tab, sinsol_tab, obs_f32, obs_f64, reward_f64, reward_i32, done, n_envs, env_offset,
+             traj, traj_n, traj_stride};
   const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
   const double hinv = cfg->substeps_per_sec * (double)cfg->micro;
@@ -526,6 +539,22 @@ int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld,
   else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3ph>(cfg->par, hinv), a);
   CK(cudaGetLastError());
   return PVDER_OK;
+}
+
+int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+               const double* vgrid_tab, const double* sinsol_tab, float* obs_f32, double* obs_f64, double* reward_f64,
+               int32_t* reward_i32, uint8_t* done, int64_t n_envs, int64_t env_offset, void* stream) {
+  return launch_step(cfg, sd, si, ld, action, vgrid_tab, sinsol_tab, obs_f32, obs_f64, reward_f64, reward_i32, done, n_envs,
+                     env_offset, nullptr, 0, 1, stream);
+}
+
+int pvder_step_record(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+                      const double* vgrid_tab, const double* sinsol_tab, float* obs_f32, double* obs_f64,
+                      double* reward_f64, int32_t* reward_i32, uint8_t* done, int64_t n_envs, int64_t env_offset,
+                      double* traj, int64_t traj_envs, int64_t traj_stride, void* stream) {
+  if (!traj) return PVDER_ERR_INVALID;
+  return launch_step(cfg, sd, si, ld, action, vgrid_tab, sinsol_tab, obs_f32, obs_f64, reward_f64, reward_i32, done, n_envs,
+                     env_offset, traj, traj_envs, traj_stride, stream);
 }
 
 int pvder_generate_events(const pvder_env_config* cfg, const int32_t* episode, double* vgrid_tab, double* sinsol_tab,

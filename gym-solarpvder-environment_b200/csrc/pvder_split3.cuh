@@ -582,6 +582,35 @@ PVDER_DEV void init_env_split(const LN& ln, const pvder_env_config& cfg, Split3:
   Sinsol = 100.0;
 }
 
+// Trajectory recording (see record_substep): every lane writes the rows of its phase, lane a the shared
+// tail and the event values.  traj is null in the lanes that do not record.
+#ifdef __CUDACC__
+template <class LN>
+PVDER_DEV void record_substep_split(const LN& ln, double* traj, int64_t traj_ld, int s, const Split3::Vec& y, double Vgrid,
+                                    double Sinsol) {
+  double* row = traj + (int64_t)s * 25 * traj_ld;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) row[(int64_t)(6 * ln.p + i) * traj_ld] = y.p[i];
+  if (ln.p == 0) {
+#pragma unroll
+    for (int i = 0; i < 5; ++i) row[(int64_t)(18 + i) * traj_ld] = y.s[i];
+    row[(int64_t)23 * traj_ld] = Vgrid;
+    row[(int64_t)24 * traj_ld] = Sinsol;
+  }
+}
+#else
+template <class LN>
+inline void record_substep_split(const LN&, double* traj, int64_t traj_ld, int s, const Split3::Vec& y, double Vgrid,
+                                 double Sinsol) {
+  double* row = traj + (int64_t)s * 25 * traj_ld;
+  for (int i = 0; i < 6; ++i)
+    for (int k = 0; k < 3; ++k) row[(int64_t)(6 * k + i) * traj_ld] = y.p[i].v[k];
+  for (int i = 0; i < 5; ++i) row[(int64_t)(18 + i) * traj_ld] = y.s[i];
+  row[(int64_t)23 * traj_ld] = Vgrid;
+  row[(int64_t)24 * traj_ld] = Sinsol;
+}
+#endif
+
 // One env step of one env on three lanes (every lane runs the same bookkeeping; see advance_env for
 // the reference line numbers).  The warp stays converged through the integration: when at least one env
 // of the warp steps, ALL its lanes integrate -- an env that must not step (done, bad action, padding)
@@ -591,7 +620,7 @@ template <class Restore>
 PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, const RodasTab& tab, EnvRegsSplit& r,
                                  int act, bool active, const double* vtab, const double* stab, int64_t ld, int64_t e,
                                  uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear,
-                                 Restore restore) {
+                                 Restore restore, double* traj = nullptr, int64_t traj_ld = 0) {
   using S = Split3;
   const Params& par = cfg.par;
   const S::Consts kc = S::consts(ln);
@@ -636,6 +665,7 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
           r.exact += 1;
         }
       }
+      if (traj) record_substep_split(ln, traj, traj_ld, s, r.y, r.Vgrid, r.Sinsol);
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);

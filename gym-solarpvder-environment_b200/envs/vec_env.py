@@ -69,6 +69,8 @@ class PVDERVecEnv:
         self._initialised = False
         self._step_index = 0
         self.launches = 0
+        self.traj = None
+        self._traj_stride = 1
 
     # ---- plumbing -------------------------------------------------------------------------
     def _stream(self):
@@ -104,14 +106,37 @@ class PVDERVecEnv:
         if actions.numel() != self.num_envs:
             raise ValueError("actions must have num_envs elements")
         with t.cuda.device(self.device):
-            _cabi.check(self.lib.pvder_step(self._cfgp(), _ptr(self.sd), _ptr(self.si), self.ld, _ptr(actions),
-                                            _ptr(self.vgrid_tab), _ptr(self.sinsol_tab), _ptr(self.obs),
-                                            _ptr(self.obs64), _ptr(self.reward), _ptr(self.reward_i), _ptr(self.done),
-                                            self.num_envs, self.env_offset, self._stream()))
+            if self.traj is None:
+                _cabi.check(self.lib.pvder_step(self._cfgp(), _ptr(self.sd), _ptr(self.si), self.ld, _ptr(actions),
+                                                _ptr(self.vgrid_tab), _ptr(self.sinsol_tab), _ptr(self.obs),
+                                                _ptr(self.obs64), _ptr(self.reward), _ptr(self.reward_i), _ptr(self.done),
+                                                self.num_envs, self.env_offset, self._stream()))
+            else:
+                _cabi.check(self.lib.pvder_step_record(self._cfgp(), _ptr(self.sd), _ptr(self.si), self.ld, _ptr(actions),
+                                                       _ptr(self.vgrid_tab), _ptr(self.sinsol_tab), _ptr(self.obs),
+                                                       _ptr(self.obs64), _ptr(self.reward), _ptr(self.reward_i),
+                                                       _ptr(self.done), self.num_envs, self.env_offset, _ptr(self.traj),
+                                                       self.traj.shape[2], self._traj_stride, self._stream()))
         self.launches += 1
         self._step_index += 1
         reward = self.reward_i if self.cfg.DISCRETE_REWARD else self.reward
         return self.obs, reward, self.done.view(t.bool), {}
+
+    def record_trajectory(self, n_envs=1, stride=1):
+        """Record, from the next step() on, the state after every half-cycle sub-step of the envs
+        0, stride, 2*stride, ... (n_envs of them) -- the per-sub-step time series the reference plots through
+        pvder's SimulationResults (PVDER_env.py:358-364).  After each step ``self.traj`` holds
+        [n_sub_per_step, n_state + 2, n_envs] (rows: state in stored order with the PLL angle as delta, then
+        Vgrid and Sinsol in force).  ``record_trajectory(0)`` switches recording off."""
+        t = self.torch
+        if n_envs <= 0:
+            self.traj = None
+            return None
+        if (n_envs - 1) * stride >= self.num_envs:
+            raise ValueError("recorded envs exceed num_envs")
+        self._traj_stride = int(stride)
+        self.traj = t.zeros((self.cfg.c.n_sub_per_step, self.ns + 2, int(n_envs)), dtype=t.float64, device=self.device)
+        return self.traj
 
     def sample_actions(self, out=None):
         """action_space.sample() for every env, on device (Philox stream 1)."""

@@ -129,6 +129,15 @@ int pvder_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld,
                double* reward_f64, int32_t* reward_i32, uint8_t* done, int64_t n_envs, int64_t env_offset,
                void* stream);
 
+/* step() that also records the trajectory inside the env step (what the reference's SimulationResults
+ * plots after run_simulation(), PVDER_env.py:358-364): for the envs e = j * traj_stride, j < traj_envs,
+ * traj[s][r][j] (device double[n_sub_per_step][6*phases + 5 + 2][traj_envs]) receives the state (stored
+ * layout, PLL angle as delta) after half-cycle sub-step s, then Vgrid and Sinsol in force during it. */
+int pvder_step_record(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+                      const double* vgrid_tab, const double* sinsol_tab, float* obs_f32, double* obs_f64,
+                      double* reward_f64, int32_t* reward_i32, uint8_t* done, int64_t n_envs, int64_t env_offset,
+                      double* traj, int64_t traj_envs, int64_t traj_stride, void* stream);
+
 /* Event generator (replaces SimulationEvents.create_random_events as called at
  * PVDER_env.py:408-411): materialises the per-env tables the step kernel draws on the fly in
  * PVDER_EVENTS_PHILOX mode.  episode: device int32[n_envs] or NULL (= 0). */

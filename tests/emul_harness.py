@@ -61,8 +61,13 @@ class EmulVecEnv:
         self._init = True
         return self.obs64.copy()
 
-    def step(self, actions):
+    def step(self, actions, record=False):
         a = np.ascontiguousarray(actions, dtype=np.int32)
+        if record:
+            self.traj = np.zeros((self.cfg.c.n_sub_per_step, self.ns + 2, self.n))
+            self.lib.emul_set_traj(_p(self.traj))
+        else:
+            self.lib.emul_set_traj(None)
         self.lib.emul_step(C.byref(self.cfg.c), _p(self.sd), _p(self.si), C.c_int64(self.ld), _p(a), _p(self.vtab),
                            _p(self.stab), _p(self.obs64), _p(self.reward), _p(self.reward_i), _p(self.done),
                            C.c_int64(self.n), C.c_int64(self.off))

@@ -13,6 +13,8 @@
 
 using namespace pvder;
 
+static double* g_traj = nullptr;   // optional trajectory buffer [n_sub][NS_STORE + 2][n] of the next emul_step call
+
 template <class M, bool AUTO3 = false>
 static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
                      const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
@@ -41,10 +43,10 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
     bool run;
     if constexpr (AUTO3)
       run = advance_env_auto3(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out, hist_inc,
-                              hist_clear);
+                              hist_clear, g_traj ? g_traj + e : nullptr, n);
     else
       run = advance_env<M>(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out, hist_inc,
-                           hist_clear);
+                           hist_clear, g_traj ? g_traj + e : nullptr, n);
     if (reward) reward[e] = o.reward;
     if (reward_i) reward_i[e] = o.reward_i;
     if (done) done[e] = (uint8_t)done_out;
@@ -177,7 +179,8 @@ static void step_all_split(const pvder_env_config& cfg, double* sd, int32_t* si,
     int done_out, hist_inc;
     bool hist_clear;
     const bool run = advance_env_split(ln, cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o,
-                                       done_out, hist_inc, hist_clear, [](EnvRegsSplit&) {});
+                                       done_out, hist_inc, hist_clear, [](EnvRegsSplit&) {},
+                                       g_traj ? g_traj + e : nullptr, n);
     if (reward) reward[e] = o.reward;
     if (reward_i) reward_i[e] = o.reward_i;
     if (done) done[e] = (uint8_t)done_out;
@@ -278,6 +281,8 @@ int emul_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, 
   else step_all<Model3ph>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   return 0;
 }
+
+void emul_set_traj(double* traj) { g_traj = traj; }
 
 int emul_reset(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, int init, double* obs64, int64_t n,
                int64_t off) {

@@ -442,3 +442,36 @@ def test_split_kernel_full_episode_with_auto_reset(cuda):
         np.testing.assert_allclose(oa.cpu().numpy(), ob.cpu().numpy(), rtol=1e-6, atol=1e-7)
         assert int((ra.cpu().numpy() != rb.cpu().numpy()).sum()) <= 1
     assert int(a_env.si[2, :n].min()) >= 1    # every env went through an auto-reset
+
+
+@pytest.mark.parametrize("model_type,mode", [("model_1", "auto"), ("model_2", "auto"), ("model_2", "split"), ("model_2", False)])
+def test_trajectory_recording(cuda, model_type, mode):
+    """pvder_step_record: per-sub-step states of every 7th env against the C++ build of the same source; the
+    last record is the stored state; envs that are not selected are untouched by recording."""
+    import torch
+    import emul_harness as E
+
+    n, stride, nrec = 100, 7, 12
+    kw = dict(model_type=model_type, events_spec=H.SAG_SPEC, seed=21, DISCRETE_REWARD=True, balanced_three_phase=mode)
+    g = _venv(cuda, n, **kw)
+    ref = _venv(cuda, n, **kw)
+    e = E.EmulVecEnv(n, **kw)
+    g.reset(); ref.reset(); e.reset()
+    traj = g.record_trajectory(nrec, stride)
+    ns = g.ns
+    assert traj.shape == (g.cfg.c.n_sub_per_step, ns + 2, nrec)
+    for step in range(5):
+        a = g.sample_actions()
+        ref._step_index = g._step_index - 0
+        g.step(a)
+        ref.step(a)
+        e.step(a.cpu().numpy(), record=True)
+        torch.cuda.synchronize()
+        t = traj.cpu().numpy()
+        np.testing.assert_array_equal(g.sd[:, :n].cpu().numpy(), ref.sd[:, :n].cpu().numpy())     # recording changes nothing
+        np.testing.assert_array_equal(t[-1, :ns, :], g.sd[:ns, 0:stride * nrec:stride].cpu().numpy())
+        np.testing.assert_allclose(t, e.traj[:, :, 0:stride * nrec:stride], rtol=1e-9, atol=1e-11)
+    with pytest.raises(ValueError):
+        g.record_trajectory(20, 7)
+    g.record_trajectory(0)
+    g.step(g.sample_actions())
