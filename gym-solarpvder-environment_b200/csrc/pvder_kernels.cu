@@ -637,6 +637,9 @@ struct pvder_env {
   double* d_stab;
   cudaStream_t stream;        // compute + H2D
   cudaStream_t copy_stream;   // D2H of finished chunks, overlapped with the next chunk's kernel
+  cudaStream_t h2d_stream;    // H2D of the actions of later chunks, overlapped with the first chunk's kernel
+  cudaEvent_t act_ready[8];
+  int64_t wave_envs;          // envs one full wave of resident CTAs processes (chunks are whole waves)
   cudaEvent_t e0, e1;
   cudaEvent_t chunk_done[8];
   double ms_total;
@@ -658,7 +661,28 @@ int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_of
   h->ns = 6 * cfg->phases + 5;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
   for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
+  for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->act_ready[c], cudaEventDisableTiming));
+  {
+    // one wave = resident CTAs per SM x SMs x envs per CTA of the step kernel this config launches
+    int dev = 0, sms = 148, per_sm = 2;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t envs_per_cta = BLOCK;
+    if (cfg->phases == 1) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<Model1ph>, BLOCK, 0));
+    else if (cfg->balanced3 == PVDER_3PH_BALANCED)
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<Model3phBal>, BLOCK, 0));
+    else if (cfg->balanced3 == PVDER_3PH_AUTO)
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<Model3ph, true>, BLOCK, 0));
+    else if (cfg->balanced3 == PVDER_3PH_SPLIT) {
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_split3, BLOCK, 0));
+      envs_per_cta = SPLIT_ENVS_PER_BLOCK;
+    } else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<Model3ph>, BLOCK, 0));
+    if (per_sm < 1) per_sm = 1;
+    // chunk starts must stay multiples of 32 envs (state rows are read with the chunk offset applied)
+    h->wave_envs = (int64_t)per_sm * sms * envs_per_cta;
+  }
   CK(cudaEventCreate(&h->e0));
   CK(cudaEventCreate(&h->e1));
   CK(cudaMalloc(&h->sd, sizeof(double) * PVDER_SD_FIELDS(h->ns) * h->ld));
@@ -689,6 +713,8 @@ int pvder_env_destroy(pvder_env* h) {
   cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_vtab); cudaFree(h->d_stab);
   cudaEventDestroy(h->e0); cudaEventDestroy(h->e1);
   for (int c = 0; c < 8; ++c) cudaEventDestroy(h->chunk_done[c]);
+  for (int c = 0; c < 8; ++c) cudaEventDestroy(h->act_ready[c]);
+  cudaStreamDestroy(h->h2d_stream);
   cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -722,23 +748,54 @@ int pvder_env_reset_host(pvder_env* h, float* obs_out, double* obs64_out) {
 int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
                         uint8_t* done_out) {
   if (!h || !action) return PVDER_ERR_INVALID;
-  // Large batches are processed in up to 8 chunks of whole CTAs: the D2H copy of chunk c runs on
-  // the copy stream while the kernel of chunk c+1 runs on the compute stream.
-  int chunks = 1;
-  if (h->n >= (1 << 16)) chunks = 8;
-  const int64_t per = ((h->n + chunks - 1) / chunks + BLOCK - 1) / BLOCK * BLOCK;
-  CK(cudaMemcpyAsync(h->d_action, action, sizeof(int32_t) * h->n, cudaMemcpyHostToDevice, h->stream));
+  // Large batches are cut into up to 8 chunks of WHOLE WAVES of resident CTAs (no partial-wave tail per
+  // launch) whose sizes shrink geometrically: the D2H copy of chunk c (copy stream) and the H2D copy of
+  // the actions of chunk c+1 (h2d stream) run under the kernel of the neighbouring chunk, and only the
+  // small last chunk's results are copied after the last kernel.  D2H moves ~53 B/env at PCIe speed,
+  // about 3x faster than the kernel produces them, so each chunk may be up to 3x smaller than the
+  // previous one and still hide its predecessor's copy.
+  int64_t start[9];
+  int chunks = 0;
+  start[0] = 0;
+  const int64_t waves = h->n / h->wave_envs;      // whole waves available
+  if (h->n < (1 << 16) || waves < 4) {
+    start[1] = h->n;
+    chunks = 1;
+  } else {
+    // sizes in waves, built from the end: 1, 3, 9, ... while waves remain (each chunk hides the copy of
+    // the 3x larger chunk before it); the first chunk takes what is left (<= 3x the second)
+    int64_t sizes[8];
+    int k = 0;
+    int64_t rest = waves, last = 0;
+    while (k < 7 && rest > 3 * last) {
+      const int64_t w = last ? 3 * last : 1;
+      sizes[k++] = w;
+      rest -= w;
+      last = w;
+    }
+    sizes[k++] = rest;                            // first chunk
+    int64_t pos = 0;
+    for (int c = k - 1; c >= 0; --c) {            // largest first, one-wave chunk last
+      pos += sizes[c] * h->wave_envs;
+      start[++chunks] = pos;
+    }
+    start[chunks] = h->n;                         // the remainder (< 1 wave) rides with the last chunk
+  }
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t lo = start[c], cnt = start[c + 1] - lo;
+    CK(cudaMemcpyAsync(h->d_action + lo, action + lo, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, h->h2d_stream));
+    CK(cudaEventRecord(h->act_ready[c], h->h2d_stream));
+  }
   CK(cudaEventRecord(h->e0, h->stream));
   for (int c = 0; c < chunks; ++c) {
-    const int64_t lo = (int64_t)c * per;
-    if (lo >= h->n) break;
-    const int64_t cnt = (h->n - lo < per) ? (h->n - lo) : per;
+    const int64_t lo = start[c], cnt = start[c + 1] - lo;
+    CK(cudaStreamWaitEvent(h->stream, h->act_ready[c], 0));
     int rc = pvder_step(&h->cfg, h->sd + lo, h->si + lo, h->ld, h->d_action + lo, h->d_vtab ? h->d_vtab + lo : nullptr,
                         h->d_stab ? h->d_stab + lo : nullptr, obs_out ? h->d_obs + lo * PVDER_OBS_DIM : nullptr,
                         obs64_out ? h->d_obs64 + lo * PVDER_OBS_DIM : nullptr, h->d_reward + lo, nullptr, h->d_done + lo,
                         cnt, h->off + lo, h->stream);
     if (rc) return rc;
-    if (c == chunks - 1 || lo + cnt >= h->n) CK(cudaEventRecord(h->e1, h->stream));
+    if (c == chunks - 1) CK(cudaEventRecord(h->e1, h->stream));
     CK(cudaEventRecord(h->chunk_done[c], h->stream));
     CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
     if (obs_out)
