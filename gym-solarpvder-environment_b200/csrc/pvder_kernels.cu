@@ -749,11 +749,11 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
                         uint8_t* done_out) {
   if (!h || !action) return PVDER_ERR_INVALID;
   // Large batches are cut into up to 8 chunks of WHOLE WAVES of resident CTAs (no partial-wave tail per
-  // launch) whose sizes shrink geometrically: the D2H copy of chunk c (copy stream) and the H2D copy of
-  // the actions of chunk c+1 (h2d stream) run under the kernel of the neighbouring chunk, and only the
-  // small last chunk's results are copied after the last kernel.  D2H moves ~53 B/env at PCIe speed,
-  // about 3x faster than the kernel produces them, so each chunk may be up to 3x smaller than the
-  // previous one and still hide its predecessor's copy.
+  // launch) whose sizes shrink by ~1.5x: the D2H copy of chunk c (copy stream) and the H2D copy of the
+  // actions of chunk c+1 (h2d stream) run under the kernels of the neighbouring chunks, and only the
+  // one-wave last chunk's results are copied after the last kernel.  D2H moves ~53 B/env -- about 3x
+  // faster than the kernel produces them on an idle host, less when 8 ranks share the host memory
+  // system -- so a ratio of 1.5 keeps every copy hidden up to a 2x slower link.
   int64_t start[9];
   int chunks = 0;
   start[0] = 0;
@@ -762,16 +762,29 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
     start[1] = h->n;
     chunks = 1;
   } else {
-    // sizes in waves, built from the end: 1, 3, 9, ... while waves remain (each chunk hides the copy of
-    // the 3x larger chunk before it); the first chunk takes what is left (<= 3x the second)
+    // sizes in waves, built from the end as a geometric series 1, q, q^2, ... (q = 1.5, or larger when 8
+    // chunks of ratio 1.5 cannot cover the batch); the first chunk takes what is left
+    double q = 1.5;
+    for (;;) {
+      double sum = 0.0, t = 1.0;
+      for (int i = 0; i < 8; ++i) { sum += t; t *= q; }
+      if (sum >= (double)waves) break;
+      q += 0.1;
+    }
     int64_t sizes[8];
     int k = 0;
-    int64_t rest = waves, last = 0;
-    while (k < 7 && rest > 3 * last) {
-      const int64_t w = last ? 3 * last : 1;
+    int64_t rest = waves;
+    double t = 1.0;
+    while (k < 7) {
+      const int64_t w = (int64_t)(t + 0.5);
+      if (2 * w >= rest) break;      // what is left becomes the first chunk (no more than ~2x the next one)
       sizes[k++] = w;
       rest -= w;
-      last = w;
+      t *= q;
+    }
+    if (k > 0 && k < 7 && rest > 2 * sizes[k - 1]) {   // halve an oversized first chunk
+      sizes[k] = rest / 2;
+      rest -= sizes[k++];
     }
     sizes[k++] = rest;                            // first chunk
     int64_t pos = 0;
