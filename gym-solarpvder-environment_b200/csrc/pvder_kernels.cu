@@ -175,7 +175,12 @@ __global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_e
 constexpr int SPLIT_ENVS_PER_WARP = 10;
 constexpr int SPLIT_ENVS_PER_BLOCK = SPLIT_ENVS_PER_WARP * (BLOCK / 32);
 
-__global__ void __launch_bounds__(BLOCK, PVDER_MINBLOCKS_SPLIT)
+#ifdef PVDER_MAXNREG_SPLIT
+#define PVDER_SPLIT_BOUNDS __maxnreg__(PVDER_MAXNREG_SPLIT)
+#else
+#define PVDER_SPLIT_BOUNDS __launch_bounds__(BLOCK, PVDER_MINBLOCKS_SPLIT)
+#endif
+__global__ void PVDER_SPLIT_BOUNDS
     step_kernel_split3(const __grid_constant__ pvder_env_config cfg, const __grid_constant__ RodasTab tab, const StepArgs a) {
   constexpr int NS = 23;
   __shared__ float stage[SPLIT_ENVS_PER_BLOCK * PVDER_OBS_DIM];

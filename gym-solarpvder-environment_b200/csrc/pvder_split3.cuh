@@ -159,12 +159,29 @@ struct Split3 {
   static constexpr int NS = 23;
   static constexpr int NS_STORE = 23;
   static constexpr int PHASES = 3;
-  static constexpr int N_LUC = 2;
+  static constexpr int N_LUC = 13;
 
-  // luc[0] = 1/ghinv, luc[1] = 1/(ghinv + wp): reciprocal pivots of a clamped / free u row
+  // Launch constants: reciprocal pivots and every gain-derived coefficient of the factorisation for the
+  // common case that no anti-windup clamp is active (FREE instantiations read them from the constant bank
+  // instead of carrying them in registers).
+  enum { LC_INV_GH = 0, LC_DU = 1, LC_GX = 2, LC_TH = 3, LC_KA = 4, LC_TK = 5, LC_G4H = 6, LC_G5H = 7, LC_PID_DC = 8,
+         LC_PIQ = 9, LC_PIW = 10, LC_PID = 11, LC_KIPLL_H = 12 };
   static PVDER_HD void lu_consts(const Params& par, double ghinv, double* luc) {
-    luc[0] = 1.0 / ghinv;
-    luc[1] = 1.0 / (ghinv + par.wp);
+    const double inv_gh = 1.0 / ghinv;
+    luc[LC_INV_GH] = inv_gh;
+    luc[LC_DU] = 1.0 / (ghinv + par.wp);           // reciprocal pivot of a free u row (a clamped one: 1/ghinv)
+    luc[LC_GX] = par.Ki_GCC * inv_gh;
+    luc[LC_TH] = luc[LC_GX] + par.Kp_GCC;
+    luc[LC_KA] = luc[LC_DU] * par.wp;
+    luc[LC_TK] = luc[LC_TH] * luc[LC_KA];
+    luc[LC_G4H] = par.Ki_DC * inv_gh;
+    luc[LC_G5H] = par.Ki_Q * inv_gh;
+    luc[LC_PID_DC] = luc[LC_G4H] + par.Kp_DC;
+    luc[LC_PIQ] = luc[LC_G5H] + par.Kp_Q;
+    const double kpll = par.Ki_PLL * inv_gh + par.Kp_PLL;
+    luc[LC_PIW] = par.inv_wb * kpll;
+    luc[LC_PID] = kpll * inv_gh;
+    luc[LC_KIPLL_H] = par.Ki_PLL * inv_gh;
   }
 
   // One lane's share of a 23-vector: p = (iR, iI, xR, xI, uR, uI) of its phase, s = (Vdc, xDC, xQ,
@@ -239,20 +256,25 @@ struct Split3 {
   }
 
   // Autonomous right-hand side (A.3) from the point record.
+  // FREE: no clamp active in this warp -> the gains are the parameters (constant bank), g is not read.
+  template <bool FREE>
   static PVDER_DEV void rhs(const Params& par, const Consts& k, const Aux& ax, const Gains& g, const Vec& Y, const Pt& q,
                             Vec& F) {
+    const V g0 = FREE ? V(par.Ki_GCC) : g.g0, g1 = FREE ? V(par.Ki_GCC) : g.g1;
+    const V g2 = FREE ? V(par.wp) : g.g2, g3 = FREE ? V(par.wp) : g.g3;
+    const double g4 = FREE ? par.Ki_DC : g.g4, g5 = FREE ? par.Ki_Q : g.g5;
     const double hV = 0.5 * Y.s[0];
     const V iR = Y.p[0], iI = Y.p[1];
     F.p[0] = vfma(q.wr, iI, par.inv_Lf * vfma(q.mR, hV, vfma(-par.Rf, iR, -q.vR)));
     F.p[1] = vfma(-q.wr, iR, par.inv_Lf * vfma(q.mI, hV, vfma(-par.Rf, iI, -q.vI)));
-    F.p[2] = g.g0 * Y.p[4];
-    F.p[3] = g.g1 * Y.p[5];
+    F.p[2] = g0 * Y.p[4];
+    F.p[3] = g1 * Y.p[5];
     const V rfR = vfma(k.rr, q.irefR, -(k.ri * q.irefI)), rfI = vfma(k.ri, q.irefR, k.rr * q.irefI);
-    F.p[4] = g.g2 * ((rfR - Y.p[4]) - iR);
-    F.p[5] = g.g3 * ((rfI - Y.p[5]) - iI);
+    F.p[4] = g2 * ((rfR - Y.p[4]) - iR);
+    F.p[5] = g3 * ((rfI - Y.p[5]) - iI);
     F.s[0] = fma(-0.25 * Y.s[0], q.Ps, ax.Ppv) * (par.inv_C * ax.inv_Vdc);
-    F.s[1] = g.g4 * q.dV;
-    F.s[2] = -(g.g5 * q.dQ);
+    F.s[1] = g4 * q.dV;
+    F.s[2] = -(g5 * q.dQ);
     F.s[3] = par.Ki_PLL * q.vd;
     F.s[4] = q.wex + par.dw;
   }
@@ -270,10 +292,11 @@ struct Split3 {
     double RQ[3], Rv[3], RP[3];   // response of the three sums to beta_1 (d wr), beta_3, beta_4 (d iref)
     double N[9];         // inverse of the 3x3 border matrix, row-major
     double vdd;          // d vd / d delta
-    double piw, piD, piQ, pid, g4h, g5h;
+    double piD, piQ, g4h, g5h;
+    // thR..kaI, gxR, gxI, piD, piQ, g4h, g5h depend on the gains only: FREE instantiations neither write nor read them
   };
 
-  template <class L>
+  template <bool FREE, class L>
   static PVDER_DEV void factor(const L& ln, const Params& par, const Consts& k, const In& in, const Aux& ax,
                                const Gains& g, const Vec& y, const Pt& q, double ghinv, const double* luc, Fac& f) {
     const double inv_gh = luc[0];
@@ -281,13 +304,20 @@ struct Split3 {
     f.e = par.inv_Lf * (0.5 * y.s[0]);
     const double a = fma(par.inv_Lf, par.Rf + par.Rt, ghinv);
     const double c = fma(par.inv_Lf, par.Xt, q.wr);
-    f.gxR = g.g0 * inv_gh;
-    f.gxI = g.g1 * inv_gh;
-    f.thR = f.gxR + par.Kp_GCC;
-    f.thI = f.gxI + par.Kp_GCC;
-    f.kaR = g.duR * g.g2;
-    f.kaI = g.duI * g.g3;
-    const V tkR = f.thR * f.kaR, tkI = f.thI * f.kaI;
+    V tkR, tkI;
+    if (FREE) {
+      tkR = V(luc[LC_TK]);
+      tkI = tkR;
+    } else {
+      f.gxR = g.g0 * inv_gh;
+      f.gxI = g.g1 * inv_gh;
+      f.thR = f.gxR + par.Kp_GCC;
+      f.thI = f.gxI + par.Kp_GCC;
+      f.kaR = g.duR * g.g2;
+      f.kaI = g.duI * g.g3;
+      tkR = f.thR * f.kaR;
+      tkI = f.thI * f.kaI;
+    }
     f.epR = f.e * tkR;
     f.epI = f.e * tkI;
     const V AR = f.epR + a, AI = f.epI + a;
@@ -323,19 +353,23 @@ struct Split3 {
     f.RQ[0] = RQ1; f.RQ[1] = RQ3; f.RQ[2] = RQ4;
     f.Rv[0] = Rv1; f.Rv[1] = Rv3; f.Rv[2] = Rv4;
     f.RP[0] = RP1; f.RP[1] = RP3; f.RP[2] = RP4;
-    const double kpll = fma(par.Ki_PLL, inv_gh, par.Kp_PLL);
-    f.piw = par.inv_wb * kpll;
-    f.pid = kpll * inv_gh;
-    f.g4h = g.g4 * inv_gh;
-    f.g5h = g.g5 * inv_gh;
-    f.piD = f.g4h + par.Kp_DC;
-    f.piQ = f.g5h + par.Kp_Q;
+    const double piw = luc[LC_PIW], pid = luc[LC_PID];
+    double piD, piQ;
+    if (FREE) {
+      piD = luc[LC_PID_DC];
+      piQ = luc[LC_PIQ];
+    } else {
+      f.g4h = g.g4 * inv_gh;
+      f.g5h = g.g5 * inv_gh;
+      f.piD = piD = f.g4h + par.Kp_DC;
+      f.piQ = piQ = f.g5h + par.Kp_Q;
+    }
     const double qC = 0.25 * par.inv_C;
     const double jVV = par.inv_C * ax.inv_Vdc * fma(-ax.Ppv, ax.inv_Vdc, ax.dPpv);
     // border matrix in u = (dQ, d vd, K_Vdc)
-    const double m00 = fma(-RQ4, f.piQ, 1.0), m01 = -(RQ1 * f.piw), m02 = fma(f.piD, RQ3, -RQ2);
-    const double m10 = -(Rv4 * f.piQ), m11 = fma(-f.vdd, f.pid, fma(-Rv1, f.piw, 1.0)), m12 = fma(f.piD, Rv3, -Rv2);
-    const double m20 = qC * (RP4 * f.piQ), m21 = qC * (RP1 * f.piw), m22 = fma(qC, fma(-f.piD, RP3, RP2), ghinv - jVV);
+    const double m00 = fma(-RQ4, piQ, 1.0), m01 = -(RQ1 * piw), m02 = fma(piD, RQ3, -RQ2);
+    const double m10 = -(Rv4 * piQ), m11 = fma(-f.vdd, pid, fma(-Rv1, piw, 1.0)), m12 = fma(piD, Rv3, -Rv2);
+    const double m20 = qC * (RP4 * piQ), m21 = qC * (RP1 * piw), m22 = fma(qC, fma(-piD, RP3, RP2), ghinv - jVV);
     const double k00 = fma(m11, m22, -(m12 * m21)), k01 = fma(m02, m21, -(m01 * m22)), k02 = fma(m01, m12, -(m02 * m11));
     const double k10 = fma(m12, m20, -(m10 * m22)), k11 = fma(m00, m22, -(m02 * m20)), k12 = fma(m02, m10, -(m00 * m12));
     const double k20 = fma(m10, m21, -(m11 * m20)), k21 = fma(m01, m20, -(m00 * m21)), k22 = fma(m00, m11, -(m01 * m10));
@@ -347,13 +381,21 @@ struct Split3 {
   }
 
   // b <- W^-1 b
-  template <class L>
+  template <bool FREE, class L>
   static PVDER_DEV void solve(const L& ln, const Params& par, const Consts& k, const Gains& g, const Fac& f,
-                              const Vec& y, double inv_gh, Vec& b) {
+                              const Vec& y, const double* luc, Vec& b) {
+    const double inv_gh = luc[LC_INV_GH];
+    const V duR = FREE ? V(luc[LC_DU]) : g.duR, duI = FREE ? V(luc[LC_DU]) : g.duI;
+    const V thR = FREE ? V(luc[LC_TH]) : f.thR, thI = FREE ? V(luc[LC_TH]) : f.thI;
+    const V kaR = FREE ? V(luc[LC_KA]) : f.kaR, kaI = FREE ? V(luc[LC_KA]) : f.kaI;
+    const V gxR = FREE ? V(luc[LC_GX]) : f.gxR, gxI = FREE ? V(luc[LC_GX]) : f.gxI;
+    const double piD = FREE ? luc[LC_PID_DC] : f.piD, piQ = FREE ? luc[LC_PIQ] : f.piQ;
+    const double g4h = FREE ? luc[LC_G4H] : f.g4h, g5h = FREE ? luc[LC_G5H] : f.g5h;
+    const double piw = luc[LC_PIW], pid = luc[LC_PID];
     const V iR = y.p[0], iI = y.p[1];
     const V hxR = b.p[2] * inv_gh, hxI = b.p[3] * inv_gh;
-    const V buR = g.duR * b.p[4], buI = g.duI * b.p[5];
-    const V mmR = vfma(f.thR, buR, hxR), mmI = vfma(f.thI, buI, hxI);
+    const V buR = duR * b.p[4], buI = duI * b.p[5];
+    const V mmR = vfma(thR, buR, hxR), mmI = vfma(thI, buI, hxI);
     const V rR = vfma(f.e, mmR, b.p[0]), rI = vfma(f.e, mmI, b.p[1]);
     const V tR = vfma(f.n11, rR, f.n12 * rI), tI = vfma(f.n22, rI, -(f.n12 * rR));
     const double sQ = ln.sum3(vfma(f.qR, tR, f.qI * tI));
@@ -369,25 +411,25 @@ struct Split3 {
     const double dQ = fma(f.N[0], r1, fma(f.N[1], r2, f.N[2] * r3));
     const double dvd = fma(f.N[3], r1, fma(f.N[4], r2, f.N[5] * r3));
     const double KV = fma(f.N[6], r1, fma(f.N[7], r2, f.N[8] * r3));
-    const double be1 = fma(f.piw, dvd, b1);
-    const double be3 = fma(-f.piD, KV, b3);
-    const double be4 = fma(f.piQ, dQ, b4);
+    const double be1 = fma(piw, dvd, b1);
+    const double be3 = fma(-piD, KV, b3);
+    const double be4 = fma(piQ, dQ, b4);
     const V rfR = vfma(k.rr, be3, -(k.ri * be4)), rfI = vfma(k.ri, be3, k.rr * be4);
     const V r2R = vfma(iI, be1, vfma(f.hmR, KV, vfma(f.epR, rfR, rR)));
     const V r2I = vfma(-iR, be1, vfma(f.hmI, KV, vfma(f.epI, rfI, rI)));
     const V KiR = vfma(f.n11, r2R, f.n12 * r2I), KiI = vfma(f.n22, r2I, -(f.n12 * r2R));
-    const V KuR = vfma(f.kaR, rfR - KiR, buR), KuI = vfma(f.kaI, rfI - KiI, buI);
+    const V KuR = vfma(kaR, rfR - KiR, buR), KuI = vfma(kaI, rfI - KiI, buI);
     b.p[0] = KiR;
     b.p[1] = KiI;
-    b.p[2] = vfma(f.gxR, KuR, hxR);
-    b.p[3] = vfma(f.gxI, KuI, hxI);
+    b.p[2] = vfma(gxR, KuR, hxR);
+    b.p[3] = vfma(gxI, KuI, hxI);
     b.p[4] = KuR;
     b.p[5] = KuI;
     b.s[0] = KV;
-    b.s[1] = fma(-f.g4h, KV, b3);
-    b.s[2] = fma(f.g5h, dQ, b4);
-    b.s[3] = fma(par.Ki_PLL * inv_gh, dvd, hp);
-    b.s[4] = fma(f.pid, dvd, kd0);
+    b.s[1] = fma(-g4h, KV, b3);
+    b.s[2] = fma(g5h, dQ, b4);
+    b.s[3] = fma(luc[LC_KIPLL_H], dvd, hp);
+    b.s[4] = fma(pid, dvd, kd0);
   }
 
   // Anti-windup mode (A.3) sampled at the sub-step start; same decisions as freeze_bits<Model3ph>.
@@ -410,7 +452,7 @@ struct Split3 {
     m_over_out = m_over;
     // branch-free (the warp stays converged for the group votes): flags are masked by the group-wide
     // over-limit conditions instead of being computed under them
-    const V zero(0.0), kig(par.Ki_GCC), wp(par.wp), du_free(luc[1]), du_frz(luc[0]);
+    const V zero(0.0), kig(par.Ki_GCC), wp(par.wp), du_free(luc[LC_DU]), du_frz(luc[LC_INV_GH]);
     const V uR = y.p[4], uI = y.p[5];
     const V duR = par.wp * (-uR + (k.rr * irefR - k.ri * irefI) - iR);
     const V duI = par.wp * (-uI + (k.ri * irefR + k.rr * irefI) - iI);
@@ -432,14 +474,13 @@ struct Split3 {
 // side-inputs as rodas4_core).  K1..K4 are folded into the stage-5/6 sums as soon as K4 exists, so
 // at most five lane-vectors are live.
 // ---------------------------------------------------------------------------------------------
-template <bool EXACT, class LN>
+template <bool EXACT, bool FREE, class LN>
 PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_config& cfg, const Inputs& in_s,
                                  const Split3::In& in, const Split3::Consts& k, const RodasTab& tab,
                                  const Split3::Gains& g, Aux& base) {
   using S = Split3;
   using Vec = S::Vec;
   const Params& par = cfg.par;
-  const double inv_gh = tab.luc[0];
   bool oor = false;
   const double dl0 = y.s[4], V0 = y.s[0];
   ppv_from_exp(par, in_s, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
@@ -448,10 +489,10 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   S::Fac fac;
   {
     const S::Pt q = S::point(ln, par, k, in, base, y);
-    S::factor(ln, par, k, in, base, g, y, q, tab.ghinv, tab.luc, fac);
-    S::rhs(par, k, base, g, y, q, K1);
+    S::template factor<FREE>(ln, par, k, in, base, g, y, q, tab.ghinv, tab.luc, fac);
+    S::template rhs<FREE>(par, k, base, g, y, q, K1);
   }
-  S::solve(ln, par, k, g, fac, y, inv_gh, K1);
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K1);
   // the same statement on the six per-phase slots (V) and the five shared slots (double)
 #define PVDER_EACH(ST)                                        \
   _Pragma("unroll") for (int i = 0; i < 6; ++i) { ST(p) }     \
@@ -461,31 +502,31 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K2);
+  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K2);
 #define ST(m) K2.m[i] = vfma(tab.c21, K1.m[i], K2.m[i]);
   PVDER_EACH(ST)
 #undef ST
-  S::solve(ln, par, k, g, fac, y, inv_gh, K2);
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K2);
   // stage 3
 #define ST(m) Y.m[i] = vfma(tab.a32, K2.m[i], vfma(tab.a31, K1.m[i], y.m[i]));
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K3);
+  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K3);
 #define ST(m) K3.m[i] = vfma(tab.c32, K2.m[i], vfma(tab.c31, K1.m[i], K3.m[i]));
   PVDER_EACH(ST)
 #undef ST
-  S::solve(ln, par, k, g, fac, y, inv_gh, K3);
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K3);
   // stage 4
 #define ST(m) Y.m[i] = vfma(tab.a43, K3.m[i], vfma(tab.a42, K2.m[i], vfma(tab.a41, K1.m[i], y.m[i])));
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
+  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K4.m[i] = vfma(tab.c43, K3.m[i], vfma(tab.c42, K2.m[i], vfma(tab.c41, K1.m[i], K4.m[i])));
   PVDER_EACH(ST)
 #undef ST
-  S::solve(ln, par, k, g, fac, y, inv_gh, K4);
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K4);
   // fold K1..K4 into Y5, C5 (-> K2) and C6 (-> K3); K1, K4 are dead afterwards
 #define ST(m)                                                                                                  \
   {                                                                                                            \
@@ -498,11 +539,11 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
 #undef ST
   // stage 5
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
+  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K2.m[i] = K2.m[i] + K4.m[i];
   PVDER_EACH(ST)
 #undef ST
-  S::solve(ln, par, k, g, fac, y, inv_gh, K2);      // K2 = K5
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K2);      // K2 = K5
   // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
 #define ST(m)                                   \
   Y.m[i] = Y.m[i] + K2.m[i];                    \
@@ -510,11 +551,11 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::rhs(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
+  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K3.m[i] = K3.m[i] + K4.m[i];
   PVDER_EACH(ST)
 #undef ST
-  S::solve(ln, par, k, g, fac, y, inv_gh, K3);      // K3 = K6
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K3);      // K3 = K6
 #define ST(m) Y.m[i] = Y.m[i] + K3.m[i];
   PVDER_EACH(ST)
 #undef ST
@@ -536,7 +577,7 @@ PVDER_NOINLINE SplitStepResult rodas4_exact_split(LanesT<true> ln, Split3::Vec y
                                                   Split3::In in, Split3::Consts k, const RodasTab* tab,
                                                   Split3::Gains g, Aux base) {
   SplitStepResult r;
-  rodas4_core_split<true>(ln, y, *cfg, in_s, in, k, *tab, g, base);
+  rodas4_core_split<true, false>(ln, y, *cfg, in_s, in, k, *tab, g, base);
   r.y = y;
   r.base = base;
   return r;
@@ -656,7 +697,10 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
       const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
       if (g.any) r.windup += 1;
       for (int m = 0; m < cfg.micro; ++m) {
-        const bool ok = rodas4_core_split<false>(ln, r.y, cfg, in_s, in, kc, tab, g, base);
+        // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
+        // come from the constant bank (fewer live registers, no spills in the common case)
+        const bool ok = ln.any_warp(g.any) ? rodas4_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base)
+                                           : rodas4_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base);
         const LanesT<true> lx = ln.sub(!ok);
         if (!ok) {
           const SplitStepResult res = rodas4_exact_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base);

@@ -107,6 +107,11 @@ def freeze_bits(cfg, y, inp4):
     return int(load().emul_freeze_bits(C.byref(cfg.c), _p(y), _p(i4)))
 
 
+def split_free_path(on):
+    """frz == 0 calls use the FREE instantiation (gains from the constant table) when on, else the general one."""
+    load().emul_split_free_path(C.c_int(1 if on else 0))
+
+
 def split_rhs(cfg, y, inp4, frz=0):
     """Right-hand side of the lane-split three-phase model (pvder_split3.cuh), lanes emulated on the host."""
     f = np.zeros(23)

@@ -210,6 +210,8 @@ static void step_all_split(const pvder_env_config& cfg, double* sd, int32_t* si,
 
 // rhs (mode 0) or W^-1 b (mode 1) of the lane-split model at a 23-state point; frz = freeze mask bits
 // in the order of Model3ph (per phase xR,xI,uR,uI; then xDC, xQ)
+static bool free_path = true;   // frz == 0: exercise the FREE (constant-bank gains) instantiation or the general one
+
 static void split_one(const pvder_env_config& cfg, const double* yin, const double* inp4, unsigned frz, double ghinv,
                       int mode, double* out) {
   const Lanes3 ln;
@@ -233,12 +235,18 @@ static void split_one(const pvder_env_config& cfg, const double* yin, const doub
   g.any = frz != 0;
   const Split3::Pt q = Split3::point(ln, cfg.par, kc, in, ax, y);
   if (mode == 0) {
-    Split3::rhs(cfg.par, kc, ax, g, y, q, b);
+    if (frz == 0 && free_path) Split3::rhs<true>(cfg.par, kc, ax, g, y, q, b);
+    else Split3::rhs<false>(cfg.par, kc, ax, g, y, q, b);
   } else {
     load_split(out, 1, 0, b);
     Split3::Fac fac;
-    Split3::factor(ln, cfg.par, kc, in, ax, g, y, q, ghinv, luc, fac);
-    Split3::solve(ln, cfg.par, kc, g, fac, y, luc[0], b);
+    if (frz == 0 && free_path) {
+      Split3::factor<true>(ln, cfg.par, kc, in, ax, g, y, q, ghinv, luc, fac);
+      Split3::solve<true>(ln, cfg.par, kc, g, fac, y, luc, b);
+    } else {
+      Split3::factor<false>(ln, cfg.par, kc, in, ax, g, y, q, ghinv, luc, fac);
+      Split3::solve<false>(ln, cfg.par, kc, g, fac, y, luc, b);
+    }
   }
   store_split(out, 1, 0, b);
 }
@@ -305,6 +313,8 @@ void emul_wsolve(const pvder_env_config* cfg, const double* y, const double* inp
 unsigned emul_freeze_bits(const pvder_env_config* cfg, const double* y, const double* inp4) {
   return cfg->phases == 1 ? frz_one<Model1ph>(*cfg, y, inp4) : frz_one<Model3ph>(*cfg, y, inp4);
 }
+
+void emul_split_free_path(int on) { free_path = on != 0; }
 
 void emul_split_rhs(const pvder_env_config* cfg, const double* y, const double* inp4, unsigned frz, double* f) {
   split_one(*cfg, y, inp4, frz, 480.0, 0, f);

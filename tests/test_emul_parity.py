@@ -326,6 +326,11 @@ def test_split_model_rhs_and_block_solve(ratio):
         gh = 480.0
         b = rng.standard_normal(23)
         x_sp = E.split_wsolve(cfg, y, inp4, gh, b, frz)
+        if frz == 0:       # the constant-table (no clamp in the warp) instantiation against the general one
+            E.split_free_path(False)
+            np.testing.assert_allclose(E.split_wsolve(cfg, y, inp4, gh, b, 0), x_sp, rtol=0, atol=1e-13 * np.abs(x_sp).max())
+            np.testing.assert_array_equal(E.split_rhs(cfg, y, inp4, 0), f_sp)
+            E.split_free_path(True)
         x_lu = E.wsolve(cfg, y, inp4, gh, b, frz)
         x_np = np.linalg.solve(np.eye(23) * gh - m.jac(list(y), 0.0, inp), b)
         np.testing.assert_allclose(x_sp, x_lu, rtol=0, atol=1e-12 * np.abs(x_lu).max())
