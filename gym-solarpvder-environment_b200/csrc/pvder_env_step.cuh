@@ -18,6 +18,9 @@ namespace pvder {
 #ifndef PVDER_FOLD
 #define PVDER_FOLD 1   // fold K1..K4 into the stage-5/6 sums early: same FMAs, 2 fewer live vectors (B200: 3.11 -> 3.04 ms)
 #endif
+#ifndef PVDER_FREE_PATH
+#define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the Rodas4 core, chosen per warp (experiment)
+#endif
 constexpr double RG = 0.25;
 struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant bank
   double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54;
@@ -134,11 +137,13 @@ PVDER_DEV void make_gains(const Params& par, unsigned frz, double (&gn)[M::NFRZ]
 
 // One half-cycle Rodas4 step.  `base` is the Aux record at y on entry and at the new y on exit.
 // Returns false (y, base untouched) when EXACT == false and a stage left the incremental range.
-template <class M, bool EXACT>
+// FREE: no clamp is active (frz == 0 in every lane that takes this instantiation): the effective gains are
+// the parameters themselves, read from the constant bank instead of occupying registers.
+template <class M, bool EXACT, bool FREE = false>
 PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
                            unsigned frz, Aux& base) {
   double gn[M::NFRZ];
-  make_gains<M>(par, frz, gn);
+  make_gains<M>(par, FREE ? 0u : frz, gn);
   constexpr int NS = M::NS;
   bool oor = false;
   const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
@@ -255,7 +260,19 @@ PVDER_DEV bool rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& 
   // One instantiation serves clamped and unclamped envs (the clamp enters through the per-row
   // effective gains): with a random policy two thirds of the warps hold a clamped lane late in an
   // episode, so a separate divergent code path for them cost 2x there.
-  if (!rodas4_core<M, false>(y, par, in, tab, frz, base)) {
+#if PVDER_FREE_PATH
+  // warp-uniform choice between the clamp-free instantiation and the general one (never both in a warp)
+#ifdef __CUDACC__
+  const bool any_frz = __any_sync(__activemask(), frz != 0u) != 0;
+#else
+  const bool any_frz = frz != 0u;
+#endif
+  const bool ok = any_frz ? rodas4_core<M, false, false>(y, par, in, tab, frz, base)
+                          : rodas4_core<M, false, true>(y, par, in, tab, frz, base);
+#else
+  const bool ok = rodas4_core<M, false>(y, par, in, tab, frz, base);
+#endif
+  if (!ok) {
     rodas4_exact<M>(y, par, in, tab, frz, base);
     return false;
   }
