@@ -108,6 +108,6 @@ PVDER_HD double u53(uint32_t hi, uint32_t lo) {
   return (double)(a * 67108864ull + b) * (1.0 / 9007199254740992.0);
 }
 
-enum : uint32_t { STREAM_EVENTS = 0u, STREAM_ACTIONS = 1u };
+enum : uint32_t { STREAM_EVENTS = 0u, STREAM_ACTIONS = 1u, STREAM_POLICY = 2u };
 
 }  // namespace pvder

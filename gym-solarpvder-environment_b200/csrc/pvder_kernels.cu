@@ -351,6 +351,87 @@ __global__ void __launch_bounds__(BLOCK) actions_kernel(uint64_t seed, int64_t s
   action[e] = (int32_t)(((uint64_t)r[0] * PVDER_N_ACTIONS) >> 32);   // unbiased to 2^-32
 }
 
+
+// Policy in the loop (BASELINE config 5; the collect step of the reference's tf-agents DQN demo:
+// QNetwork(fc_layer_params=(100,)) + epsilon-greedy): obs[N][11] f32 -> Q = W2 relu(W1 obs + b1) + b2 ->
+// argmax / epsilon-greedy -> action[N] i32, one thread per env.  The weights (6.8 KB) sit in shared
+// memory, padded so that every read is a broadcast LDS.128; the obs rows of the block are staged through
+// shared memory for coalesced loads.  Exploration uses the counter-based Philox stream 2 keyed by
+// (global env, step), so a rollout is reproducible and shard-invariant.
+constexpr int QNET_MAX_HIDDEN = 256;
+constexpr int QNET_IN_PAD = 12;    // 11 inputs padded to three float4
+constexpr int QNET_OUT_PAD = 8;    // 5 outputs padded to two float4
+
+__global__ void __launch_bounds__(BLOCK) qnet_policy_kernel(const float* __restrict__ obs, const float* __restrict__ w1,
+                                                            const float* __restrict__ b1, const float* __restrict__ w2,
+                                                            const float* __restrict__ b2, int hidden, float epsilon,
+                                                            uint64_t seed, int64_t step_index,
+                                                            const int64_t* __restrict__ step_index_dev,
+                                                            int32_t* __restrict__ action, float* __restrict__ q_out,
+                                                            int64_t n, int64_t env_offset) {
+  if (step_index_dev) step_index += *step_index_dev;   // device-side counter: a captured CUDA graph draws fresh numbers per replay
+  extern __shared__ float4 smem4[];
+  float* sw1 = reinterpret_cast<float*>(smem4);                   // [hidden][12]
+  float* sw2 = sw1 + hidden * QNET_IN_PAD;                        // [hidden][8]  (transposed: per hidden unit its 5 output weights)
+  float* sb1 = sw2 + hidden * QNET_OUT_PAD;                       // [hidden]
+  float* so = sb1 + ((hidden + 3) & ~3);                          // [BLOCK][11] obs staging
+  const int t = threadIdx.x;
+  for (int idx = t; idx < hidden * QNET_IN_PAD; idx += BLOCK) {
+    const int h = idx / QNET_IN_PAD, j = idx - h * QNET_IN_PAD;
+    sw1[idx] = j < PVDER_OBS_DIM ? w1[h * PVDER_OBS_DIM + j] : 0.f;
+  }
+  for (int idx = t; idx < hidden * QNET_OUT_PAD; idx += BLOCK) {
+    const int h = idx / QNET_OUT_PAD, k = idx - h * QNET_OUT_PAD;
+    sw2[idx] = k < PVDER_N_ACTIONS ? w2[k * hidden + h] : 0.f;
+  }
+  for (int idx = t; idx < hidden; idx += BLOCK) sb1[idx] = b1[idx];
+  const int64_t block_first = (int64_t)blockIdx.x * BLOCK;
+  const int64_t rows = min((int64_t)BLOCK, n - block_first);
+  const int total = (int)rows * PVDER_OBS_DIM;
+  for (int idx = t; idx < total; idx += BLOCK) so[idx] = obs[block_first * PVDER_OBS_DIM + idx];
+  __syncthreads();
+  const int64_t e = block_first + t;
+  if (e >= n) return;
+  float o[QNET_IN_PAD];
+#pragma unroll
+  for (int j = 0; j < PVDER_OBS_DIM; ++j) o[j] = so[t * PVDER_OBS_DIM + j];
+  o[11] = 0.f;
+  float q[PVDER_N_ACTIONS];
+#pragma unroll
+  for (int k = 0; k < PVDER_N_ACTIONS; ++k) q[k] = b2[k];
+  const float4* w1v = reinterpret_cast<const float4*>(sw1);
+  const float4* w2v = reinterpret_cast<const float4*>(sw2);
+#pragma unroll 4
+  for (int h = 0; h < hidden; ++h) {
+    const float4 a0 = w1v[3 * h], a1 = w1v[3 * h + 1], a2 = w1v[3 * h + 2];
+    float a = sb1[h];
+    a = fmaf(a0.x, o[0], a); a = fmaf(a0.y, o[1], a); a = fmaf(a0.z, o[2], a); a = fmaf(a0.w, o[3], a);
+    a = fmaf(a1.x, o[4], a); a = fmaf(a1.y, o[5], a); a = fmaf(a1.z, o[6], a); a = fmaf(a1.w, o[7], a);
+    a = fmaf(a2.x, o[8], a); a = fmaf(a2.y, o[9], a); a = fmaf(a2.z, o[10], a);
+    a = fmaxf(a, 0.f);
+    const float4 c0 = w2v[2 * h], c1 = w2v[2 * h + 1];
+    q[0] = fmaf(c0.x, a, q[0]); q[1] = fmaf(c0.y, a, q[1]); q[2] = fmaf(c0.z, a, q[2]); q[3] = fmaf(c0.w, a, q[3]);
+    q[4] = fmaf(c1.x, a, q[4]);
+  }
+  int best = 0;
+  float qb = q[0];
+#pragma unroll
+  for (int k = 1; k < PVDER_N_ACTIONS; ++k)
+    if (q[k] > qb) { qb = q[k]; best = k; }          // first maximum, like argmax
+  if (epsilon > 0.f) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)(env_offset + e), (uint32_t)step_index, (uint32_t)(step_index >> 32), STREAM_POLICY,
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const float u = (float)(r[0] >> 8) * (1.0f / 16777216.0f);      // 24-bit uniform in [0, 1)
+    if (u < epsilon) best = (int)(((uint64_t)r[1] * PVDER_N_ACTIONS) >> 32);
+  }
+  action[e] = best;
+  if (q_out) {
+#pragma unroll
+    for (int k = 0; k < PVDER_N_ACTIONS; ++k) q_out[e * PVDER_N_ACTIONS + k] = q[k];
+  }
+}
+
 __global__ void stats_kernel(const double* sd, const int32_t* si, int64_t ld, int ns, int64_t n, double* out) {
   double acc[12];
 #pragma unroll
@@ -580,6 +661,20 @@ int pvder_sample_actions(uint64_t seed, int64_t step_index, int32_t* action, int
   if (n_envs == 0) return PVDER_OK;
   const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
   actions_kernel<<<grid, BLOCK, 0, (cudaStream_t)stream>>>(seed, step_index, action, n_envs, env_offset);
+  CK(cudaGetLastError());
+  return PVDER_OK;
+}
+
+int pvder_qnet_policy(const float* obs_f32, const float* w1, const float* b1, const float* w2, const float* b2, int hidden,
+                      float epsilon, uint64_t seed, int64_t step_index, const int64_t* step_index_dev, int32_t* action,
+                      float* q_out, int64_t n_envs, int64_t env_offset, void* stream) {
+  if (!obs_f32 || !w1 || !b1 || !w2 || !b2 || !action || n_envs < 0 || hidden < 1 || hidden > QNET_MAX_HIDDEN)
+    return PVDER_ERR_INVALID;
+  if (n_envs == 0) return PVDER_OK;
+  const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
+  const size_t smem = sizeof(float) * ((size_t)hidden * (QNET_IN_PAD + QNET_OUT_PAD) + ((hidden + 3) & ~3) + BLOCK * PVDER_OBS_DIM);
+  qnet_policy_kernel<<<grid, BLOCK, smem, (cudaStream_t)stream>>>(obs_f32, w1, b1, w2, b2, hidden, epsilon, seed, step_index,
+                                                                  step_index_dev, action, q_out, n_envs, env_offset);
   CK(cudaGetLastError());
   return PVDER_OK;
 }

@@ -5,8 +5,12 @@ step per iteration, replay buffer) with every piece on the same GPU and stream:
     obs[N,11] f32 --Q-net (11-100-5)--> argmax / eps-greedy --> actions[N] i32 --step kernel--> obs'
 
 Nothing crosses PCIe or NVLink per step; the whole iteration (policy forward, action selection,
-env step, replay write) can be captured once in a CUDA graph and replayed.  The Q-network is a
-plain torch module (library GEMMs) -- it is the consumer of the hot path, not part of it.
+env step, replay write) can be captured once in a CUDA graph and replayed.
+
+policy="fused" (default for the demo's 11-h-5 ReLU network in fp32): one hand-written kernel
+(``pvder_qnet_policy``: weights in shared memory, one thread per env, Philox epsilon-greedy) turns
+obs into actions; policy="torch": the same network through torch ops (library GEMMs), kept as the
+cross-check and for arbitrary modules.
 """
 from __future__ import annotations
 
@@ -24,7 +28,7 @@ def make_qnet(hidden=100, device="cuda", dtype=None):
 class DQNRollout:
     """Collect driver over a PVDERVecEnv (env should be created with auto_reset=True)."""
 
-    def __init__(self, venv, qnet=None, epsilon=0.1, replay_steps=8, use_cuda_graph=True, seed=0):
+    def __init__(self, venv, qnet=None, epsilon=0.1, replay_steps=8, use_cuda_graph=True, seed=0, policy="auto"):
         import torch
 
         self.torch = torch
@@ -45,9 +49,42 @@ class DQNRollout:
         self.use_graph = bool(use_cuda_graph)
         self.graph = None
         self.steps_done = 0
+        self.seed = int(seed)
+        fusable = self._fusable(self.qnet)
+        if policy == "auto":
+            policy = "fused" if fusable else "torch"
+        if policy not in ("fused", "torch"):
+            raise ValueError("policy must be 'auto', 'fused' or 'torch'")
+        if policy == "fused" and not fusable:
+            raise ValueError("policy='fused' needs Sequential(Linear(11, h), ReLU, Linear(h, 5)) in float32 with h <= 256")
+        self.policy = policy
+
+    def _fusable(self, net):
+        t = self.torch
+        try:
+            l1, act, l2 = net[0], net[1], net[2]
+            return (len(net) == 3 and isinstance(l1, t.nn.Linear) and isinstance(act, t.nn.ReLU)
+                    and isinstance(l2, t.nn.Linear) and l1.in_features == 11 and l2.out_features == 5
+                    and l1.out_features == l2.in_features <= 256 and l1.weight.dtype == t.float32
+                    and l1.bias is not None and l2.bias is not None)
+        except Exception:
+            return False
+
+    def _select_actions_fused(self, obs):
+        import ctypes as C
+        from . import _cabi
+
+        l1, l2 = self.qnet[0], self.qnet[2]
+        p = lambda x: C.c_void_p(x.data_ptr())
+        _cabi.check(_cabi.load().pvder_qnet_policy(
+            p(obs), p(l1.weight), p(l1.bias), p(l2.weight), p(l2.bias), l1.out_features, self.epsilon,
+            self.seed & 0xFFFFFFFFFFFFFFFF, 0, p(self.slot), p(self.actions), None, self.venv.num_envs,
+            self.venv.env_offset, C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)))
 
     def _select_actions(self, obs):
         t = self.torch
+        if self.policy == "fused":
+            return self._select_actions_fused(obs)
         with t.no_grad():
             q = self.qnet(obs.to(next(self.qnet.parameters()).dtype))
             greedy = q.argmax(dim=1).to(t.int32)
@@ -106,5 +143,5 @@ class DQNRollout:
         self.steps_done += n_steps
         n = self.venv.num_envs
         return {"env_steps_per_s": n * n_steps / (ms * 1e-3), "ms_per_iteration": ms / n_steps,
-                "wall_s": wall, "n_envs": n, "steps": n_steps, "cuda_graph": self.graph is not None,
+                "wall_s": wall, "n_envs": n, "steps": n_steps, "cuda_graph": self.graph is not None, "policy": self.policy,
                 "obs_bytes_per_step": n * 44, "action_bytes_per_step": n * 4}

@@ -148,6 +148,17 @@ int pvder_generate_events(const pvder_env_config* cfg, const int32_t* episode, d
 int pvder_sample_actions(uint64_t seed, int64_t step_index, int32_t* action, int64_t n_envs,
                          int64_t env_offset, void* stream);
 
+/* Policy in the loop (the collect step of examples/gym_PVDER_environment_tf_agents_DQN_demo.ipynb:
+ * QNetwork(fc_layer_params=(hidden,)) + epsilon-greedy collect policy): obs_f32[n][11] ->
+ * Q = W2 relu(W1 obs + b1) + b2 -> argmax, or with probability epsilon a uniform action (Philox stream 2
+ * keyed by global env index and step) -> action[n].  step = step_index + *step_index_dev (device counter,
+ * nullable: lets a captured CUDA graph draw fresh numbers on every replay).  w1[hidden][11], b1[hidden],
+ * w2[5][hidden], b2[5]: device float32, row-major (torch Linear layout); hidden <= 256.  q_out (nullable):
+ * Q values [n][5]. */
+int pvder_qnet_policy(const float* obs_f32, const float* w1, const float* b1, const float* w2, const float* b2,
+                      int hidden, float epsilon, uint64_t seed, int64_t step_index, const int64_t* step_index_dev,
+                      int32_t* action, float* q_out, int64_t n_envs, int64_t env_offset, void* stream);
+
 /* Episode statistics (env_utilities.py:12-46) reduced over envs into 16 device doubles:
  * [0] sum return, [1] sum steps, [2] n done, [3] n failed, [4..8] action histogram,
  * [9] windup sub-steps, [10] n_envs, [11] sub-steps redone with library transcendentals. */

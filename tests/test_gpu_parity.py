@@ -329,7 +329,7 @@ def test_dqn_rollout_loop_config5(cuda):
     for graph in (False, True):
         venv = G.PVDERVecEnv(2048, device=cuda, model_type="model_2", auto_reset=True, seed=3)
         venv.reset()
-        ro = DQNRollout(venv, qnet=qnet, epsilon=0.0, replay_steps=4, use_cuda_graph=graph)
+        ro = DQNRollout(venv, qnet=qnet, epsilon=0.0, replay_steps=4, use_cuda_graph=graph, policy="torch")
         stats = ro.collect(5, warmup=2)
         assert stats["cuda_graph"] == graph and stats["env_steps_per_s"] > 0
         res.append((venv.sd.clone(), ro.rb_act.clone(), ro.rb_rew.clone(), ro.rb_next.clone()))
@@ -528,3 +528,64 @@ def test_full_size_three_phase_modes_agree_1M(cuda):
     assert float((err / scale).max()) < 1e-8
     assert mism <= 2            # a reward class can flip only for an env sitting on a threshold to 1e-9
     assert bool(torch.isfinite(b.sd).all()) and int(b.status.sum()) == 0
+
+
+def test_fused_qnet_policy_kernel(cuda):
+    """pvder_qnet_policy (obs -> Q-net 11-100-5 -> argmax / epsilon-greedy in one kernel) against the torch
+    module: same Q values to fp32 rounding, same greedy actions except at near-ties; exploration draws are
+    the Philox stream-2 twin bit for bit; CUDA-graph replay equals the eager loop."""
+    import ctypes as C
+    import torch
+    import gym_pvder_b200 as G
+    from gym_pvder_b200 import _cabi
+    from gym_pvder_b200.rollout import DQNRollout, make_qnet
+
+    torch.manual_seed(1)
+    qnet = make_qnet(device=cuda)
+    n = 5000
+    venv = G.PVDERVecEnv(n, device=cuda, model_type="model_2", auto_reset=True, seed=3, env_offset=11)
+    venv.reset()
+    for _ in range(3):
+        venv.step(venv.sample_actions())
+    obs = venv.obs
+    act = torch.zeros(n, dtype=torch.int32, device=cuda)
+    q = torch.zeros((n, 5), dtype=torch.float32, device=cuda)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    l1, l2 = qnet[0], qnet[2]
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib = _cabi.load()
+    _cabi.check(lib.pvder_qnet_policy(p(obs), p(l1.weight), p(l1.bias), p(l2.weight), p(l2.bias), 100, 0.0, 7, 5, None,
+                                      p(act), p(q), n, 11, st))
+    with torch.no_grad():
+        q_ref = qnet(obs)
+    torch.cuda.synchronize()
+    assert float((q - q_ref).abs().max()) < 1e-5 * float(q_ref.abs().max()) + 1e-6
+    greedy_ref = q_ref.argmax(1).to(torch.int32)
+    diff = act != greedy_ref
+    top2 = q_ref.topk(2, dim=1).values
+    assert bool(((top2[:, 0] - top2[:, 1])[diff] < 1e-5).all())          # only near-ties may differ
+    assert torch.equal(act, q.argmax(1).to(torch.int32))                   # exactly the argmax of its own Q
+    # exploration: epsilon = 0.3, twin of the Philox draw
+    step_dev = torch.tensor([40], dtype=torch.int64, device=cuda)
+    _cabi.check(lib.pvder_qnet_policy(p(obs), p(l1.weight), p(l1.bias), p(l2.weight), p(l2.bias), 100, 0.3, 7, 2, p(step_dev),
+                                      p(act), None, n, 11, st))
+    torch.cuda.synchronize()
+    env = np.arange(11, 11 + n, dtype=np.uint64)
+    r = twin.philox4x32_10(env, np.uint64(42), np.uint64(0), np.uint64(2), 7, 0)
+    u = (r[0] >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    explore = u < np.float32(0.3)
+    rnd = ((r[1] * np.uint64(5)) >> np.uint64(32)).astype(np.int32)
+    expect = np.where(explore, rnd, q.argmax(1).cpu().numpy().astype(np.int32))
+    np.testing.assert_array_equal(act.cpu().numpy(), expect)
+    assert abs(explore.mean() - 0.3) < 0.03
+    # rollout driver: graph replay == eager, actions vary from step to step under exploration
+    res = []
+    for graph in (False, True):
+        v = G.PVDERVecEnv(2048, device=cuda, model_type="model_2", auto_reset=True, seed=3)
+        v.reset()
+        ro = DQNRollout(v, qnet=qnet, epsilon=0.2, replay_steps=8, use_cuda_graph=graph, seed=5)
+        assert ro.policy == "fused"
+        ro.collect(5, warmup=2)
+        res.append((v.sd.clone(), ro.rb_act.clone(), ro.rb_rew.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert not torch.equal(res[0][1][0], res[0][1][1])
