@@ -589,3 +589,35 @@ def test_fused_qnet_policy_kernel(cuda):
         res.append((v.sd.clone(), ro.rb_act.clone(), ro.rb_rew.clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
     assert not torch.equal(res[0][1][0], res[0][1][1])
+
+
+def test_config3_subset_vs_tight_oracle(cuda):
+    """BASELINE config 3: 65,536 envs, Philox sag + insolation events, DISCRETE_REWARD, random actions; a random
+    subset of envs is re-run by the oracle's tight LSODA with the twin's event tables and action stream (SURVEY 8d:
+    'trajectories vs O1 on a random subset')."""
+    n, seed, steps = 65536, 1234, 12
+    g = _venv(cuda, n, model_type="model_1", events_spec=H.SAG_SPEC, seed=seed, DISCRETE_REWARD=True)
+    g.reset()
+    c = g.cfg.c
+    vt, st = twin.event_tables_twin(seed, n, 0, 0, c.ev_count, True, True, c.ev_v_min, c.ev_v_max, c.ev_s_min, c.ev_s_max)
+    subset = np.random.default_rng(0).choice(n, size=20, replace=False)
+    orcs = {}
+    for i in subset:
+        o = OraclePVDEREnv(model_type="model_1", solver="tight", events=H.table_to_events(vt[:, i], st[:, i], c),
+                           DISCRETE_REWARD=True)
+        o.reset()
+        orcs[int(i)] = o
+    near = 0
+    for s in range(steps):                      # 3 s of simulated time: crosses the events at t = 1 s and 2 s
+        a = g.sample_actions()
+        a_np = twin.sample_actions_twin(seed, s, n, 0)
+        obs, rew, done, _ = g.step(a)
+        y = g.y.cpu().numpy()
+        o64 = g.obs64.cpu().numpy()
+        r_np = rew.cpu().numpy()
+        for i, o in orcs.items():
+            oo, orw, od, _ = o.step(int(a_np[i]))
+            H.assert_state_close(y[:, i], H.oracle_delta_state(o), 1, what=f"env{i} step{s}")
+            np.testing.assert_allclose(o64[i], oo, rtol=H.RTOL, atol=H.ATOL)
+            near += int(r_np[i] != orw)
+    assert near <= 1      # a discrete class can differ only for a state within 1e-5 of a threshold
