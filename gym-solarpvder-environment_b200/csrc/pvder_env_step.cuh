@@ -67,10 +67,13 @@ PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[
 
 // Aux record at (dl, V) close to the base point (angle dl0, DC voltage V0, record b):
 //   sin/cos(dl0 + d) by rotating (sn0, cs0) through d,  exp(kappa (V0 + dv)) = E0 * exp(kappa dv),
-//   1/V by three Newton steps from 1/V0 -- short polynomials (|d|, |kappa dv| < 2^-4: truncation
-//   below 3e-19) instead of 3 library calls per Rodas stage.  Outside that range (PLL pull-in right
-//   after reset) the step is redone by the EXACT instantiation, which is kept out of line so the
-//   hot loop stays small.
+//   1/V by two Newton steps from 1/V0 -- short Taylor polynomials instead of 3 library calls per Rodas
+//   stage.  Degrees are chosen against the integrator, not against the ulp: within the range
+//   |d|, |kappa dv| < 2^-4, |dv| < 2^-6 V0 the truncation is below 1e-10 relative (sin: d^7/5040, cos:
+//   d^6/720, exp: x^6/720, 1/V: (dv/V0)^4), three orders below the 1e-7 accuracy of a half-cycle Rodas4 step;
+//   and because every argument is O(h), the error terms are O(h^6) and beyond -- past the method's own
+//   order, so they do not change its convergence.  Outside the range (PLL pull-in right after reset) the
+//   step is redone by the EXACT instantiation, kept out of line so the hot loop stays small.
 template <bool EXACT>
 PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0, double dl,
                               double V, Aux& a, bool& out_of_range) {
@@ -82,31 +85,21 @@ PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b,
   const double dv = V - V0;
   const double x = par.kappa * dv;
   // outside the polynomial range the caller discards this step and redoes it with EXACT = true
-  out_of_range |= !(fabs(d) < 0.0625 && fabs(x) < 0.0625 && fabs(dv) < 0.0625 * V0);
+  out_of_range |= !(fabs(d) < 0.0625 && fabs(x) < 0.0625 && fabs(dv) < 0.015625 * V0);
   {
     const double d2 = d * d;
-    double ps = fma(d2, 1.0 / 362880.0, -1.0 / 5040.0);
-    ps = fma(ps, d2, 1.0 / 120.0);
-    ps = fma(ps, d2, -1.0 / 6.0);
-    const double sd = fma(ps * d2, d, d);                      // sin d
-    double pc = fma(d2, -1.0 / 3628800.0, 1.0 / 40320.0);
-    pc = fma(pc, d2, -1.0 / 720.0);
-    pc = fma(pc, d2, 1.0 / 24.0);
-    pc = fma(pc, d2, -0.5);
-    const double cdm1 = pc * d2;                               // cos d - 1
+    const double ps = fma(d2, 1.0 / 120.0, -1.0 / 6.0);
+    const double sd = fma(ps * d2, d, d);                      // sin d  = d - d^3/6 + d^5/120
+    const double pc = fma(d2, 1.0 / 24.0, -0.5);
+    const double cdm1 = pc * d2;                               // cos d - 1 = -d^2/2 + d^4/24
     a.sn = fma(b.sn, cdm1, fma(b.cs, sd, b.sn));
     a.cs = fma(b.cs, cdm1, fma(-b.sn, sd, b.cs));
-    double pe = fma(x, 1.0 / 362880.0, 1.0 / 40320.0);
-    pe = fma(pe, x, 1.0 / 5040.0);
-    pe = fma(pe, x, 1.0 / 720.0);
-    pe = fma(pe, x, 1.0 / 120.0);
-    pe = fma(pe, x, 1.0 / 24.0);
+    double pe = fma(x, 1.0 / 120.0, 1.0 / 24.0);
     pe = fma(pe, x, 1.0 / 6.0);
     pe = fma(pe, x, 0.5);
     pe = fma(pe, x, 1.0);
-    a.E = fma(b.E * pe, x, b.E);                               // E0 * exp(x)
+    a.E = fma(b.E * pe, x, b.E);                               // E0 * exp(x), exp to x^5/120
     double r = b.inv_Vdc;
-    r = fma(r, fma(-V, r, 1.0), r);
     r = fma(r, fma(-V, r, 1.0), r);
     r = fma(r, fma(-V, r, 1.0), r);
     a.inv_Vdc = r;

@@ -849,11 +849,11 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
                         uint8_t* done_out) {
   if (!h || !action) return PVDER_ERR_INVALID;
   // Large batches are cut into up to 8 chunks of WHOLE WAVES of resident CTAs (no partial-wave tail per
-  // launch) whose sizes shrink by ~1.5x: the D2H copy of chunk c (copy stream) and the H2D copy of the
+  // launch) whose sizes shrink by ~2x: the D2H copy of chunk c (copy stream) and the H2D copy of the
   // actions of chunk c+1 (h2d stream) run under the kernels of the neighbouring chunks, and only the
   // one-wave last chunk's results are copied after the last kernel.  D2H moves ~53 B/env -- about 3x
   // faster than the kernel produces them on an idle host, less when 8 ranks share the host memory
-  // system -- so a ratio of 1.5 keeps every copy hidden up to a 2x slower link.
+  // system -- so a ratio of 2 keeps every copy hidden up to a 1.5x slower link with few launches.
   int64_t start[9];
   int chunks = 0;
   start[0] = 0;
@@ -862,9 +862,9 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
     start[1] = h->n;
     chunks = 1;
   } else {
-    // sizes in waves, built from the end as a geometric series 1, q, q^2, ... (q = 1.5, or larger when 8
-    // chunks of ratio 1.5 cannot cover the batch); the first chunk takes what is left
-    double q = 1.5;
+    // sizes in waves, built from the end as a geometric series 1, q, q^2, ... (q = 2, or larger when 8
+    // chunks of ratio 2 cannot cover the batch); the first chunk takes what is left
+    double q = 2.0;
     for (;;) {
       double sum = 0.0, t = 1.0;
       for (int i = 0; i < 8; ++i) { sum += t; t *= q; }

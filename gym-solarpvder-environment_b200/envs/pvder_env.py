@@ -174,8 +174,11 @@ class PVDER(Utilities):
                                                      self._obs64.ctypes.data, self._rew.ctypes.data,
                                                      self._done_buf.ctypes.data))
         self.sim.tStop = self.sim.tStart + self._sim_time_per_env_step
-        si = self._state_i32()
-        status = int(si[_cabi.SI_STATUS])
+        # a failed integration is reported by the kernel as reward -100 + done (PVDER_env.py:170-172); only then
+        # is the status word fetched (one synchronous copy less per step)
+        status = _cabi.STATUS_OK
+        if self._done_buf[0] and self._rew[0] == -100.0:
+            status = int(self._state_i32()[_cabi.SI_STATUS])
         self.CONVERGENCE_FAILURE = status == _cabi.STATUS_NONFINITE
         assert not self.CONVERGENCE_FAILURE, "Convergence flag should be true to calculate reward!"   # :177
         self._reward = int(self._rew[0]) if self.DISCRETE_REWARD else float(self._rew[0])
