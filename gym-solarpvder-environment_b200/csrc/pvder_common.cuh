@@ -29,6 +29,21 @@ using std::isfinite;
 
 namespace pvder {
 
+// Reciprocal of a well-scaled pivot (normal, positive, far from the ends of the exponent range): hardware
+// seed (2^-23) + two Newton steps = full double accuracy without the IEEE division's special-case
+// branches, which split the straight-line Rodas4 code into scheduling regions.
+PVDER_DEV double pvder_rcp(double x) {
+#ifdef __CUDACC__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(r, fma(-x, r, 1.0), r);
+  r = fma(r, fma(-x, r, 1.0), r);
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+
 using Params = ::pvder_params;
 
 // Exogenous inputs held constant over one half-cycle sub-step (events frozen per sub-step, A.8).

@@ -576,12 +576,9 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
     int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
     int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
     Aux base;
-    {
-      const Inputs in0 = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
-      aux_exact<M>(par, in0, r.y, base);      // library sincos/exp/div once per env step, then incremental
-    }
+    Inputs in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);   // changes only when an event fires
+    aux_exact<M>(par, in, r.y, base);         // library sincos/exp/div once per env step, then incremental
     for (int s = 0; s < cfg.n_sub_per_step; ++s) {
-      const Inputs in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
       bool m_over;
       const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
       if (frz) r.windup += 1;
@@ -594,6 +591,7 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
+        in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
         j_next += 1;
         next_k += cfg.ev_step_k;
       }

@@ -80,6 +80,7 @@ PVDER_DEV Lanes3 make_lanes(int lane) {
 }
 PVDER_DEV double vfma(double a, double b, double c) { return fma(a, b, c); }
 PVDER_DEV double vsel(bool c, double a, double b) { return c ? a : b; }
+PVDER_DEV double vrcp(double a) { return pvder_rcp(a); }
 PVDER_DEV bool vgt(double a, double b) { return a > b; }
 PVDER_DEV bool vor(bool a, bool b) { return a || b; }
 PVDER_DEV bool vand(bool a, bool b) { return a && b; }
@@ -111,6 +112,7 @@ inline V3 vfma(const V3& a, const V3& b, const V3& c) {
   return V3(std::fma(a.v[0], b.v[0], c.v[0]), std::fma(a.v[1], b.v[1], c.v[1]), std::fma(a.v[2], b.v[2], c.v[2]));
 }
 inline double vfma(double a, double b, double c) { return std::fma(a, b, c); }
+inline V3 vrcp(const V3& a) { return V3(1.0 / a.v[0], 1.0 / a.v[1], 1.0 / a.v[2]); }
 inline V3 vsel(const B3& c, const V3& a, const V3& b) {
   return V3(c.v[0] ? a.v[0] : b.v[0], c.v[1] ? a.v[1] : b.v[1], c.v[2] ? a.v[2] : b.v[2]);
 }
@@ -322,7 +324,7 @@ struct Split3 {
     f.epI = f.e * tkI;
     const V AR = f.epR + a, AI = f.epI + a;
     const V det = vfma(AR, AI, V(c * c));
-    const V idet = V(1.0) / det;
+    const V idet = vrcp(det);
     f.n11 = AI * idet;
     f.n22 = AR * idet;
     f.n12 = c * idet;
@@ -374,7 +376,7 @@ struct Split3 {
     const double k10 = fma(m12, m20, -(m10 * m22)), k11 = fma(m00, m22, -(m02 * m20)), k12 = fma(m02, m10, -(m00 * m12));
     const double k20 = fma(m10, m21, -(m11 * m20)), k21 = fma(m01, m20, -(m00 * m21)), k22 = fma(m00, m11, -(m01 * m10));
     const double dt = fma(m00, k00, fma(m01, k10, m02 * k20));
-    const double idt = 1.0 / dt;
+    const double idt = pvder_rcp(dt);
     f.N[0] = k00 * idt; f.N[1] = k01 * idt; f.N[2] = k02 * idt;
     f.N[3] = k10 * idt; f.N[4] = k11 * idt; f.N[5] = k12 * idt;
     f.N[6] = k20 * idt; f.N[7] = k21 * idt; f.N[8] = k22 * idt;
@@ -686,13 +688,10 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
     int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
     int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
     Aux base;
-    {
-      const Inputs in0 = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
-      aux_exact_sv(par, in0, r.y.s[4], r.y.s[0], base);
-    }
+    Inputs in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);   // changes only when an event fires
+    S::In in = S::inputs(ln, kc, in_s);
+    aux_exact_sv(par, in_s, r.y.s[4], r.y.s[0], base);
     for (int s = 0; s < cfg.n_sub_per_step; ++s) {
-      const Inputs in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
-      const S::In in = S::inputs(ln, kc, in_s);
       bool m_over;
       const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
       if (g.any) r.windup += 1;
@@ -713,6 +712,8 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
+        in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
+        in = S::inputs(ln, kc, in_s);
         j_next += 1;
         next_k += cfg.ev_step_k;
       }

@@ -455,7 +455,7 @@ def generate(P, mult=1):
             if k in const_piv:
                 A(f"    const double d_{k} = luc[{const_piv[k] + 1}];")
             else:
-                A(f"    const double d_{k} = 1.0 / w_{k}_{k};")
+                A(f"    const double d_{k} = pvder_rcp(w_{k}_{k});")
         elif op[0] == "mul":
             _, r, k = op
             A(f"    {wname(r, k)} *= d_{k};")
