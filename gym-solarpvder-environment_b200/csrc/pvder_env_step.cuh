@@ -18,6 +18,9 @@ namespace pvder {
 #ifndef PVDER_FOLD
 #define PVDER_FOLD 1   // fold K1..K4 into the stage-5/6 sums early: same FMAs, 2 fewer live vectors (B200: 3.11 -> 3.04 ms)
 #endif
+#ifndef PVDER_EXACT_BY_COPY
+#define PVDER_EXACT_BY_COPY 0   // 1: slow-path call on copies (experiment: keeps y/base out of local memory)
+#endif
 #ifndef PVDER_FREE_PATH
 #define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the Rodas4 core, chosen per warp (experiment)
 #endif
@@ -266,7 +269,19 @@ PVDER_DEV bool rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& 
   const bool ok = rodas4_core<M, false>(y, par, in, tab, frz, base);
 #endif
   if (!ok) {
+#if PVDER_EXACT_BY_COPY
+    // the out-of-line call works on copies, so y and base never have their address taken in the hot loop
+    double yc[M::NS];
+    Aux bc = base;
+#pragma unroll
+    for (int i = 0; i < M::NS; ++i) yc[i] = y[i];
+    rodas4_exact<M>(yc, par, in, tab, frz, bc);
+#pragma unroll
+    for (int i = 0; i < M::NS; ++i) y[i] = yc[i];
+    base = bc;
+#else
     rodas4_exact<M>(y, par, in, tab, frz, base);
+#endif
     return false;
   }
   return true;
