@@ -151,6 +151,33 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU hangs
+    off, so that N ranks do not push their device->host copies through one socket.  Returns a short description."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return f"{dev}: no NUMA information"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"{dev}: node {node} has no allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"{dev}: node {node}, {len(cpus)} cpus"
+    except Exception as exc:      # sysfs layout, permissions, old torch ...
+        return f"unavailable ({type(exc).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,6 +233,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    config["host_affinity"] = bind_to_gpu_numa_node(local_rank) if world > 1 else "not set (single rank)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.load()
