@@ -172,6 +172,32 @@ class PVDERVecEnv:
                                                     _ptr(self._stats), self._stream()))
         return self._stats
 
+    # ---- checkpoint / resume ----------------------------------------------------------------
+    def state_dict(self):
+        """Everything needed to resume bit-identically: the two SoA state tensors (ODE states, references, event
+        values, counters, RNG episode keys), the action-stream position and the last outputs."""
+        d = {"sd": self.sd.clone(), "si": self.si.clone(), "step_index": int(self._step_index),
+             "obs": self.obs.clone(), "done": self.done.clone(), "num_envs": self.num_envs, "env_offset": self.env_offset,
+             "model_type": self.cfg.model_type, "seed": int(self.cfg.seed)}
+        if self.vgrid_tab is not None:
+            d["vgrid_tab"], d["sinsol_tab"] = self.vgrid_tab.clone(), self.sinsol_tab.clone()
+        return d
+
+    def load_state_dict(self, d):
+        if (d["num_envs"], d["env_offset"], d["model_type"]) != (self.num_envs, self.env_offset, self.cfg.model_type):
+            raise ValueError("checkpoint was taken from a different shard / model")
+        if int(d["seed"]) != int(self.cfg.seed):
+            raise ValueError("checkpoint was taken with another seed (event and action streams would differ)")
+        self.sd.copy_(d["sd"])
+        self.si.copy_(d["si"])
+        self.obs.copy_(d["obs"])
+        self.done.copy_(d["done"])
+        if self.vgrid_tab is not None and "vgrid_tab" in d:
+            self.vgrid_tab.copy_(d["vgrid_tab"])
+            self.sinsol_tab.copy_(d["sinsol_tab"])
+        self._step_index = int(d["step_index"])
+        self._initialised = True
+
     # ---- state views ------------------------------------------------------------------------
     @property
     def y(self):

@@ -621,3 +621,29 @@ def test_config3_subset_vs_tight_oracle(cuda):
             np.testing.assert_allclose(o64[i], oo, rtol=H.RTOL, atol=H.ATOL)
             near += int(r_np[i] != orw)
     assert near <= 1      # a discrete class can differ only for a state within 1e-5 of a threshold
+
+
+def test_checkpoint_resume_state_dict(cuda):
+    """state_dict()/load_state_dict(): a fresh env object resumed from a checkpoint continues bit-identically
+    (states, counters, event and action streams), also across an auto-reset."""
+    import torch
+
+    kw = dict(model_type="model_2", events_spec=H.SAG_SPEC, seed=31, DISCRETE_REWARD=True, auto_reset=True,
+              max_sim_time=2.0)
+    a = _venv(cuda, 777, **kw)
+    a.reset()
+    for _ in range(5):
+        a.step(a.sample_actions())
+    ck = a.state_dict()
+    outs_a = []
+    for _ in range(6):                 # crosses the auto-reset at step 8
+        o, r, d, _ = a.step(a.sample_actions())
+        outs_a.append((o.clone(), r.clone(), d.clone()))
+    b = _venv(cuda, 777, **kw)
+    b.load_state_dict(ck)
+    for i in range(6):
+        o, r, d, _ = b.step(b.sample_actions())
+        assert torch.equal(o, outs_a[i][0]) and torch.equal(r, outs_a[i][1]) and torch.equal(d, outs_a[i][2])
+    assert torch.equal(a.sd, b.sd) and torch.equal(a.si, b.si)
+    with pytest.raises(ValueError):
+        _venv(cuda, 776, **kw).load_state_dict(ck)
