@@ -708,7 +708,7 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
           r.exact += 1;
         }
       }
-      if (traj) record_substep_split(ln, traj, traj_ld, s, r.y, r.Vgrid, r.Sinsol);
+      if (traj && run) record_substep_split(ln, traj, traj_ld, s, r.y, r.Vgrid, r.Sinsol);   // not the keep-converged dummy work
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);

@@ -647,3 +647,33 @@ def test_checkpoint_resume_state_dict(cuda):
     assert torch.equal(a.sd, b.sd) and torch.equal(a.si, b.si)
     with pytest.raises(ValueError):
         _venv(cuda, 776, **kw).load_state_dict(ck)
+
+
+@pytest.mark.parametrize("mode", ["auto", "split"])
+def test_step_after_done_is_a_no_op_inside_a_running_warp(cuda, mode):
+    """PVDER_env.py:145-152: stepping a finished env returns the cached tuple and changes nothing -- also when its
+    warp neighbours keep running (the three-lane kernel keeps such an env's lanes busy to stay converged and must
+    restore it), and nothing is recorded for it."""
+    import torch
+    from gym_pvder_b200 import _cabi
+
+    n = 64
+    g = _venv(cuda, n, model_type="model_2", events_spec=H.SAG_SPEC, seed=2, DISCRETE_REWARD=True,
+              balanced_three_phase=mode, max_sim_time=1.0)           # 4 steps per episode, no auto-reset
+    g.reset()
+    for _ in range(2):
+        g.step(g.sample_actions())
+    # finish every third env early by hand: mark it done
+    g.si[_cabi.SI_DONE, 0:n:3] = 1
+    before_sd, before_si = g.sd.clone(), g.si.clone()
+    o0, r0, d0, _ = g.step(g.sample_actions())
+    o0, r0 = o0.clone(), r0.clone()
+    traj = g.record_trajectory(n, 1)
+    o1, r1, d1, _ = g.step(g.sample_actions())
+    frozen = torch.arange(0, n, 3, device=cuda)
+    assert torch.equal(g.sd[:, frozen], before_sd[:, frozen]) and torch.equal(g.si[:, frozen], before_si[:, frozen])
+    assert torch.equal(o1[frozen], o0[frozen]) and torch.equal(r1[frozen], r0[frozen]) and bool(d1[frozen].all())
+    assert float(traj[:, :, frozen].abs().max()) == 0.0            # nothing recorded for a finished env
+    running = torch.tensor([i for i in range(n) if i % 3], device=cuda)
+    assert bool((g.steps[running] == 4).all()) and bool(d1[running].all())
+    assert float(traj[-1, :g.ns, running].sub(g.sd[:g.ns, running]).abs().max()) == 0.0
