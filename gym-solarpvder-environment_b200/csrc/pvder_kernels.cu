@@ -735,7 +735,9 @@ struct pvder_env {
   uint8_t* d_done;
   double* d_vtab;
   double* d_stab;
-  cudaStream_t stream;        // compute + H2D
+  cudaStream_t stream;        // compute (even chunks)
+  cudaStream_t stream2;       // compute (odd chunks): the chunks touch disjoint envs, so the head of chunk c+1 may fill
+                              // the SMs that the draining tail of chunk c leaves idle
   cudaStream_t copy_stream;   // D2H of finished chunks, overlapped with the next chunk's kernel
   cudaStream_t h2d_stream;    // H2D of the actions of later chunks, overlapped with the first chunk's kernel
   cudaEvent_t act_ready[8];
@@ -762,6 +764,7 @@ int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_of
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
   for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->act_ready[c], cudaEventDisableTiming));
   {
@@ -815,6 +818,7 @@ int pvder_env_destroy(pvder_env* h) {
   for (int c = 0; c < 8; ++c) cudaEventDestroy(h->chunk_done[c]);
   for (int c = 0; c < 8; ++c) cudaEventDestroy(h->act_ready[c]);
   cudaStreamDestroy(h->h2d_stream);
+  cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -902,14 +906,15 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
   CK(cudaEventRecord(h->e0, h->stream));
   for (int c = 0; c < chunks; ++c) {
     const int64_t lo = start[c], cnt = start[c + 1] - lo;
-    CK(cudaStreamWaitEvent(h->stream, h->act_ready[c], 0));
+    cudaStream_t cs = (c & 1) ? h->stream2 : h->stream;
+    if (c == 1) CK(cudaStreamWaitEvent(h->stream2, h->e0, 0));      // keep launch order: chunk 1 after the start mark
+    CK(cudaStreamWaitEvent(cs, h->act_ready[c], 0));
     int rc = pvder_step(&h->cfg, h->sd + lo, h->si + lo, h->ld, h->d_action + lo, h->d_vtab ? h->d_vtab + lo : nullptr,
                         h->d_stab ? h->d_stab + lo : nullptr, obs_out ? h->d_obs + lo * PVDER_OBS_DIM : nullptr,
                         obs64_out ? h->d_obs64 + lo * PVDER_OBS_DIM : nullptr, h->d_reward + lo, nullptr, h->d_done + lo,
-                        cnt, h->off + lo, h->stream);
+                        cnt, h->off + lo, cs);
     if (rc) return rc;
-    if (c == chunks - 1) CK(cudaEventRecord(h->e1, h->stream));
-    CK(cudaEventRecord(h->chunk_done[c], h->stream));
+    CK(cudaEventRecord(h->chunk_done[c], cs));
     CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
     if (obs_out)
       CK(cudaMemcpyAsync(obs_out + lo * PVDER_OBS_DIM, h->d_obs + lo * PVDER_OBS_DIM, sizeof(float) * PVDER_OBS_DIM * cnt,
@@ -921,7 +926,11 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
       CK(cudaMemcpyAsync(reward_out + lo, h->d_reward + lo, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
     if (done_out) CK(cudaMemcpyAsync(done_out + lo, h->d_done + lo, cnt, cudaMemcpyDeviceToHost, h->copy_stream));
   }
+  // end mark of the kernel span: after the last chunk of either compute stream
+  if (chunks > 1) CK(cudaStreamWaitEvent(h->stream, h->chunk_done[((chunks - 1) & 1) ? chunks - 1 : chunks - 2], 0));
+  CK(cudaEventRecord(h->e1, h->stream));
   CK(cudaStreamSynchronize(h->copy_stream));
+  CK(cudaStreamSynchronize(h->stream2));
   CK(cudaStreamSynchronize(h->stream));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->e0, h->e1));
