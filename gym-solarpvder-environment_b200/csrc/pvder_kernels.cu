@@ -852,51 +852,42 @@ int pvder_env_reset_host(pvder_env* h, float* obs_out, double* obs64_out) {
 int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
                         uint8_t* done_out) {
   if (!h || !action) return PVDER_ERR_INVALID;
-  // Large batches are cut into up to 8 chunks of WHOLE WAVES of resident CTAs (no partial-wave tail per
-  // launch) whose sizes shrink by ~2x: the D2H copy of chunk c (copy stream) and the H2D copy of the
-  // actions of chunk c+1 (h2d stream) run under the kernels of the neighbouring chunks, and only the
-  // one-wave last chunk's results are copied after the last kernel.  D2H moves ~53 B/env -- about 3x
-  // faster than the kernel produces them on an idle host, less when 8 ranks share the host memory
-  // system -- so a ratio of 2 keeps every copy hidden up to a 1.5x slower link with few launches.
+  // Large batches are cut into up to 8 chunks (units of a quarter wave of resident CTAs) that run alternately
+  // on two compute streams -- they touch disjoint envs, so the head of chunk c+1 fills the SMs the draining
+  // tail of chunk c leaves idle -- while the action H2D copies (h2d stream) run ahead of the kernels and the
+  // D2H copy of chunk c (copy stream) runs under the later kernels.  Schedule: a one-wave first chunk (its
+  // actions arrive after ~150 KB of H2D, so the GPU starts at once), the bulk, then chunks halving down to
+  // one wave and a final quarter wave, so that only ~0.5 MB of results is copied after the last kernel and
+  // every other copy hides under at least as much compute as produced it (D2H moves 53 B/env, ~3x faster
+  // than the kernel produces them on an idle host).
   int64_t start[9];
   int chunks = 0;
   start[0] = 0;
-  const int64_t waves = h->n / h->wave_envs;      // whole waves available
-  if (h->n < (1 << 16) || waves < 4) {
+  const int64_t unit = h->wave_envs / 4;
+  const int64_t units = h->n / unit;
+  if (h->n < (1 << 16) || units < 24) {
     start[1] = h->n;
     chunks = 1;
   } else {
-    // sizes in waves, built from the end as a geometric series 1, q, q^2, ... (q = 2, or larger when 8
-    // chunks of ratio 2 cannot cover the batch); the first chunk takes what is left
-    double q = 2.0;
-    for (;;) {
-      double sum = 0.0, t = 1.0;
-      for (int i = 0; i < 8; ++i) { sum += t; t *= q; }
-      if (sum >= (double)waves) break;
-      q += 0.1;
-    }
-    int64_t sizes[8];
+    int64_t tail[6];                               // sizes from the end: 1, 4, 8, 16, ... units
     int k = 0;
-    int64_t rest = waves;
-    double t = 1.0;
-    while (k < 7) {
-      const int64_t w = (int64_t)(t + 0.5);
-      if (2 * w >= rest) break;      // what is left becomes the first chunk (no more than ~2x the next one)
-      sizes[k++] = w;
+    int64_t rest = units - 4 - 1;                  // minus the first chunk (4 units) and the last (1 unit)
+    tail[k++] = 1;
+    int64_t w0 = (units - 5 + 62) / 63;            // six doubling chunks must be able to cover a very large batch
+    if (w0 < 4) w0 = 4;
+    for (int64_t w = w0; k < 6 && rest - w >= w; w *= 2) {
+      tail[k++] = w;
       rest -= w;
-      t *= q;
     }
-    if (k > 0 && k < 7 && rest > 2 * sizes[k - 1]) {   // halve an oversized first chunk
-      sizes[k] = rest / 2;
-      rest -= sizes[k++];
-    }
-    sizes[k++] = rest;                            // first chunk
-    int64_t pos = 0;
-    for (int c = k - 1; c >= 0; --c) {            // largest first, one-wave chunk last
-      pos += sizes[c] * h->wave_envs;
+    int64_t pos = 4 * unit;
+    start[++chunks] = pos;                         // first chunk: one wave
+    pos += rest * unit;
+    start[++chunks] = pos;                         // the bulk
+    for (int c = k - 1; c >= 1; --c) {
+      pos += tail[c] * unit;
       start[++chunks] = pos;
     }
-    start[chunks] = h->n;                         // the remainder (< 1 wave) rides with the last chunk
+    start[++chunks] = h->n;                        // last quarter wave + the remainder (< 1 unit)
   }
   for (int c = 0; c < chunks; ++c) {
     const int64_t lo = start[c], cnt = start[c + 1] - lo;
