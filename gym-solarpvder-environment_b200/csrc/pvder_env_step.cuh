@@ -30,6 +30,10 @@ struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant 
   double c21, c31, c32, c41, c42, c43, c51, c52, c53, c54, c61, c62, c63, c64, c65;
   double ghinv;     // 1/(h*gamma)
   double luc[16];   // launch-constant reciprocal pivots of the symbolic LU (M::lu_consts)
+  // Unit-pivot rows (M::unit_row: the pure integrators x, xDC, xQ, xPLL): their equation is scaled by h*gamma,
+  // i.e. their gains and their sums of c_ij/h K_j are -- then the pivot is exactly 1 and costs no multiply.
+  double cs21, cs31, cs32, cs41, cs42, cs43, cs51, cs52, cs53, cs54, cs61, cs62, cs63, cs64, cs65;   // c_ij * gamma
+  double kx, kdc, kq, kpll;   // Ki_GCC, Ki_DC, Ki_Q, Ki_PLL times h*gamma
 };
 
 template <class M>
@@ -49,6 +53,13 @@ inline RodasTab make_rodas_tab(const Params& par, double hinv) {
   t.c61 = 0.8083246795921522e+01 * hinv; t.c62 = -0.7981132988064893e+01 * hinv; t.c63 = -0.3152159432874371e+02 * hinv;
   t.c64 = 0.1631930543123136e+02 * hinv; t.c65 = -0.6058818238834054e+01 * hinv;
   t.ghinv = hinv * (1.0 / RG);
+  const double hg = 1.0 / t.ghinv;
+  t.cs21 = t.c21 * hg;
+  t.cs31 = t.c31 * hg; t.cs32 = t.c32 * hg;
+  t.cs41 = t.c41 * hg; t.cs42 = t.c42 * hg; t.cs43 = t.c43 * hg;
+  t.cs51 = t.c51 * hg; t.cs52 = t.c52 * hg; t.cs53 = t.c53 * hg; t.cs54 = t.c54 * hg;
+  t.cs61 = t.c61 * hg; t.cs62 = t.c62 * hg; t.cs63 = t.c63 * hg; t.cs64 = t.c64 * hg; t.cs65 = t.c65 * hg;
+  t.kx = par.Ki_GCC * hg; t.kdc = par.Ki_DC * hg; t.kq = par.Ki_Q * hg; t.kpll = par.Ki_PLL * hg;
   for (int i = 0; i < 16; ++i) t.luc[i] = 0.0;
   M::lu_consts(par, t.ghinv, t.luc);
   return t;
@@ -116,19 +127,21 @@ PVDER_DEV void aux_advance(const Params& par, const Inputs& in, const Aux& b, do
   aux_advance_sv<EXACT>(par, in, b, dl0, V0, Y[M::IDX_DL], Y[M::IDX_VDC], a, out_of_range);
 }
 
-// Effective gains of the freezable rows (bit order of freeze_bits): the parameter, or 0 while the
-// row is clamped.  Computed once per sub-step; the generated RHS/Jacobian take them as inputs.
+// Effective gains of the freezable rows (bit order of freeze_bits): the parameter, or 0 while the row is
+// clamped; the unit-pivot rows (x, xDC, xQ) carry theirs pre-scaled by h*gamma, and gn[NFRZ] is the scaled
+// Ki_PLL.  Computed once per sub-step; the generated RHS/Jacobian take them as inputs.
 template <class M>
-PVDER_DEV void make_gains(const Params& par, unsigned frz, double (&gn)[M::NFRZ]) {
+PVDER_DEV void make_gains(const Params& par, const RodasTab& tab, unsigned frz, double (&gn)[M::NGAIN]) {
 #pragma unroll
   for (int k = 0; k < M::PHASES; ++k) {
-    gn[4 * k] = (frz & (1u << (4 * k))) ? 0.0 : par.Ki_GCC;
-    gn[4 * k + 1] = (frz & (1u << (4 * k + 1))) ? 0.0 : par.Ki_GCC;
+    gn[4 * k] = (frz & (1u << (4 * k))) ? 0.0 : tab.kx;
+    gn[4 * k + 1] = (frz & (1u << (4 * k + 1))) ? 0.0 : tab.kx;
     gn[4 * k + 2] = (frz & (1u << (4 * k + 2))) ? 0.0 : par.wp;
     gn[4 * k + 3] = (frz & (1u << (4 * k + 3))) ? 0.0 : par.wp;
   }
-  gn[4 * M::PHASES] = (frz & (1u << (4 * M::PHASES))) ? 0.0 : par.Ki_DC;
-  gn[4 * M::PHASES + 1] = (frz & (1u << (4 * M::PHASES + 1))) ? 0.0 : par.Ki_Q;
+  gn[4 * M::PHASES] = (frz & (1u << (4 * M::PHASES))) ? 0.0 : tab.kdc;
+  gn[4 * M::PHASES + 1] = (frz & (1u << (4 * M::PHASES + 1))) ? 0.0 : tab.kq;
+  gn[M::NFRZ] = tab.kpll;
 }
 
 // One half-cycle Rodas4 step.  `base` is the Aux record at y on entry and at the new y on exit.
@@ -138,8 +151,8 @@ PVDER_DEV void make_gains(const Params& par, unsigned frz, double (&gn)[M::NFRZ]
 template <class M, bool EXACT, bool FREE = false>
 PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
                            unsigned frz, Aux& base) {
-  double gn[M::NFRZ];
-  make_gains<M>(par, FREE ? 0u : frz, gn);
+  double gn[M::NGAIN];
+  make_gains<M>(par, tab, FREE ? 0u : frz, gn);
   constexpr int NS = M::NS;
   bool oor = false;
   const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
@@ -157,7 +170,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs(Y, par, in, ax, gn, K2);
 #pragma unroll
-  for (int i = 0; i < NS; ++i) K2[i] = fma(tab.c21, K1[i], K2[i]);
+  for (int i = 0; i < NS; ++i) K2[i] = fma((M::unit_row(i) ? tab.cs21 : tab.c21), K1[i], K2[i]);
   M::solve(lu, tab.luc, K2);
   // stage 3
 #pragma unroll
@@ -165,7 +178,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs(Y, par, in, ax, gn, K3);
 #pragma unroll
-  for (int i = 0; i < NS; ++i) K3[i] = fma(tab.c32, K2[i], fma(tab.c31, K1[i], K3[i]));
+  for (int i = 0; i < NS; ++i) K3[i] = fma((M::unit_row(i) ? tab.cs32 : tab.c32), K2[i], fma((M::unit_row(i) ? tab.cs31 : tab.c31), K1[i], K3[i]));
   M::solve(lu, tab.luc, K3);
   // stage 4
 #pragma unroll
@@ -173,7 +186,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs(Y, par, in, ax, gn, K4);
 #pragma unroll
-  for (int i = 0; i < NS; ++i) K4[i] = fma(tab.c43, K3[i], fma(tab.c42, K2[i], fma(tab.c41, K1[i], K4[i])));
+  for (int i = 0; i < NS; ++i) K4[i] = fma((M::unit_row(i) ? tab.cs43 : tab.c43), K3[i], fma((M::unit_row(i) ? tab.cs42 : tab.c42), K2[i], fma((M::unit_row(i) ? tab.cs41 : tab.c41), K1[i], K4[i])));
   M::solve(lu, tab.luc, K4);
 #if PVDER_FOLD
   // K1..K4 are folded into the stage-5/6 sums as soon as K4 exists (same FMAs, done early): three
@@ -182,31 +195,22 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
 #pragma unroll
   for (int i = 0; i < NS; ++i) {
     Y[i] = fma(tab.a54, K4[i], fma(tab.a53, K3[i], fma(tab.a52, K2[i], fma(tab.a51, K1[i], y[i]))));
-    C6[i] = fma(tab.c64, K4[i], fma(tab.c63, K3[i], fma(tab.c62, K2[i], tab.c61 * K1[i])));
-    K5[i] = fma(tab.c54, K4[i], fma(tab.c53, K3[i], fma(tab.c52, K2[i], tab.c51 * K1[i])));
+    C6[i] = fma((M::unit_row(i) ? tab.cs64 : tab.c64), K4[i], fma((M::unit_row(i) ? tab.cs63 : tab.c63), K3[i], fma((M::unit_row(i) ? tab.cs62 : tab.c62), K2[i], (M::unit_row(i) ? tab.cs61 : tab.c61) * K1[i])));
+    K5[i] = fma((M::unit_row(i) ? tab.cs54 : tab.c54), K4[i], fma((M::unit_row(i) ? tab.cs53 : tab.c53), K3[i], fma((M::unit_row(i) ? tab.cs52 : tab.c52), K2[i], (M::unit_row(i) ? tab.cs51 : tab.c51) * K1[i])));
   }
-  // stage 5
+  // stage 5: the right-hand side is accumulated onto the pre-loaded sum (rhs_acc folds the addend into each
+  // row's last multiply: no separate adds)
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
-  {
-    double F[NS];
-    M::rhs(Y, par, in, ax, gn, F);
-#pragma unroll
-    for (int i = 0; i < NS; ++i) K5[i] += F[i];
-  }
+  M::rhs_acc(Y, par, in, ax, gn, K5);
   M::solve(lu, tab.luc, K5);
   // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
 #pragma unroll
   for (int i = 0; i < NS; ++i) {
     Y[i] += K5[i];
-    C6[i] = fma(tab.c65, K5[i], C6[i]);
+    C6[i] = fma((M::unit_row(i) ? tab.cs65 : tab.c65), K5[i], C6[i]);
   }
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
-  {
-    double F[NS];
-    M::rhs(Y, par, in, ax, gn, F);
-#pragma unroll
-    for (int i = 0; i < NS; ++i) C6[i] += F[i];
-  }
+  M::rhs_acc(Y, par, in, ax, gn, C6);
   M::solve(lu, tab.luc, C6);
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] += C6[i];
@@ -220,7 +224,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   M::rhs(Y, par, in, ax, gn, K5);
 #pragma unroll
   for (int i = 0; i < NS; ++i)
-    K5[i] = fma(tab.c54, K4[i], fma(tab.c53, K3[i], fma(tab.c52, K2[i], fma(tab.c51, K1[i], K5[i]))));
+    K5[i] = fma((M::unit_row(i) ? tab.cs54 : tab.c54), K4[i], fma((M::unit_row(i) ? tab.cs53 : tab.c53), K3[i], fma((M::unit_row(i) ? tab.cs52 : tab.c52), K2[i], fma((M::unit_row(i) ? tab.cs51 : tab.c51), K1[i], K5[i]))));
   M::solve(lu, tab.luc, K5);
   // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
 #pragma unroll
@@ -230,7 +234,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   M::rhs(Y, par, in, ax, gn, K6);
 #pragma unroll
   for (int i = 0; i < NS; ++i)
-    K6[i] = fma(tab.c65, K5[i], fma(tab.c64, K4[i], fma(tab.c63, K3[i], fma(tab.c62, K2[i], fma(tab.c61, K1[i], K6[i])))));
+    K6[i] = fma((M::unit_row(i) ? tab.cs65 : tab.c65), K5[i], fma((M::unit_row(i) ? tab.cs64 : tab.c64), K4[i], fma((M::unit_row(i) ? tab.cs63 : tab.c63), K3[i], fma((M::unit_row(i) ? tab.cs62 : tab.c62), K2[i], fma((M::unit_row(i) ? tab.cs61 : tab.c61), K1[i], K6[i])))));
   M::solve(lu, tab.luc, K6);
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] += K6[i];

@@ -162,6 +162,10 @@ struct Split3 {
   static constexpr int NS_STORE = 23;
   static constexpr int PHASES = 3;
   static constexpr int N_LUC = 13;
+  // Unit-pivot slots (pure integrators: x of each phase; xDC, xQ, xPLL of the shared tail): their equations are
+  // scaled by h*gamma like in the one-thread models (gains and c_ij/h sums pre-scaled, pivot exactly 1).
+  static constexpr PVDER_HD bool unit_p(int i) { return i == 2 || i == 3; }
+  static constexpr PVDER_HD bool unit_s(int i) { return i >= 1 && i <= 3; }
 
   // Launch constants: reciprocal pivots and every gain-derived coefficient of the factorisation for the
   // common case that no anti-windup clamp is active (FREE instantiations read them from the constant bank
@@ -200,9 +204,9 @@ struct Split3 {
     double Qref, Vdcref;
   };
   struct Gains {      // effective gains of the freezable rows (0 while clamped)
-    V g0, g1, g2, g3; // xR, xI (Ki_GCC) ; uR, uI (wp)
+    V g0, g1, g2, g3; // xR, xI (Ki_GCC * h gamma: unit-pivot rows) ; uR, uI (wp)
     V duR, duI;       // 1/(ghinv + g2), 1/(ghinv + g3)
-    double g4, g5;    // xDC (Ki_DC), xQ (Ki_Q)
+    double g4, g5;    // xDC (Ki_DC * h gamma), xQ (Ki_Q * h gamma)
     bool any;
   };
   struct Pt {         // algebraic quantities at one state (A.2)
@@ -260,11 +264,12 @@ struct Split3 {
   // Autonomous right-hand side (A.3) from the point record.
   // FREE: no clamp active in this warp -> the gains are the parameters (constant bank), g is not read.
   template <bool FREE>
-  static PVDER_DEV void rhs(const Params& par, const Consts& k, const Aux& ax, const Gains& g, const Vec& Y, const Pt& q,
-                            Vec& F) {
-    const V g0 = FREE ? V(par.Ki_GCC) : g.g0, g1 = FREE ? V(par.Ki_GCC) : g.g1;
+  static PVDER_DEV void rhs(const Params& par, const Consts& k, const Aux& ax, const Gains& g, const double* luc,
+                            const Vec& Y, const Pt& q, Vec& F) {
+    // x, xDC, xQ, xPLL rows: gains pre-scaled by h*gamma (unit-pivot rows)
+    const V g0 = FREE ? V(luc[LC_GX]) : g.g0, g1 = FREE ? V(luc[LC_GX]) : g.g1;
     const V g2 = FREE ? V(par.wp) : g.g2, g3 = FREE ? V(par.wp) : g.g3;
-    const double g4 = FREE ? par.Ki_DC : g.g4, g5 = FREE ? par.Ki_Q : g.g5;
+    const double g4 = FREE ? luc[LC_G4H] : g.g4, g5 = FREE ? luc[LC_G5H] : g.g5;
     const double hV = 0.5 * Y.s[0];
     const V iR = Y.p[0], iI = Y.p[1];
     F.p[0] = vfma(q.wr, iI, par.inv_Lf * vfma(q.mR, hV, vfma(-par.Rf, iR, -q.vR)));
@@ -277,7 +282,7 @@ struct Split3 {
     F.s[0] = fma(-0.25 * Y.s[0], q.Ps, ax.Ppv) * (par.inv_C * ax.inv_Vdc);
     F.s[1] = g4 * q.dV;
     F.s[2] = -(g5 * q.dQ);
-    F.s[3] = par.Ki_PLL * q.vd;
+    F.s[3] = luc[LC_KIPLL_H] * q.vd;
     F.s[4] = q.wex + par.dw;
   }
 
@@ -311,8 +316,8 @@ struct Split3 {
       tkR = V(luc[LC_TK]);
       tkI = tkR;
     } else {
-      f.gxR = g.g0 * inv_gh;
-      f.gxI = g.g1 * inv_gh;
+      f.gxR = g.g0;        // gains of the unit-pivot rows arrive scaled by h*gamma
+      f.gxI = g.g1;
       f.thR = f.gxR + par.Kp_GCC;
       f.thI = f.gxI + par.Kp_GCC;
       f.kaR = g.duR * g.g2;
@@ -361,8 +366,8 @@ struct Split3 {
       piD = luc[LC_PID_DC];
       piQ = luc[LC_PIQ];
     } else {
-      f.g4h = g.g4 * inv_gh;
-      f.g5h = g.g5 * inv_gh;
+      f.g4h = g.g4;
+      f.g5h = g.g5;
       f.piD = piD = f.g4h + par.Kp_DC;
       f.piQ = piQ = f.g5h + par.Kp_Q;
     }
@@ -395,7 +400,7 @@ struct Split3 {
     const double g4h = FREE ? luc[LC_G4H] : f.g4h, g5h = FREE ? luc[LC_G5H] : f.g5h;
     const double piw = luc[LC_PIW], pid = luc[LC_PID];
     const V iR = y.p[0], iI = y.p[1];
-    const V hxR = b.p[2] * inv_gh, hxI = b.p[3] * inv_gh;
+    const V hxR = b.p[2], hxI = b.p[3];             // unit-pivot rows: right-hand side arrives scaled by h*gamma
     const V buR = duR * b.p[4], buI = duI * b.p[5];
     const V mmR = vfma(thR, buR, hxR), mmI = vfma(thI, buI, hxI);
     const V rR = vfma(f.e, mmR, b.p[0]), rI = vfma(f.e, mmI, b.p[1]);
@@ -403,7 +408,7 @@ struct Split3 {
     const double sQ = ln.sum3(vfma(f.qR, tR, f.qI * tI));
     const double sv = ln.sum3(vfma(f.dR, tR, f.dI * tI));
     const double sP = ln.sum3(vfma(f.pR, tR, vfma(f.pI, tI, vfma(iR, mmR, iI * mmI))));
-    const double b3 = inv_gh * b.s[1], b4 = inv_gh * b.s[2], hp = inv_gh * b.s[3];
+    const double b3 = b.s[1], b4 = b.s[2], hp = b.s[3];
     const double b1 = par.inv_wb * hp;
     const double kd0 = (b.s[4] + hp) * inv_gh;
     const double r1 = fma(f.RQ[0], b1, fma(f.RQ[1], b3, fma(f.RQ[2], b4, sQ)));
@@ -454,7 +459,7 @@ struct Split3 {
     m_over_out = m_over;
     // branch-free (the warp stays converged for the group votes): flags are masked by the group-wide
     // over-limit conditions instead of being computed under them
-    const V zero(0.0), kig(par.Ki_GCC), wp(par.wp), du_free(luc[LC_DU]), du_frz(luc[LC_INV_GH]);
+    const V zero(0.0), kig(luc[LC_GX]), wp(par.wp), du_free(luc[LC_DU]), du_frz(luc[LC_INV_GH]);
     const V uR = y.p[4], uI = y.p[5];
     const V duR = par.wp * (-uR + (k.rr * irefR - k.ri * irefI) - iR);
     const V duI = par.wp * (-uI + (k.ri * irefR + k.rr * irefI) - iI);
@@ -464,8 +469,8 @@ struct Split3 {
     g.g2 = vsel(f2, zero, wp); g.g3 = vsel(f3, zero, wp);
     g.duR = vsel(f2, du_frz, du_free); g.duI = vsel(f3, du_frz, du_free);
     const bool fdc = i_over && (sbits & 2), fq = i_over && (sbits & 4);
-    g.g4 = fdc ? 0.0 : par.Ki_DC;
-    g.g5 = fq ? 0.0 : par.Ki_Q;
+    g.g4 = fdc ? 0.0 : luc[LC_G4H];
+    g.g5 = fq ? 0.0 : luc[LC_G5H];
     g.any = ln.any3(vor(vor(f0, f1), vor(f2, f3))) || fdc || fq;
     return g;
   }
@@ -492,10 +497,12 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   {
     const S::Pt q = S::point(ln, par, k, in, base, y);
     S::template factor<FREE>(ln, par, k, in, base, g, y, q, tab.ghinv, tab.luc, fac);
-    S::template rhs<FREE>(par, k, base, g, y, q, K1);
+    S::template rhs<FREE>(par, k, base, g, tab.luc, y, q, K1);
   }
   S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K1);
-  // the same statement on the six per-phase slots (V) and the five shared slots (double)
+  // the same statement on the six per-phase slots (V) and the five shared slots (double); CC(m, nn) = c_nn/h,
+  // or c_nn*gamma on a unit-pivot slot
+#define CC(m, nn) (S::unit_##m(i) ? tab.cs##nn : tab.c##nn)
 #define PVDER_EACH(ST)                                        \
   _Pragma("unroll") for (int i = 0; i < 6; ++i) { ST(p) }     \
   _Pragma("unroll") for (int i = 0; i < 5; ++i) { ST(s) }
@@ -504,8 +511,8 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K2);
-#define ST(m) K2.m[i] = vfma(tab.c21, K1.m[i], K2.m[i]);
+  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K2);
+#define ST(m) K2.m[i] = vfma(CC(m, 21), K1.m[i], K2.m[i]);
   PVDER_EACH(ST)
 #undef ST
   S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K2);
@@ -514,8 +521,8 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K3);
-#define ST(m) K3.m[i] = vfma(tab.c32, K2.m[i], vfma(tab.c31, K1.m[i], K3.m[i]));
+  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K3);
+#define ST(m) K3.m[i] = vfma(CC(m, 32), K2.m[i], vfma(CC(m, 31), K1.m[i], K3.m[i]));
   PVDER_EACH(ST)
 #undef ST
   S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K3);
@@ -524,8 +531,8 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
-#define ST(m) K4.m[i] = vfma(tab.c43, K3.m[i], vfma(tab.c42, K2.m[i], vfma(tab.c41, K1.m[i], K4.m[i])));
+  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
+#define ST(m) K4.m[i] = vfma(CC(m, 43), K3.m[i], vfma(CC(m, 42), K2.m[i], vfma(CC(m, 41), K1.m[i], K4.m[i])));
   PVDER_EACH(ST)
 #undef ST
   S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K4);
@@ -534,14 +541,14 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   {                                                                                                            \
     const auto k1 = K1.m[i], k2 = K2.m[i], k3 = K3.m[i], k4 = K4.m[i];                                         \
     Y.m[i] = vfma(tab.a54, k4, vfma(tab.a53, k3, vfma(tab.a52, k2, vfma(tab.a51, k1, y.m[i]))));               \
-    K2.m[i] = vfma(tab.c54, k4, vfma(tab.c53, k3, vfma(tab.c52, k2, tab.c51 * k1)));                           \
-    K3.m[i] = vfma(tab.c64, k4, vfma(tab.c63, k3, vfma(tab.c62, k2, tab.c61 * k1)));                           \
+    K2.m[i] = vfma(CC(m, 54), k4, vfma(CC(m, 53), k3, vfma(CC(m, 52), k2, CC(m, 51) * k1)));                           \
+    K3.m[i] = vfma(CC(m, 64), k4, vfma(CC(m, 63), k3, vfma(CC(m, 62), k2, CC(m, 61) * k1)));                           \
   }
   PVDER_EACH(ST)
 #undef ST
   // stage 5
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
+  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K2.m[i] = K2.m[i] + K4.m[i];
   PVDER_EACH(ST)
 #undef ST
@@ -549,11 +556,11 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
 #define ST(m)                                   \
   Y.m[i] = Y.m[i] + K2.m[i];                    \
-  K3.m[i] = vfma(tab.c65, K2.m[i], K3.m[i]);
+  K3.m[i] = vfma(CC(m, 65), K2.m[i], K3.m[i]);
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::template rhs<FREE>(par, k, ax, g, Y, S::point(ln, par, k, in, ax, Y), K4);
+  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K3.m[i] = K3.m[i] + K4.m[i];
   PVDER_EACH(ST)
 #undef ST
@@ -562,6 +569,7 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   PVDER_EACH(ST)
 #undef ST
 #undef PVDER_EACH
+#undef CC
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   if (!EXACT && ln.any3(oor)) return false;   // group-wide: the three lanes must agree on the redo
   y = Y;

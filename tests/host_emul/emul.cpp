@@ -107,8 +107,10 @@ static void rhs_one(const pvder_env_config& cfg, const double* yin, const double
   Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
   Aux ax;
   aux_exact<M>(cfg.par, in, y, ax);
-  double gn[M::NFRZ];
-  make_gains<M>(cfg.par, frz, gn);
+  // h*gamma = 1: the unit-pivot rows come out unscaled (tests compare with the oracle's f)
+  const RodasTab tab = make_rodas_tab<M>(cfg.par, RG);
+  double gn[M::NGAIN];
+  make_gains<M>(cfg.par, tab, frz, gn);
   M::rhs(y, cfg.par, in, ax, gn, ff);
   for (int i = 0; i < M::NS; ++i) f[i] = ff[i];
 }
@@ -122,12 +124,14 @@ static void wsolve_one(const pvder_env_config& cfg, const double* yin, const dou
   typename M::LU lu;
   Aux ax;
   aux_exact<M>(cfg.par, in, y, ax);
-  double luc[16];
-  M::lu_consts(cfg.par, ghinv, luc);
-  double gn[M::NFRZ];
-  make_gains<M>(cfg.par, frz, gn);
-  M::factor(y, cfg.par, in, ax, gn, ghinv, luc, lu);
-  M::solve(lu, luc, bb);
+  // the solve works on the scaled system: unit-pivot rows of the right-hand side are pre-scaled by h*gamma
+  const RodasTab tab = make_rodas_tab<M>(cfg.par, ghinv * RG);
+  double gn[M::NGAIN];
+  make_gains<M>(cfg.par, tab, frz, gn);
+  for (int i = 0; i < M::NS; ++i)
+    if (M::unit_row(i)) bb[i] *= 1.0 / tab.ghinv;
+  M::factor(y, cfg.par, in, ax, gn, tab.ghinv, tab.luc, lu);
+  M::solve(lu, tab.luc, bb);
   for (int i = 0; i < M::NS; ++i) b[i] = bb[i];
 }
 
@@ -226,19 +230,28 @@ static void split_one(const pvder_env_config& cfg, const double* yin, const doub
   Split3::lu_consts(cfg.par, ghinv, luc);
   Split3::Gains g;
   auto bit = [&](int b_) { return (frz >> b_) & 1u; };
+  // mode 0 (rhs): h*gamma = 1 so that the unit-pivot rows come out unscaled; mode 1: the solve works on the scaled
+  // system (gains of the unit-pivot rows and their right-hand sides pre-scaled by h*gamma = 1/ghinv)
+  if (mode == 0) ghinv = 1.0;
+  Split3::lu_consts(cfg.par, ghinv, luc);
+  const double hg = 1.0 / ghinv;
   auto gv = [&](int j, double val) { return V3(bit(j) ? 0.0 : val, bit(4 + j) ? 0.0 : val, bit(8 + j) ? 0.0 : val); };
-  g.g0 = gv(0, cfg.par.Ki_GCC); g.g1 = gv(1, cfg.par.Ki_GCC); g.g2 = gv(2, cfg.par.wp); g.g3 = gv(3, cfg.par.wp);
+  g.g0 = gv(0, cfg.par.Ki_GCC * hg); g.g1 = gv(1, cfg.par.Ki_GCC * hg); g.g2 = gv(2, cfg.par.wp); g.g3 = gv(3, cfg.par.wp);
   g.duR = V3(1.0) / (g.g2 + V3(ghinv));
   g.duI = V3(1.0) / (g.g3 + V3(ghinv));
-  g.g4 = bit(12) ? 0.0 : cfg.par.Ki_DC;
-  g.g5 = bit(13) ? 0.0 : cfg.par.Ki_Q;
+  g.g4 = bit(12) ? 0.0 : cfg.par.Ki_DC * hg;
+  g.g5 = bit(13) ? 0.0 : cfg.par.Ki_Q * hg;
   g.any = frz != 0;
   const Split3::Pt q = Split3::point(ln, cfg.par, kc, in, ax, y);
   if (mode == 0) {
-    if (frz == 0 && free_path) Split3::rhs<true>(cfg.par, kc, ax, g, y, q, b);
-    else Split3::rhs<false>(cfg.par, kc, ax, g, y, q, b);
+    if (frz == 0 && free_path) Split3::rhs<true>(cfg.par, kc, ax, g, luc, y, q, b);
+    else Split3::rhs<false>(cfg.par, kc, ax, g, luc, y, q, b);
   } else {
     load_split(out, 1, 0, b);
+    for (int i = 0; i < 6; ++i)
+      if (Split3::unit_p(i)) b.p[i] = b.p[i] * V3(hg);
+    for (int i = 0; i < 5; ++i)
+      if (Split3::unit_s(i)) b.s[i] *= hg;
     Split3::Fac fac;
     if (frz == 0 && free_path) {
       Split3::factor<true>(ln, cfg.par, kc, in, ax, g, y, q, ghinv, luc, fac);

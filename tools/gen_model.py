@@ -69,7 +69,8 @@ def build(P, mult=1):
     # effective values g_b (= the parameter, or 0 while the row is clamped), so clamping costs
     # nothing inside the RHS/Jacobian and a clamped row of W is automatically e_r/(h*gamma).
     nfrz = 4 * P + 2
-    gs = [sp.Symbol(f"g_{b}") for b in range(nfrz)]
+    # gs[nfrz] is not a freezable row: it carries Ki_PLL pre-scaled by h*gamma (unit-pivot rows, see generate())
+    gs = [sp.Symbol(f"g_{b}") for b in range(nfrz + 1)]
     vR, vI, mR, mI = [], [], [], []
     Q = 0
     Pinv = 0
@@ -107,7 +108,7 @@ def build(P, mult=1):
     f[base] = (inp["Ppv"] - Pinv) * p["inv_C"] * inv_Vdc
     f[base + 1] = gs[4 * P] * (inp["Vdcref"] - Vdc)                                  # Ki_DC
     f[base + 2] = -gs[4 * P + 1] * (inp["Qref"] - Q)                                 # Ki_Q
-    f[base + 3] = p["Ki_PLL"] * vd
+    f[base + 3] = gs[nfrz] * vd
     f[base + 4] = p["Kp_PLL"] * vd + xPLL + p["dw"]
     # Jacobian: chain rule through the helper symbols
     helpers = {sn: sp.sin(dl), cs: sp.cos(dl), inv_Vdc: 1 / Vdc}
@@ -134,11 +135,20 @@ def build(P, mult=1):
     for k in range(P):
         frozen_rows += [6 * k + 2, 6 * k + 3, 6 * k + 4, 6 * k + 5]
     frozen_rows += [base + 1, base + 2]
+    # Unit-pivot rows: pure integrators (x, xDC, xQ, xPLL) whose row of W is [.. -J_rc .., 1/(h g), ..] with
+    # J_rr = 0.  Their gains arrive PRE-SCALED by h*gamma (so f_r and J_rc come out scaled at no cost) and the
+    # stepper scales their c_ij/h sums by the same constant: the pivot is exactly 1 and needs no multiply.
+    unit_rows = []
+    for k in range(P):
+        unit_rows += [6 * k + 2, 6 * k + 3]
+    unit_rows += [base + 1, base + 2, base + 3]
+    for r in unit_rows:
+        assert (r, r) not in J, r
     return dict(P=P, mult=mult, n=n, names=names, gs=gs, y=y, f=f, J=J, par=par, inp=inp, frozen=frozen_rows,
-                helpers=(sn, cs, inv_Vdc))
+                helpers=(sn, cs, inv_Vdc), unit_rows=unit_rows)
 
 
-def emit_rhs_structured(m):
+def emit_rhs_structured(m, acc=False):
     """Hand-structured emission of the right-hand side (same function as m['f'], which the Jacobian
     is differentiated from; equality is asserted numerically in gen-time self-check and by
     tests/test_emul_parity.py).  About 30 % fewer FP64 instructions than CSE of the expanded
@@ -148,6 +158,9 @@ def emit_rhs_structured(m):
     nm = m["names"]
     L = []
     A = L.append
+    # acc: f[] arrives pre-loaded (the stage's sum of c_ij/h K_j) and the right-hand side is ADDED to it; every
+    # row but the last ends in a multiply that becomes an FMA with that addend, so the sum costs no extra adds
+    T = (lambda i: f"f[{i}]") if acc else (lambda i: None)
     c3 = "0.86602540378443864676"
     rots = [("1", "0")] if P == 1 else [("1", "0"), ("-0.5", "-" + c3), ("-0.5", c3)]
     alph = [("1", "0")] if P == 1 else [("1", "0"), ("-0.5", c3), ("-0.5", "-" + c3)]
@@ -190,27 +203,34 @@ def emit_rhs_structured(m):
         o = 6 * k
         iR, iI, xR, xI, uR, uI = ["y_" + nm[o + j] for j in range(6)]
         rr, ri = rots[k]
-        A(f"    f[{o}] = fma(wr, {iI}, p_inv_Lf * fma(mR{k}, hV, fma(-p_Rf, {iR}, -vR{k})));")
-        A(f"    f[{o + 1}] = fma(-wr, {iR}, p_inv_Lf * fma(mI{k}, hV, fma(-p_Rf, {iI}, -vI{k})));")
-        A(f"    f[{o + 2}] = g_{4 * k} * {uR};")
-        A(f"    f[{o + 3}] = g_{4 * k + 1} * {uI};")
+        def mul_or_fma(i, a, b):
+            return f"    f[{i}] = fma({a}, {b}, f[{i}]);" if acc else f"    f[{i}] = {a} * {b};"
+
+        if acc:
+            A(f"    f[{o}] = fma(wr, {iI}, fma(p_inv_Lf, fma(mR{k}, hV, fma(-p_Rf, {iR}, -vR{k})), f[{o}]));")
+            A(f"    f[{o + 1}] = fma(-wr, {iR}, fma(p_inv_Lf, fma(mI{k}, hV, fma(-p_Rf, {iI}, -vI{k})), f[{o + 1}]));")
+        else:
+            A(f"    f[{o}] = fma(wr, {iI}, p_inv_Lf * fma(mR{k}, hV, fma(-p_Rf, {iR}, -vR{k})));")
+            A(f"    f[{o + 1}] = fma(-wr, {iR}, p_inv_Lf * fma(mI{k}, hV, fma(-p_Rf, {iI}, -vI{k})));")
+        A(mul_or_fma(o + 2, f"g_{4 * k}", uR))
+        A(mul_or_fma(o + 3, f"g_{4 * k + 1}", uI))
         if k == 0:
-            A(f"    f[{o + 4}] = g_{4 * k + 2} * ((irefR - {uR}) - {iR});")
-            A(f"    f[{o + 5}] = g_{4 * k + 3} * ((irefI - {uI}) - {iI});")
+            A(mul_or_fma(o + 4, f"g_{4 * k + 2}", f"((irefR - {uR}) - {iR})"))
+            A(mul_or_fma(o + 5, f"g_{4 * k + 3}", f"((irefI - {uI}) - {iI})"))
         else:
             A(f"    const double rfR{k} = fma({rr}, irefR, -({ri} * irefI)), rfI{k} = fma({ri}, irefR, {rr} * irefI);")
-            A(f"    f[{o + 4}] = g_{4 * k + 2} * ((rfR{k} - {uR}) - {iR});")
-            A(f"    f[{o + 5}] = g_{4 * k + 3} * ((rfI{k} - {uI}) - {iI});")
-    A(f"    f[{base}] = fma({-0.25 * mult} * y_Vdc, Ps, in_Ppv) * (p_inv_C * inv_Vdc);")
-    A(f"    f[{base + 1}] = g_{4 * P} * dV;")
-    A(f"    f[{base + 2}] = -(g_{4 * P + 1} * dQ);")
-    A(f"    f[{base + 3}] = p_Ki_PLL * vd;")
-    A(f"    f[{base + 4}] = wex + p_dw;")
+            A(mul_or_fma(o + 4, f"g_{4 * k + 2}", f"((rfR{k} - {uR}) - {iR})"))
+            A(mul_or_fma(o + 5, f"g_{4 * k + 3}", f"((rfI{k} - {uI}) - {iI})"))
+    A(mul_or_fma(base, f"fma({-0.25 * mult} * y_Vdc, Ps, in_Ppv)", "(p_inv_C * inv_Vdc)"))
+    A(mul_or_fma(base + 1, f"g_{4 * P}", "dV"))
+    A(mul_or_fma(base + 2, f"(-g_{4 * P + 1})", "dQ") if acc else f"    f[{base + 2}] = -(g_{4 * P + 1} * dQ);")
+    A(mul_or_fma(base + 3, f"g_{4 * P + 2}", "vd"))
+    A(f"    f[{base + 4}] = (wex + p_dw) + f[{base + 4}];" if acc else f"    f[{base + 4}] = wex + p_dw;")
     return L
 
 
-def check_structured_rhs(m, lines):
-    """Gen-time self-check: evaluate the emitted C (as Python) against the symbolic f."""
+def check_structured_rhs(m, lines, acc=False):
+    """Gen-time self-check: evaluate the emitted C (as Python) against the symbolic f (acc: against f + preload)."""
     import math
     import random
 
@@ -222,14 +242,15 @@ def check_structured_rhs(m, lines):
         env[str(s_)] = v
         syms[s_] = v
     syms[sp.Symbol("SQ3")] = math.sqrt(3.0)
-    f = [0.0] * m["n"]
+    pre = [rnd.uniform(-1.0, 1.0) if acc else 0.0 for _ in range(m["n"])]
+    f = list(pre)
     env["f"] = f
     for ln in lines:
         stmt = ln.strip().rstrip(";").replace("const double ", "")
         for part in _split_decl(stmt):
             exec(part, env)
     for r in range(m["n"]):
-        ref = float(m["f"][r].subs(syms))
+        ref = float(m["f"][r].subs(syms)) + pre[r]
         assert abs(f[r] - ref) <= 1e-12 * max(1.0, abs(ref)), (r, f[r], ref)
 
 
@@ -330,6 +351,12 @@ def generate(P, mult=1):
     nf = len(m["frozen"])
     A(f"  static constexpr int NFRZ = {nf};   // freezable rows / freeze-mask bits (rows: " +
       ",".join(m["names"][r] for r in m["frozen"]) + ")")
+    unit = set(m["unit_rows"])
+    A(f"  static constexpr int NGAIN = {nf + 1};  // gn[]: the NFRZ effective gains + Ki_PLL; the gains of the unit-pivot rows")
+    A("                                    // and Ki_PLL are pre-scaled by h*gamma (make_gains)")
+    A("  // rows whose equation is scaled by h*gamma so that their pivot is exactly 1 (pure integrators)")
+    A(f"  static constexpr unsigned UNIT_MASK = {hex(sum(1 << r for r in unit))}u;   // rows: " + ",".join(m["names"][r] for r in sorted(unit)))
+    A("  static constexpr PVDER_HD bool unit_row(int i) { return ((UNIT_MASK >> i) & 1u) != 0u; }")
     A(f"  static constexpr int IDX_VDC = {6 * P};")
     A(f"  static constexpr int IDX_DL = {6 * P + 4};")
     A("")
@@ -341,11 +368,11 @@ def generate(P, mult=1):
         return out
 
     par_unpack = [f"    const double p_{nme} = par.{nme};" for nme in PAR]
-    gain_unpack = [f"    const double g_{b} = gn[{b}];" for b in range(len(m["frozen"]))]
+    gain_unpack = [f"    const double g_{b} = gn[{b}];" for b in range(len(m["frozen"]) + 1)]
     # ---------- rhs
     A("  // Autonomous right-hand side f(y).  gn[b]: effective gain of freezable row b (0 while clamped).")
     A("  static PVDER_DEV void rhs(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
-    A("                            const double (&gn)[NFRZ], double (&f)[NS]) {")
+    A("                            const double (&gn)[NGAIN], double (&f)[NS]) {")
     L.extend(par_unpack)
     L.extend(unpack())
     A("    const double in_vg = in.vg, in_vgb = in.vgb, in_vgc = in.vgc, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
@@ -358,11 +385,28 @@ def generate(P, mult=1):
     L.extend(rhs_lines)
     A("  }")
     A("")
+    A("  // f += right-hand side (f pre-loaded with a stage's sum of c_ij/h K_j): the same expressions with the")
+    A("  // addend folded into each row's last multiply.")
+    A("  static PVDER_DEV void rhs_acc(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
+    A("                                const double (&gn)[NGAIN], double (&f)[NS]) {")
+    L.extend(par_unpack)
+    L.extend(unpack())
+    A("    const double in_vg = in.vg, in_vgb = in.vgb, in_vgc = in.vgc, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
+    A("    (void)in_vgb; (void)in_vgc;")
+    A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
+    A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, inv_Vdc = aux.inv_Vdc;")
+    L.extend(gain_unpack)
+    acc_lines = emit_rhs_structured(m, acc=True)
+    check_structured_rhs(m, acc_lines, acc=True)
+    L.extend(acc_lines)
+    A("  }")
+    A("")
     # ---------- factor
     pattern = set(J.keys()) | {(i, i) for i in range(n)}
     order = elimination_order(n, pattern, P)
     wname = lambda r, c: f"w_{r}_{c}"
-    A("  // LU factors of W = I/(h*gamma) - J(y), fixed pattern, fixed pivot order:")
+    A("  // LU factors of W = I/(h*gamma) - J(y) with the UNIT_ROW rows scaled by h*gamma (their gains and their")
+    A("  // right-hand sides arrive pre-scaled: pivot 1), fixed pattern, fixed pivot order:")
     A("  //   " + " ".join(m["names"][k] for k in order))
     # symbolic elimination to learn the final pattern
     pat = set(pattern)
@@ -417,7 +461,7 @@ def generate(P, mult=1):
         if r != c and not (r in coreset and c in coreset):
             A(f"    double {wname(r, c)};")
     for k in range(n):
-        if not (CONST_PIVOTS == "bank" and k in const_piv) and k not in coreset:
+        if not (CONST_PIVOTS == "bank" and k in const_piv) and k not in coreset and k not in unit:
             A(f"    double d_{k};")
     for r in core:
         for c in core:
@@ -427,7 +471,7 @@ def generate(P, mult=1):
     A(f"  static constexpr int LU_ENTRIES = {len(members)};   // incl. {len(members) - len(pattern)} fill-ins")
     A("")
     A("  static PVDER_DEV void factor(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
-    A("                               const double (&gn)[NFRZ], double ghinv, const double* luc, LU& lu) {")
+    A("                               const double (&gn)[NGAIN], double ghinv, const double* luc, LU& lu) {")
     L.extend(par_unpack)
     L.extend(unpack())
     A("    const double in_vg = in.vg, in_vgb = in.vgb, in_vgc = in.vgc, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
@@ -442,6 +486,8 @@ def generate(P, mult=1):
     L.extend(emit_block([(f"j_{r}_{c}", J[(r, c)]) for (r, c) in keys], "q"))
     # W entries
     for i in range(n):
+        if i in unit:
+            continue                      # pivot exactly 1 (scaled row, J_ii = 0)
         if (i, i) in J:
             A(f"    double w_{i}_{i} = ghinv - j_{i}_{i};")
         else:
@@ -452,13 +498,16 @@ def generate(P, mult=1):
     for op in ops:
         if op[0] == "inv":
             k = op[1]
-            if k in const_piv:
+            if k in unit:
+                pass
+            elif k in const_piv:
                 A(f"    const double d_{k} = luc[{const_piv[k] + 1}];")
             else:
                 A(f"    const double d_{k} = pvder_rcp(w_{k}_{k});")
         elif op[0] == "mul":
             _, r, k = op
-            A(f"    {wname(r, k)} *= d_{k};")
+            if k not in unit:
+                A(f"    {wname(r, k)} *= d_{k};")
         elif op[0] == "fma":
             _, r, c, k = op
             A(f"    {wname(r, c)} = fma(-{wname(r, k)}, {wname(k, c)}, {wname(r, c)});")
@@ -503,7 +552,7 @@ def generate(P, mult=1):
         if r != c and not (r in coreset and c in coreset):
             A(f"    lu.{wname(r, c)} = {wname(r, c)};")
     for k in range(n):
-        if not (CONST_PIVOTS == "bank" and k in const_piv) and k not in coreset:
+        if not (CONST_PIVOTS == "bank" and k in const_piv) and k not in coreset and k not in unit:
             A(f"    lu.d_{k} = d_{k};")
     A("  }")
     A("")
@@ -534,6 +583,8 @@ def generate(P, mult=1):
         for c in sorted(c for c in range(n) if pos[c] > pos[k] and (k, c) in pat):
             A(f"    b[{k}] = fma(-lu.{wname(k, c)}, b[{c}], b[{k}]);")
             nflop_s += 2
+        if k in unit:
+            continue                      # unit pivot
         if CONST_PIVOTS == "bank" and k in const_piv:
             A(f"    b[{k}] *= luc[{const_piv[k] + 1}];")
         else:
