@@ -34,6 +34,7 @@ struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant 
   // i.e. their gains and their sums of c_ij/h K_j are -- then the pivot is exactly 1 and costs no multiply.
   double cs21, cs31, cs32, cs41, cs42, cs43, cs51, cs52, cs53, cs54, cs61, cs62, cs63, cs64, cs65;   // c_ij * gamma
   double kx, kdc, kq, kpll;   // Ki_GCC, Ki_DC, Ki_Q, Ki_PLL times h*gamma
+  double du_free, du_frz;     // reciprocal pivot of a free / clamped u row: 1/(1/(h g) + wp), h g
 };
 
 template <class M>
@@ -60,6 +61,8 @@ inline RodasTab make_rodas_tab(const Params& par, double hinv) {
   t.cs51 = t.c51 * hg; t.cs52 = t.c52 * hg; t.cs53 = t.c53 * hg; t.cs54 = t.c54 * hg;
   t.cs61 = t.c61 * hg; t.cs62 = t.c62 * hg; t.cs63 = t.c63 * hg; t.cs64 = t.c64 * hg; t.cs65 = t.c65 * hg;
   t.kx = par.Ki_GCC * hg; t.kdc = par.Ki_DC * hg; t.kq = par.Ki_Q * hg; t.kpll = par.Ki_PLL * hg;
+  t.du_free = 1.0 / (t.ghinv + par.wp);
+  t.du_frz = hg;
   for (int i = 0; i < 16; ++i) t.luc[i] = 0.0;
   M::lu_consts(par, t.ghinv, t.luc);
   return t;
@@ -142,6 +145,12 @@ PVDER_DEV void make_gains(const Params& par, const RodasTab& tab, unsigned frz, 
   gn[4 * M::PHASES] = (frz & (1u << (4 * M::PHASES))) ? 0.0 : tab.kdc;
   gn[4 * M::PHASES + 1] = (frz & (1u << (4 * M::PHASES + 1))) ? 0.0 : tab.kq;
   gn[M::NFRZ] = tab.kpll;
+  // reciprocal pivots of the u rows: 1/(1/(h g) + wp), or h g while the row is clamped
+#pragma unroll
+  for (int k = 0; k < M::PHASES; ++k) {
+    gn[M::NFRZ + 1 + 2 * k] = (frz & (1u << (4 * k + 2))) ? tab.du_frz : tab.du_free;
+    gn[M::NFRZ + 2 + 2 * k] = (frz & (1u << (4 * k + 3))) ? tab.du_frz : tab.du_free;
+  }
 }
 
 // One half-cycle Rodas4 step.  `base` is the Aux record at y on entry and at the new y on exit.
@@ -310,7 +319,9 @@ template <class M>
 PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, const Inputs& in, bool& m_over_out) {
   constexpr int P = M::PHASES;
   constexpr int B = 6 * P;
-  double Q = 0.0;
+  // Same expression trees as the generated right-hand side (vR, vI, qs, Qp, iref): when the stepper is inlined
+  // after this function the compiler shares them with stage 1 instead of computing them twice.
+  double Qs = 0.0;
   bool m_over = false;
 #pragma unroll
   for (int k = 0; k < P; ++k) {
@@ -321,12 +332,23 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
     const double mI = fma(par.Kp_GCC, y[6 * k + 5], y[6 * k + 3]);
     m_over |= (mR * mR + mI * mI) > par.m_limit10 * par.m_limit10;
     const double vgk = M::BALANCED3 ? in.vg : vg_of_phase(in, P, k);
-    Q += M::PMULT * 0.5 * ((vgk * ri) * iR - (vgk * rr) * iI + par.Xt * (iR * iR + iI * iI));
+    double vR, vI;
+    if (P == 1 || k == 0) {
+      vR = fma(par.Rt, iR, fma(-par.Xt, iI, vgk));
+      vI = fma(par.Xt, iR, par.Rt * iI);
+    } else {
+      vR = fma(par.Rt, iR, fma(-par.Xt, iI, rr * vgk));
+      vI = fma(par.Xt, iR, fma(par.Rt, iI, ri * vgk));
+    }
+    const double qs = fma(vI, iR, -(vR * iI));
+    Qs = (k == 0) ? qs : Qs + qs;
   }
+  const double Q = (0.5 * M::PMULT) * Qs;
   m_over_out = m_over;
   const double Vdc = y[B], xDC = y[B + 1], xQ = y[B + 2];
-  const double irefR = xDC + par.Kp_DC * (in.Vdcref - Vdc);
-  const double irefI = xQ - par.Kp_Q * (in.Qref - Q);
+  const double dV = in.Vdcref - Vdc, dQ = in.Qref - Q;
+  const double irefR = fma(par.Kp_DC, dV, xDC);
+  const double irefI = fma(-par.Kp_Q, dQ, xQ);
   const bool i_over = (irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit;
   if (!(m_over || i_over)) return 0u;
   unsigned bits = 0u;
@@ -597,16 +619,27 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
     Aux base;
     Inputs in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);   // changes only when an event fires
     aux_exact<M>(par, in, r.y, base);         // library sincos/exp/div once per env step, then incremental
-    for (int s = 0; s < cfg.n_sub_per_step; ++s) {
+    // One loop over the integrator steps (micro per half-cycle, normally 1).  The clamp mode is sampled right
+    // before every step, in the same basic block as the step itself: freeze_bits uses the expression trees of the
+    // generated right-hand side, so stage 1 reuses its vR, vI, m, Q, iref instead of recomputing them.
+    const int total = cfg.n_sub_per_step * cfg.micro;
+    int m_left = cfg.micro, s = 0;
+    bool clamped = false;
+    for (int it = 0; it < total; ++it) {
       bool m_over;
       const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
-      if (frz) r.windup += 1;
+      clamped |= frz != 0u;
       // the duty-cycle clamp acts on Re/Im parts per phase and would break the symmetry the
       // balanced representation relies on: report instead of integrating something else
       if (M::BALANCED3 && m_over) r.status = PVDER_STATUS_UNBALANCED;
-      for (int m = 0; m < cfg.micro; ++m)
-        if (!rodas4_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
+      if (!rodas4_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
+      if (--m_left != 0) continue;
+      // half-cycle boundary
+      m_left = cfg.micro;
+      if (clamped) r.windup += 1;
+      clamped = false;
       if (traj) record_substep<M>(traj, traj_ld, s, r.y, r.Vgrid, r.Sinsol);
+      s += 1;
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);

@@ -70,7 +70,8 @@ def build(P, mult=1):
     # nothing inside the RHS/Jacobian and a clamped row of W is automatically e_r/(h*gamma).
     nfrz = 4 * P + 2
     # gs[nfrz] is not a freezable row: it carries Ki_PLL pre-scaled by h*gamma (unit-pivot rows, see generate())
-    gs = [sp.Symbol(f"g_{b}") for b in range(nfrz + 1)]
+    # gs[nfrz + 1 + 2k + {0,1}]: reciprocal pivots of the u rows of phase k (1/(1/(h g) + wp), or h g while clamped)
+    gs = [sp.Symbol(f"g_{b}") for b in range(nfrz + 1 + 2 * P)]
     vR, vI, mR, mI = [], [], [], []
     Q = 0
     Pinv = 0
@@ -352,8 +353,8 @@ def generate(P, mult=1):
     A(f"  static constexpr int NFRZ = {nf};   // freezable rows / freeze-mask bits (rows: " +
       ",".join(m["names"][r] for r in m["frozen"]) + ")")
     unit = set(m["unit_rows"])
-    A(f"  static constexpr int NGAIN = {nf + 1};  // gn[]: the NFRZ effective gains + Ki_PLL; the gains of the unit-pivot rows")
-    A("                                    // and Ki_PLL are pre-scaled by h*gamma (make_gains)")
+    A(f"  static constexpr int NGAIN = {nf + 1 + 2 * P};  // gn[]: the NFRZ effective gains, Ki_PLL, then the reciprocal pivots of the")
+    A("                                    // u rows; the gains of the unit-pivot rows and Ki_PLL are pre-scaled by h*gamma (make_gains)")
     A("  // rows whose equation is scaled by h*gamma so that their pivot is exactly 1 (pure integrators)")
     A(f"  static constexpr unsigned UNIT_MASK = {hex(sum(1 << r for r in unit))}u;   // rows: " + ",".join(m["names"][r] for r in sorted(unit)))
     A("  static constexpr PVDER_HD bool unit_row(int i) { return ((UNIT_MASK >> i) & 1u) != 0u; }")
@@ -369,6 +370,11 @@ def generate(P, mult=1):
 
     par_unpack = [f"    const double p_{nme} = par.{nme};" for nme in PAR]
     gain_unpack = [f"    const double g_{b} = gn[{b}];" for b in range(len(m["frozen"]) + 1)]
+    # u rows: pivot 1/(h g) + g_u is untouched by the earlier eliminations, its reciprocal comes with the gains
+    u_piv = {}
+    for k_ in range(P):
+        u_piv[6 * k_ + 4] = nf + 1 + 2 * k_
+        u_piv[6 * k_ + 5] = nf + 1 + 2 * k_ + 1
     # ---------- rhs
     A("  // Autonomous right-hand side f(y).  gn[b]: effective gain of freezable row b (0 while clamped).")
     A("  static PVDER_DEV void rhs(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
@@ -445,6 +451,7 @@ def generate(P, mult=1):
                 luc_exprs.append(1 / (GH - jkk))
         elif op[0] in ("fma", "new"):
             touched.add((op[1], op[2]))
+    touched_all = {(op[1], op[2]) for op in ops if op[0] in ("fma", "new")}
     A(f"  static constexpr int N_LUC = {len(luc_exprs) + 1};   // launch-constant reciprocal pivots (+ 1/ghinv)")
     A("  // luc[0] = 1/ghinv (pivot of a frozen row); luc[1 + i] = reciprocal of constant pivot i")
     A("  static PVDER_HD void lu_consts(const Params& par, double ghinv, double* luc) {")
@@ -500,6 +507,8 @@ def generate(P, mult=1):
             k = op[1]
             if k in unit:
                 pass
+            elif k in u_piv and (k, k) not in touched_all and J[(k, k)] == -m["gs"][4 * (k // 6) + 2 + (k % 6 - 4)]:
+                A(f"    const double d_{k} = gn[{u_piv[k]}];")
             elif k in const_piv:
                 A(f"    const double d_{k} = luc[{const_piv[k] + 1}];")
             else:
