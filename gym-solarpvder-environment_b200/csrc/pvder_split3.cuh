@@ -442,14 +442,15 @@ struct Split3 {
   // Anti-windup mode (A.3) sampled at the sub-step start; same decisions as freeze_bits<Model3ph>.
   template <class L>
   static PVDER_DEV Gains gains(const L& ln, const Params& par, const Consts& k, const In& in, const Vec& y,
-                               const Pt& q, const double* luc, bool& m_over_out) {
-    // q = point(y): the duty cycle, Q and the current reference are the ones stage 1 uses (computed once)
+                               const double* luc, bool& m_over_out) {
     Gains g;
     const V iR = y.p[0], iI = y.p[1];
-    const bool m_over = ln.any3(vgt(q.mR * q.mR + q.mI * q.mI, V(par.m_limit10 * par.m_limit10)));
-    const double Q = q.Qp;
+    const V mR = vfma(par.Kp_GCC, y.p[4], y.p[2]), mI = vfma(par.Kp_GCC, y.p[5], y.p[3]);
+    const bool m_over = ln.any3(vgt(mR * mR + mI * mI, V(par.m_limit10 * par.m_limit10)));
+    const double Q = ln.sum3(0.5 * (in.vgI * iR - in.vgR * iI + par.Xt * (iR * iR + iI * iI)));
     const double Vdc = y.s[0], xDC = y.s[1], xQ = y.s[2];
-    const double irefR = q.irefR, irefI = q.irefI;
+    const double irefR = xDC + par.Kp_DC * (in.Vdcref - Vdc);
+    const double irefI = xQ - par.Kp_Q * (in.Qref - Q);
     // decisions on the shared rows come from sums: take lane a's so the three lanes agree
     const int sbits = ln.from_a(((irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit ? 1 : 0) |
                                 (same_sign(par.Ki_DC * (in.Vdcref - Vdc), xDC) ? 2 : 0) |
@@ -483,7 +484,7 @@ struct Split3 {
 template <bool EXACT, bool FREE, class LN>
 PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_config& cfg, const Inputs& in_s,
                                  const Split3::In& in, const Split3::Consts& k, const RodasTab& tab,
-                                 const Split3::Gains& g, const Split3::Pt& q0, Aux& base) {
+                                 const Split3::Gains& g, Aux& base) {
   using S = Split3;
   using Vec = S::Vec;
   const Params& par = cfg.par;
@@ -493,9 +494,11 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   Vec K1, K2, K3, K4, Y;
   Aux ax;
   S::Fac fac;
-  // q0 = point(y) comes from the caller, which needed it for the clamp decision
-  S::template factor<FREE>(ln, par, k, in, base, g, y, q0, tab.ghinv, tab.luc, fac);
-  S::template rhs<FREE>(par, k, base, g, tab.luc, y, q0, K1);
+  {
+    const S::Pt q = S::point(ln, par, k, in, base, y);
+    S::template factor<FREE>(ln, par, k, in, base, g, y, q, tab.ghinv, tab.luc, fac);
+    S::template rhs<FREE>(par, k, base, g, tab.luc, y, q, K1);
+  }
   S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K1);
   // the same statement on the six per-phase slots (V) and the five shared slots (double); CC(m, nn) = c_nn/h,
   // or c_nn*gamma on a unit-pivot slot
@@ -584,8 +587,7 @@ PVDER_NOINLINE SplitStepResult rodas4_exact_split(LanesT<true> ln, Split3::Vec y
                                                   Split3::In in, Split3::Consts k, const RodasTab* tab,
                                                   Split3::Gains g, Aux base) {
   SplitStepResult r;
-  const Split3::Pt q0 = Split3::point(ln, cfg->par, k, in, base, y);
-  rodas4_core_split<true, false>(ln, y, *cfg, in_s, in, k, *tab, g, q0, base);
+  rodas4_core_split<true, false>(ln, y, *cfg, in_s, in, k, *tab, g, base);
   r.y = y;
   r.base = base;
   return r;
@@ -697,34 +699,26 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
     Inputs in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);   // changes only when an event fires
     S::In in = S::inputs(ln, kc, in_s);
     aux_exact_sv(par, in_s, r.y.s[4], r.y.s[0], base);
-    // one loop over the integrator steps (micro per half-cycle, normally 1); the point record of the current
-    // state serves the clamp decision and stage 1 alike
-    const int total = cfg.n_sub_per_step * cfg.micro;
-    int m_left = cfg.micro, s = 0;
-    bool clamped = false;
-    for (int it = 0; it < total; ++it) {
-      const S::Pt q0 = S::point(ln, par, kc, in, base, r.y);
+    // (two nested loops and a clamp decision with its own Q sum: merging the loops as in the one-thread kernels, or
+    // sharing one point record between the clamp decision and stage 1, cost 2-2.5 % here -- register pressure)
+    for (int s = 0; s < cfg.n_sub_per_step; ++s) {
       bool m_over;
-      const S::Gains g = S::gains(ln, par, kc, in, r.y, q0, tab.luc, m_over);
-      clamped |= g.any;
-      // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
-      // come from the constant bank (fewer live registers, no spills in the common case)
-      const bool ok = ln.any_warp(g.any) ? rodas4_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, q0, base)
-                                         : rodas4_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, q0, base);
-      const LanesT<true> lx = ln.sub(!ok);
-      if (!ok) {
-        const SplitStepResult res = rodas4_exact_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base);
-        r.y = res.y;
-        base = res.base;
-        r.exact += 1;
+      const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
+      if (g.any) r.windup += 1;
+      for (int m = 0; m < cfg.micro; ++m) {
+        // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
+        // come from the constant bank (fewer live registers, no spills in the common case)
+        const bool ok = ln.any_warp(g.any) ? rodas4_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base)
+                                           : rodas4_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base);
+        const LanesT<true> lx = ln.sub(!ok);
+        if (!ok) {
+          const SplitStepResult res = rodas4_exact_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base);
+          r.y = res.y;
+          base = res.base;
+          r.exact += 1;
+        }
       }
-      if (--m_left != 0) continue;
-      // half-cycle boundary
-      m_left = cfg.micro;
-      if (clamped) r.windup += 1;
-      clamped = false;
       if (traj && run) record_substep_split(ln, traj, traj_ld, s, r.y, r.Vgrid, r.Sinsol);   // not the keep-converged dummy work
-      s += 1;
       r.k += 1;
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);

@@ -274,10 +274,7 @@ static unsigned split_freeze_bits(const pvder_env_config& cfg, const double* yin
   double luc[16];
   Split3::lu_consts(cfg.par, ghinv, luc);
   bool m_over;
-  Aux ax;
-  aux_exact_sv(cfg.par, in_s, y.s[4], y.s[0], ax);
-  const Split3::Pt q = Split3::point(ln, cfg.par, kc, in, ax, y);
-  const Split3::Gains g = Split3::gains(ln, cfg.par, kc, in, y, q, luc, m_over);
+  const Split3::Gains g = Split3::gains(ln, cfg.par, kc, in, y, luc, m_over);
   unsigned bits = 0;
   for (int k = 0; k < 3; ++k) {
     if (g.g0.v[k] == 0.0) bits |= 1u << (4 * k);
