@@ -76,6 +76,7 @@ PVDER_DEV double vg_of_phase(const Inputs& in, int phases, int k) {
 // record can be advanced incrementally (pvder_env_step.cuh: aux_advance).
 struct Aux {
   double sn, cs, Ppv, dPpv, inv_Vdc, E;
+  double PoV;   // Ppv / Vdc: all the DC-link equation needs at a Rodas stage (Ppv, dPpv, 1/Vdc: Jacobian only)
 };
 
 // PV array power (pu) and its slope wrt Vdc from E = exp(kappa*Vdc).
@@ -86,6 +87,13 @@ PVDER_DEV void ppv_from_exp(const Params& par, const Inputs& in, double Vdc, dou
   const bool pos = Pr > 0.0;
   P = pos ? Pr : 0.0;
   dP = pos ? dPr : 0.0;
+}
+
+// Ppv / Vdc = max(Ipv, 0) * pv_scale (Vdc > 0): the array CURRENT, which is what the DC-link equation
+// (Ppv - P_inverter) / (C Vdc) needs -- no multiplication by Vdc followed by one with 1/Vdc.
+PVDER_DEV double ppv_over_v_from_exp(const Params& par, const Inputs& in, double e) {
+  const double Ipv = in.np_iph - par.np_irs * (e - 1.0);
+  return Ipv > 0.0 ? Ipv * par.pv_scale : 0.0;
 }
 
 PVDER_DEV void ppv_eval(const Params& par, const Inputs& in, double Vdc, double& P,

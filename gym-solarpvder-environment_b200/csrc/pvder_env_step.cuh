@@ -75,6 +75,7 @@ PVDER_DEV void aux_exact_sv(const Params& par, const Inputs& in, double dl, doub
   a.E = exp(par.kappa * V);
   a.inv_Vdc = 1.0 / V;
   ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
+  a.PoV = ppv_over_v_from_exp(par, in, a.E);
 }
 
 template <class M>
@@ -91,7 +92,9 @@ PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[
 //   and because every argument is O(h), the error terms are O(h^6) and beyond -- past the method's own
 //   order, so they do not change its convergence.  Outside the range (PLL pull-in right after reset) the
 //   step is redone by the EXACT instantiation, kept out of line so the hot loop stays small.
-template <bool EXACT>
+// FULL = false (Rodas stages 2..6): only what the right-hand side reads -- sin, cos, E and Ppv/Vdc.  FULL = true (the
+// state the step ends in, base point of the next step's Jacobian): also 1/Vdc, Ppv and its slope.
+template <bool EXACT, bool FULL = true>
 PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0, double dl,
                               double V, Aux& a, bool& out_of_range) {
   if (EXACT) {
@@ -116,18 +119,21 @@ PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b,
     pe = fma(pe, x, 0.5);
     pe = fma(pe, x, 1.0);
     a.E = fma(b.E * pe, x, b.E);                               // E0 * exp(x), exp to x^5/120
-    double r = b.inv_Vdc;
-    r = fma(r, fma(-V, r, 1.0), r);
-    r = fma(r, fma(-V, r, 1.0), r);
-    a.inv_Vdc = r;
-    ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
+    a.PoV = ppv_over_v_from_exp(par, in, a.E);
+    if (FULL) {
+      double r = b.inv_Vdc;
+      r = fma(r, fma(-V, r, 1.0), r);
+      r = fma(r, fma(-V, r, 1.0), r);
+      a.inv_Vdc = r;
+      ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
+    }
   }
 }
 
-template <class M, bool EXACT>
+template <class M, bool EXACT, bool FULL = true>
 PVDER_DEV void aux_advance(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0,
                            const double (&Y)[M::NS], Aux& a, bool& out_of_range) {
-  aux_advance_sv<EXACT>(par, in, b, dl0, V0, Y[M::IDX_DL], Y[M::IDX_VDC], a, out_of_range);
+  aux_advance_sv<EXACT, FULL>(par, in, b, dl0, V0, Y[M::IDX_DL], Y[M::IDX_VDC], a, out_of_range);
 }
 
 // Effective gains of the freezable rows (bit order of freeze_bits): the parameter, or 0 while the row is
@@ -166,6 +172,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   bool oor = false;
   const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
   ppv_from_exp(par, in, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
+  base.PoV = ppv_over_v_from_exp(par, in, base.E);
   typename M::LU lu;
   M::factor(y, par, in, base, gn, tab.ghinv, tab.luc, lu);
   double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], Y[NS];
@@ -176,7 +183,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   // stage 2
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a21, K1[i], y[i]);
-  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs(Y, par, in, ax, gn, K2);
 #pragma unroll
   for (int i = 0; i < NS; ++i) K2[i] = fma((M::unit_row(i) ? tab.cs21 : tab.c21), K1[i], K2[i]);
@@ -184,7 +191,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   // stage 3
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a32, K2[i], fma(tab.a31, K1[i], y[i]));
-  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs(Y, par, in, ax, gn, K3);
 #pragma unroll
   for (int i = 0; i < NS; ++i) K3[i] = fma((M::unit_row(i) ? tab.cs32 : tab.c32), K2[i], fma((M::unit_row(i) ? tab.cs31 : tab.c31), K1[i], K3[i]));
@@ -192,7 +199,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   // stage 4
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a43, K3[i], fma(tab.a42, K2[i], fma(tab.a41, K1[i], y[i])));
-  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs(Y, par, in, ax, gn, K4);
 #pragma unroll
   for (int i = 0; i < NS; ++i) K4[i] = fma((M::unit_row(i) ? tab.cs43 : tab.c43), K3[i], fma((M::unit_row(i) ? tab.cs42 : tab.c42), K2[i], fma((M::unit_row(i) ? tab.cs41 : tab.c41), K1[i], K4[i])));
@@ -209,7 +216,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   }
   // stage 5: the right-hand side is accumulated onto the pre-loaded sum (rhs_acc folds the addend into each
   // row's last multiply: no separate adds)
-  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs_acc(Y, par, in, ax, gn, K5);
   M::solve(lu, tab.luc, K5);
   // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
@@ -218,7 +225,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
     Y[i] += K5[i];
     C6[i] = fma((M::unit_row(i) ? tab.cs65 : tab.c65), K5[i], C6[i]);
   }
-  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs_acc(Y, par, in, ax, gn, C6);
   M::solve(lu, tab.luc, C6);
 #pragma unroll
@@ -229,7 +236,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
 #pragma unroll
   for (int i = 0; i < NS; ++i)
     Y[i] = fma(tab.a54, K4[i], fma(tab.a53, K3[i], fma(tab.a52, K2[i], fma(tab.a51, K1[i], y[i]))));
-  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
   M::rhs(Y, par, in, ax, gn, K5);
 #pragma unroll
   for (int i = 0; i < NS; ++i)
@@ -238,7 +245,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] += K5[i];
-  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
   double K6[NS];
   M::rhs(Y, par, in, ax, gn, K6);
 #pragma unroll

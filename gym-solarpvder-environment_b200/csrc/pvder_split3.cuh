@@ -279,7 +279,7 @@ struct Split3 {
     const V rfR = vfma(k.rr, q.irefR, -(k.ri * q.irefI)), rfI = vfma(k.ri, q.irefR, k.rr * q.irefI);
     F.p[4] = g2 * ((rfR - Y.p[4]) - iR);
     F.p[5] = g3 * ((rfI - Y.p[5]) - iI);
-    F.s[0] = fma(-0.25 * Y.s[0], q.Ps, ax.Ppv) * (par.inv_C * ax.inv_Vdc);
+    F.s[0] = par.inv_C * fma(-0.25, q.Ps, ax.PoV);      // (Ppv - Vdc Ps / 4) / (C Vdc) = (Ppv / Vdc - Ps / 4) / C
     F.s[1] = g4 * q.dV;
     F.s[2] = -(g5 * q.dQ);
     F.s[3] = luc[LC_KIPLL_H] * q.vd;
@@ -491,6 +491,7 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   bool oor = false;
   const double dl0 = y.s[4], V0 = y.s[0];
   ppv_from_exp(par, in_s, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
+  base.PoV = ppv_over_v_from_exp(par, in_s, base.E);
   Vec K1, K2, K3, K4, Y;
   Aux ax;
   S::Fac fac;
@@ -510,7 +511,7 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
 #define ST(m) Y.m[i] = vfma(tab.a21, K1.m[i], y.m[i]);
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K2);
 #define ST(m) K2.m[i] = vfma(CC(m, 21), K1.m[i], K2.m[i]);
   PVDER_EACH(ST)
@@ -520,7 +521,7 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
 #define ST(m) Y.m[i] = vfma(tab.a32, K2.m[i], vfma(tab.a31, K1.m[i], y.m[i]));
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K3);
 #define ST(m) K3.m[i] = vfma(CC(m, 32), K2.m[i], vfma(CC(m, 31), K1.m[i], K3.m[i]));
   PVDER_EACH(ST)
@@ -530,7 +531,7 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
 #define ST(m) Y.m[i] = vfma(tab.a43, K3.m[i], vfma(tab.a42, K2.m[i], vfma(tab.a41, K1.m[i], y.m[i])));
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K4.m[i] = vfma(CC(m, 43), K3.m[i], vfma(CC(m, 42), K2.m[i], vfma(CC(m, 41), K1.m[i], K4.m[i])));
   PVDER_EACH(ST)
@@ -547,7 +548,7 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   PVDER_EACH(ST)
 #undef ST
   // stage 5
-  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K2.m[i] = K2.m[i] + K4.m[i];
   PVDER_EACH(ST)
@@ -559,7 +560,7 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   K3.m[i] = vfma(CC(m, 65), K2.m[i], K3.m[i]);
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K3.m[i] = K3.m[i] + K4.m[i];
   PVDER_EACH(ST)

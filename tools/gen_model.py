@@ -222,7 +222,8 @@ def emit_rhs_structured(m, acc=False):
             A(f"    const double rfR{k} = fma({rr}, irefR, -({ri} * irefI)), rfI{k} = fma({ri}, irefR, {rr} * irefI);")
             A(mul_or_fma(o + 4, f"g_{4 * k + 2}", f"((rfR{k} - {uR}) - {iR})"))
             A(mul_or_fma(o + 5, f"g_{4 * k + 3}", f"((rfI{k} - {uI}) - {iI})"))
-    A(mul_or_fma(base, f"fma({-0.25 * mult} * y_Vdc, Ps, in_Ppv)", "(p_inv_C * inv_Vdc)"))
+    # (Ppv - Vdc Ps / 4) / (C Vdc) = (Ppv / Vdc - Ps / 4) / C: Vdc cancels in the second term
+    A(mul_or_fma(base, "p_inv_C", f"fma({-0.25 * mult}, Ps, in_PoV)"))      # in_PoV = Ppv / Vdc
     A(mul_or_fma(base + 1, f"g_{4 * P}", "dV"))
     A(mul_or_fma(base + 2, f"(-g_{4 * P + 1})", "dQ") if acc else f"    f[{base + 2}] = -(g_{4 * P + 1} * dQ);")
     A(mul_or_fma(base + 3, f"g_{4 * P + 2}", "vd"))
@@ -243,6 +244,11 @@ def check_structured_rhs(m, lines, acc=False):
         env[str(s_)] = v
         syms[s_] = v
     syms[sp.Symbol("SQ3")] = math.sqrt(3.0)
+    # the emitted code may use inv_Vdc * Vdc = 1
+    inv_sym = m["helpers"][2]
+    vdc_sym = m["y"][6 * m["P"]]
+    env[str(inv_sym)] = syms[inv_sym] = 1.0 / syms[vdc_sym]
+    env["in_PoV"] = syms[m["inp"]["Ppv"]] * syms[inv_sym]
     pre = [rnd.uniform(-1.0, 1.0) if acc else 0.0 for _ in range(m["n"])]
     f = list(pre)
     env["f"] = f
@@ -384,7 +390,7 @@ def generate(P, mult=1):
     A("    const double in_vg = in.vg, in_vgb = in.vgb, in_vgc = in.vgc, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
     A("    (void)in_vgb; (void)in_vgc;")
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
-    A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, inv_Vdc = aux.inv_Vdc;")
+    A("    const double sn = aux.sn, cs = aux.cs, in_PoV = aux.PoV;")
     L.extend(gain_unpack)
     rhs_lines = emit_rhs_structured(m)
     check_structured_rhs(m, rhs_lines)
@@ -400,7 +406,7 @@ def generate(P, mult=1):
     A("    const double in_vg = in.vg, in_vgb = in.vgb, in_vgc = in.vgc, in_Qref = in.Qref, in_Vdcref = in.Vdcref;")
     A("    (void)in_vgb; (void)in_vgc;")
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
-    A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, inv_Vdc = aux.inv_Vdc;")
+    A("    const double sn = aux.sn, cs = aux.cs, in_PoV = aux.PoV;")
     L.extend(gain_unpack)
     acc_lines = emit_rhs_structured(m, acc=True)
     check_structured_rhs(m, acc_lines, acc=True)
