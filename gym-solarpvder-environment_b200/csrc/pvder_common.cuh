@@ -53,6 +53,7 @@ struct Inputs {
   double Vdcref;   // external DC-link reference (pu), changed only by actions
   double np_iph;   // Np * Iph(Sinsol)  (A)
   double vgb, vgc; // phase b / c magnitudes = vg * grid unbalance ratio (explicit three-phase models only)
+  double pvA;      // (np_iph + Np Irs) * pv_scale: array current per pu of Vdc-power at E = 0 (see ppv_over_v_from_exp)
 };
 
 // Inputs in force for one sub-step.  Individually rounded ops: vg feeds the discrete reward.
@@ -64,6 +65,7 @@ PVDER_DEV Inputs make_inputs(const pvder_env_config& cfg, double Vgrid, double Q
   in.np_iph = __dmul_rn(cfg.par.np_iph100, __ddiv_rn(Sinsol, 100.0));
   in.vgb = __dmul_rn(in.vg, cfg.vg_ratio_b);
   in.vgc = __dmul_rn(in.vg, cfg.vg_ratio_c);
+  in.pvA = (in.np_iph + cfg.par.np_irs) * cfg.par.pv_scale;
   return in;
 }
 
@@ -80,20 +82,22 @@ struct Aux {
 };
 
 // PV array power (pu) and its slope wrt Vdc from E = exp(kappa*Vdc).
-PVDER_DEV void ppv_from_exp(const Params& par, const Inputs& in, double Vdc, double e, double& P, double& dP) {
-  const double Ipv = in.np_iph - par.np_irs * (e - 1.0);
-  const double Pr = Ipv * Vdc * par.pv_scale;
-  const double dPr = par.pv_scale * (Ipv - Vdc * (par.np_irs * par.kappa * e));
-  const bool pos = Pr > 0.0;
-  P = pos ? Pr : 0.0;
-  dP = pos ? dPr : 0.0;
+// Ipv = np_iph - Np Irs (E - 1) and Ppv = max(0, Ipv Vdc) pv_scale, written around the array current per pu
+//   PoV = Ppv / Vdc = max(0, A - B E),  A = (np_iph + Np Irs) pv_scale (changes with the insolation events only),
+//   B = Np Irs pv_scale:  one FMA per Rodas stage; Ppv = PoV Vdc and dPpv/dVdc = (A - B E) - Vdc B kappa E are
+//   needed by the Jacobian only (once per step).  The DC-link equation (Ppv - P_inverter) / (C Vdc) reads PoV
+//   directly -- no multiplication by Vdc followed by one with 1/Vdc.
+PVDER_DEV double ppv_over_v_from_exp(const Params& par, const Inputs& in, double e) {
+  const double raw = fma(-(par.np_irs * par.pv_scale), e, in.pvA);
+  return raw > 0.0 ? raw : 0.0;
 }
 
-// Ppv / Vdc = max(Ipv, 0) * pv_scale (Vdc > 0): the array CURRENT, which is what the DC-link equation
-// (Ppv - P_inverter) / (C Vdc) needs -- no multiplication by Vdc followed by one with 1/Vdc.
-PVDER_DEV double ppv_over_v_from_exp(const Params& par, const Inputs& in, double e) {
-  const double Ipv = in.np_iph - par.np_irs * (e - 1.0);
-  return Ipv > 0.0 ? Ipv * par.pv_scale : 0.0;
+PVDER_DEV void ppv_from_exp(const Params& par, const Inputs& in, double Vdc, double e, double& P, double& dP) {
+  const double B = par.np_irs * par.pv_scale;
+  const double raw = fma(-B, e, in.pvA);
+  const bool pos = raw > 0.0;
+  P = pos ? raw * Vdc : 0.0;
+  dP = pos ? fma(-(Vdc * (B * par.kappa)), e, raw) : 0.0;
 }
 
 PVDER_DEV void ppv_eval(const Params& par, const Inputs& in, double Vdc, double& P,

@@ -104,7 +104,8 @@ template <class M>
 static void rhs_one(const pvder_env_config& cfg, const double* yin, const double* inp4, unsigned frz, double* f) {
   double y[M::NS], ff[M::NS];
   for (int i = 0; i < M::NS; ++i) y[i] = yin[i];
-  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
+  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c,
+            (inp4[3] + cfg.par.np_irs) * cfg.par.pv_scale};
   Aux ax;
   aux_exact<M>(cfg.par, in, y, ax);
   // h*gamma = 1: the unit-pivot rows come out unscaled (tests compare with the oracle's f)
@@ -120,7 +121,8 @@ static void wsolve_one(const pvder_env_config& cfg, const double* yin, const dou
                        double* b) {
   double y[M::NS], bb[M::NS];
   for (int i = 0; i < M::NS; ++i) { y[i] = yin[i]; bb[i] = b[i]; }
-  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
+  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c,
+            (inp4[3] + cfg.par.np_irs) * cfg.par.pv_scale};
   typename M::LU lu;
   Aux ax;
   aux_exact<M>(cfg.par, in, y, ax);
@@ -139,7 +141,8 @@ template <class M>
 static unsigned frz_one(const pvder_env_config& cfg, const double* yin, const double* inp4) {
   double y[M::NS];
   for (int i = 0; i < M::NS; ++i) y[i] = yin[i];
-  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
+  Inputs in{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c,
+            (inp4[3] + cfg.par.np_irs) * cfg.par.pv_scale};
   bool m_over;
   return freeze_bits<M>(y, cfg.par, in, m_over);
 }
@@ -221,7 +224,8 @@ static void split_one(const pvder_env_config& cfg, const double* yin, const doub
   const Lanes3 ln;
   Split3::Vec y, b;
   load_split(yin, 1, 0, y);
-  Inputs in_s{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
+  Inputs in_s{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c,
+            (inp4[3] + cfg.par.np_irs) * cfg.par.pv_scale};
   const Split3::Consts kc = Split3::consts(ln);
   const Split3::In in = Split3::inputs(ln, kc, in_s);
   Aux ax;
@@ -268,7 +272,8 @@ static unsigned split_freeze_bits(const pvder_env_config& cfg, const double* yin
   const Lanes3 ln;
   Split3::Vec y;
   load_split(yin, 1, 0, y);
-  Inputs in_s{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c};
+  Inputs in_s{inp4[0], inp4[1], inp4[2], inp4[3], inp4[0] * cfg.vg_ratio_b, inp4[0] * cfg.vg_ratio_c,
+            (inp4[3] + cfg.par.np_irs) * cfg.par.pv_scale};
   const Split3::Consts kc = Split3::consts(ln);
   const Split3::In in = Split3::inputs(ln, kc, in_s);
   double luc[16];
