@@ -350,10 +350,10 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
     const double qs = fma(vI, iR, -(vR * iI));
     Qs = (k == 0) ? qs : Qs + qs;
   }
-  const double Q = (0.5 * M::PMULT) * Qs;
   m_over_out = m_over;
   const double Vdc = y[B], xDC = y[B + 1], xQ = y[B + 2];
-  const double dV = in.Vdcref - Vdc, dQ = in.Qref - Q;
+  const double dV = in.Vdcref - Vdc;
+  const double dQ = fma(-(0.5 * M::PMULT), Qs, in.Qref);      // Qref - Q
   const double irefR = fma(par.Kp_DC, dV, xDC);
   const double irefI = fma(-par.Kp_Q, dQ, xQ);
   const bool i_over = (irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit;
@@ -374,8 +374,8 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
     }
   }
   if (i_over) {
-    if (same_sign(par.Ki_DC * (in.Vdcref - Vdc), xDC)) bits |= 1u << (4 * P);
-    if (same_sign(-par.Ki_Q * (in.Qref - Q), xQ)) bits |= 1u << (4 * P + 1);
+    if (same_sign(par.Ki_DC * dV, xDC)) bits |= 1u << (4 * P);
+    if (same_sign(-par.Ki_Q * dQ, xQ)) bits |= 1u << (4 * P + 1);
   }
   return bits;
 }

@@ -253,7 +253,7 @@ struct Split3 {
     q.Ps = ln.sum3(ps);
     q.vd = (1.0 / 3.0) * ln.sum3(vdk);             // positive-sequence d-axis voltage (A.4)
     q.wex = fma(par.Kp_PLL, q.vd, Y.s[3]);
-    q.wr = (q.wex + par.w0) * par.inv_wb;
+    q.wr = fma(q.wex, par.inv_wb, par.w0 * par.inv_wb);
     q.dV = in.Vdcref - Y.s[0];
     q.dQ = in.Qref - q.Qp;
     q.irefR = fma(par.Kp_DC, q.dV, Y.s[1]);

@@ -192,12 +192,13 @@ def emit_rhs_structured(m, acc=False):
         A("    const double vd = vdk0;")
     else:
         A("    const double vd = (1.0 / 3.0) * (" + " + ".join(f"vdk{k}" for k in range(P)) + ");")
-    A(f"    const double Qp = {0.5 * mult} * Qs;")
     A("    const double wex = fma(p_Kp_PLL, vd, y_xPLL);")
-    A("    const double wr = (wex + p_w0) * p_inv_wb;")
+    A("    // (wex + w0) / wb; the product w0 / wb is launch-invariant")
+    A("    const double wr = fma(wex, p_inv_wb, p_w0 * p_inv_wb);")
     A("    const double hV = 0.5 * y_Vdc;")
     A("    const double dV = in_Vdcref - y_Vdc;")
-    A("    const double dQ = in_Qref - Qp;")
+    A(f"    // Qref - Q, Q = {0.5 * mult} Qs")
+    A(f"    const double dQ = fma({-0.5 * mult}, Qs, in_Qref);")
     A("    const double irefR = fma(p_Kp_DC, dV, y_xDC);")
     A("    const double irefI = fma(-p_Kp_Q, dQ, y_xQ);")
     for k in range(P):
@@ -253,6 +254,8 @@ def check_structured_rhs(m, lines, acc=False):
     f = list(pre)
     env["f"] = f
     for ln in lines:
+        if ln.strip().startswith("//"):
+            continue
         stmt = ln.strip().rstrip(";").replace("const double ", "")
         for part in _split_decl(stmt):
             exec(part, env)
