@@ -180,29 +180,36 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   // stage 1
   M::rhs(y, par, in, base, gn, K1);
   M::solve(lu, tab.luc, K1);
+  // Stages 2-4: the sum of c_ij/h K_j is pre-loaded into K_i (newest term last, so that everything but one FMA
+  // is off the critical path) and the right-hand side is accumulated onto it (rhs_acc: no separate adds).
+#define PVDER_C(nn) (M::unit_row(i) ? tab.cs##nn : tab.c##nn)
   // stage 2
 #pragma unroll
-  for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a21, K1[i], y[i]);
+  for (int i = 0; i < NS; ++i) {
+    Y[i] = fma(tab.a21, K1[i], y[i]);
+    K2[i] = PVDER_C(21) * K1[i];
+  }
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
-  M::rhs(Y, par, in, ax, gn, K2);
-#pragma unroll
-  for (int i = 0; i < NS; ++i) K2[i] = fma((M::unit_row(i) ? tab.cs21 : tab.c21), K1[i], K2[i]);
+  M::rhs_acc(Y, par, in, ax, gn, K2);
   M::solve(lu, tab.luc, K2);
   // stage 3
 #pragma unroll
-  for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a32, K2[i], fma(tab.a31, K1[i], y[i]));
+  for (int i = 0; i < NS; ++i) {
+    Y[i] = fma(tab.a32, K2[i], fma(tab.a31, K1[i], y[i]));
+    K3[i] = fma(PVDER_C(32), K2[i], PVDER_C(31) * K1[i]);
+  }
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
-  M::rhs(Y, par, in, ax, gn, K3);
-#pragma unroll
-  for (int i = 0; i < NS; ++i) K3[i] = fma((M::unit_row(i) ? tab.cs32 : tab.c32), K2[i], fma((M::unit_row(i) ? tab.cs31 : tab.c31), K1[i], K3[i]));
+  M::rhs_acc(Y, par, in, ax, gn, K3);
   M::solve(lu, tab.luc, K3);
   // stage 4
 #pragma unroll
-  for (int i = 0; i < NS; ++i) Y[i] = fma(tab.a43, K3[i], fma(tab.a42, K2[i], fma(tab.a41, K1[i], y[i])));
+  for (int i = 0; i < NS; ++i) {
+    Y[i] = fma(tab.a43, K3[i], fma(tab.a42, K2[i], fma(tab.a41, K1[i], y[i])));
+    K4[i] = fma(PVDER_C(43), K3[i], fma(PVDER_C(42), K2[i], PVDER_C(41) * K1[i]));
+  }
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
-  M::rhs(Y, par, in, ax, gn, K4);
-#pragma unroll
-  for (int i = 0; i < NS; ++i) K4[i] = fma((M::unit_row(i) ? tab.cs43 : tab.c43), K3[i], fma((M::unit_row(i) ? tab.cs42 : tab.c42), K2[i], fma((M::unit_row(i) ? tab.cs41 : tab.c41), K1[i], K4[i])));
+  M::rhs_acc(Y, par, in, ax, gn, K4);
+#undef PVDER_C
   M::solve(lu, tab.luc, K4);
 #if PVDER_FOLD
   // K1..K4 are folded into the stage-5/6 sums as soon as K4 exists (same FMAs, done early): three
