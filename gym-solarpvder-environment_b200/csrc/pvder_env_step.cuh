@@ -78,12 +78,6 @@ PVDER_DEV void aux_exact_sv(const Params& par, const Inputs& in, double dl, doub
   a.PoV = ppv_over_v_from_exp(par, in, a.E);
 }
 
-// PV part of an aux record for new inputs at an unchanged state (an insolation event fired).
-PVDER_DEV void refresh_pv(const Params& par, const Inputs& in, double V, Aux& a) {
-  ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
-  a.PoV = ppv_over_v_from_exp(par, in, a.E);
-}
-
 template <class M>
 PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[M::NS], Aux& a) {
   aux_exact_sv(par, in, y[M::IDX_DL], y[M::IDX_VDC], a);
@@ -177,6 +171,8 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   constexpr int NS = M::NS;
   bool oor = false;
   const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
+  ppv_from_exp(par, in, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
+  base.PoV = ppv_over_v_from_exp(par, in, base.E);
   typename M::LU lu;
   M::factor(y, par, in, base, gn, tab.ghinv, tab.luc, lu);
   double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], Y[NS];
@@ -662,7 +658,6 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
       if (r.k == next_k && j_next < cfg.ev_count) {
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
         in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
-        refresh_pv(par, in, r.y[M::IDX_VDC], base);      // the insolation may have changed
         j_next += 1;
         next_k += cfg.ev_step_k;
       }

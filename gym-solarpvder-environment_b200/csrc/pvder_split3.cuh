@@ -490,6 +490,8 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
   const Params& par = cfg.par;
   bool oor = false;
   const double dl0 = y.s[4], V0 = y.s[0];
+  ppv_from_exp(par, in_s, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
+  base.PoV = ppv_over_v_from_exp(par, in_s, base.E);
   Vec K1, K2, K3, K4, Y;
   Aux ax;
   S::Fac fac;
@@ -723,7 +725,6 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
         apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
         in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
         in = S::inputs(ln, kc, in_s);
-        refresh_pv(par, in_s, r.y.s[0], base);      // the insolation may have changed
         j_next += 1;
         next_k += cfg.ev_step_k;
       }
