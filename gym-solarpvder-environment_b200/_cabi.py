@@ -75,6 +75,8 @@ SIGNATURES = {
     "pvder_generate_events": (C.c_int, [_cfgp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "pvder_sample_actions": (C.c_int, [_u64, _i64, _vp, _i64, _i64, _vp]),
     "pvder_qnet_policy": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, _u64, _i64, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "pvder_qnet_collect": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int, C.c_float, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64,
+                                      _vp, _vp, _vp, _i32, _i64, _i64, _vp]),
     "pvder_stats_reduce": (C.c_int, [_vp, _vp, _i64, C.c_int, _i64, _vp, _vp]),
     "pvder_fp64_peak": (C.c_int, [C.c_int, C.POINTER(_dbl), C.POINTER(_dbl)]),
     "pvder_env_create": (C.c_int, [_cfgp, _i64, _i64, C.POINTER(_vp)]),

@@ -362,13 +362,29 @@ constexpr int QNET_MAX_HIDDEN = 256;
 constexpr int QNET_IN_PAD = 12;    // 11 inputs padded to three float4
 constexpr int QNET_OUT_PAD = 8;    // 5 outputs padded to two float4
 
+// Replay-ring writer fused into the policy kernel (SoA ring [T][n][..], slot = step counter mod T): the transition
+// that the env step just completed goes to the current slot (next obs, reward, done), the new obs and the action
+// chosen for it open the next slot -- one kernel instead of five copy kernels around the policy.
+struct ReplayArgs {
+  float* rb_obs;               // [T][n][11]
+  float* rb_next;              // [T][n][11]
+  int32_t* rb_act;             // [T][n]
+  float* rb_rew;               // [T][n]
+  uint8_t* rb_done;            // [T][n]
+  const double* reward_f64;    // step outputs (one of the two reward pointers)
+  const int32_t* reward_i32;
+  const uint8_t* done;
+  int64_t T;
+  int32_t finish;              // 1: a transition was completed by the preceding env step (0: first call of a rollout)
+};
+
 __global__ void __launch_bounds__(BLOCK) qnet_policy_kernel(const float* __restrict__ obs, const float* __restrict__ w1,
                                                             const float* __restrict__ b1, const float* __restrict__ w2,
                                                             const float* __restrict__ b2, int hidden, float epsilon,
                                                             uint64_t seed, int64_t step_index,
                                                             const int64_t* __restrict__ step_index_dev,
                                                             int32_t* __restrict__ action, float* __restrict__ q_out,
-                                                            int64_t n, int64_t env_offset) {
+                                                            int64_t n, int64_t env_offset, const ReplayArgs rb) {
   if (step_index_dev) step_index += *step_index_dev;   // device-side counter: a captured CUDA graph draws fresh numbers per replay
   extern __shared__ float4 smem4[];
   float* sw1 = reinterpret_cast<float*>(smem4);                   // [hidden][12]
@@ -426,6 +442,23 @@ __global__ void __launch_bounds__(BLOCK) qnet_policy_kernel(const float* __restr
     if (u < epsilon) best = (int)(((uint64_t)r[1] * PVDER_N_ACTIONS) >> 32);
   }
   action[e] = best;
+  if (rb.rb_obs) {
+    // step_index counts completed transitions: the one just finished lives in slot (step_index - 1) mod T,
+    // the one this action starts in slot step_index mod T
+    const int64_t cur = ((step_index % rb.T) + rb.T) % rb.T;
+    if (rb.finish) {
+      const int64_t prev = (cur + rb.T - 1) % rb.T;
+      float* nx = rb.rb_next + (prev * n + e) * PVDER_OBS_DIM;
+#pragma unroll
+      for (int j = 0; j < PVDER_OBS_DIM; ++j) nx[j] = o[j];
+      rb.rb_rew[prev * n + e] = rb.reward_i32 ? (float)rb.reward_i32[e] : (float)rb.reward_f64[e];
+      rb.rb_done[prev * n + e] = rb.done[e];
+    }
+    float* ob = rb.rb_obs + (cur * n + e) * PVDER_OBS_DIM;
+#pragma unroll
+    for (int j = 0; j < PVDER_OBS_DIM; ++j) ob[j] = o[j];
+    rb.rb_act[cur * n + e] = best;
+  }
   if (q_out) {
 #pragma unroll
     for (int k = 0; k < PVDER_N_ACTIONS; ++k) q_out[e * PVDER_N_ACTIONS + k] = q[k];
@@ -674,7 +707,26 @@ int pvder_qnet_policy(const float* obs_f32, const float* w1, const float* b1, co
   const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
   const size_t smem = sizeof(float) * ((size_t)hidden * (QNET_IN_PAD + QNET_OUT_PAD) + ((hidden + 3) & ~3) + BLOCK * PVDER_OBS_DIM);
   qnet_policy_kernel<<<grid, BLOCK, smem, (cudaStream_t)stream>>>(obs_f32, w1, b1, w2, b2, hidden, epsilon, seed, step_index,
-                                                                  step_index_dev, action, q_out, n_envs, env_offset);
+                                                                  step_index_dev, action, q_out, n_envs, env_offset, ReplayArgs{});
+  CK(cudaGetLastError());
+  return PVDER_OK;
+}
+
+int pvder_qnet_collect(const float* obs_f32, const float* w1, const float* b1, const float* w2, const float* b2, int hidden,
+                       float epsilon, uint64_t seed, const int64_t* transitions_dev, int32_t* action, float* rb_obs,
+                       float* rb_next, int32_t* rb_act, float* rb_rew, uint8_t* rb_done, int64_t ring_slots,
+                       const double* reward_f64, const int32_t* reward_i32, const uint8_t* done, int32_t finish,
+                       int64_t n_envs, int64_t env_offset, void* stream) {
+  if (!obs_f32 || !w1 || !b1 || !w2 || !b2 || !action || !transitions_dev || n_envs < 0 || hidden < 1 ||
+      hidden > QNET_MAX_HIDDEN || !rb_obs || !rb_next || !rb_act || !rb_rew || !rb_done || ring_slots < 1)
+    return PVDER_ERR_INVALID;
+  if (finish && (!done || (!reward_f64 && !reward_i32))) return PVDER_ERR_INVALID;
+  if (n_envs == 0) return PVDER_OK;
+  const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
+  const size_t smem = sizeof(float) * ((size_t)hidden * (QNET_IN_PAD + QNET_OUT_PAD) + ((hidden + 3) & ~3) + BLOCK * PVDER_OBS_DIM);
+  const ReplayArgs rb{rb_obs, rb_next, rb_act, rb_rew, rb_done, reward_f64, reward_i32, done, ring_slots, finish};
+  qnet_policy_kernel<<<grid, BLOCK, smem, (cudaStream_t)stream>>>(obs_f32, w1, b1, w2, b2, hidden, epsilon, seed, 0,
+                                                                  transitions_dev, action, nullptr, n_envs, env_offset, rb);
   CK(cudaGetLastError());
   return PVDER_OK;
 }

@@ -7,10 +7,11 @@ step per iteration, replay buffer) with every piece on the same GPU and stream:
 Nothing crosses PCIe or NVLink per step; the whole iteration (policy forward, action selection,
 env step, replay write) can be captured once in a CUDA graph and replayed.
 
-policy="fused" (default for the demo's 11-h-5 ReLU network in fp32): one hand-written kernel
-(``pvder_qnet_policy``: weights in shared memory, one thread per env, Philox epsilon-greedy) turns
-obs into actions; policy="torch": the same network through torch ops (library GEMMs), kept as the
-cross-check and for arbitrary modules.
+policy="fused" (default for the demo's 11-h-5 ReLU network in fp32): one hand-written kernel per
+iteration next to the step kernel (``pvder_qnet_collect``: weights in shared memory, one thread per env,
+Philox epsilon-greedy, and the replay-ring writes of the transition just completed and of the one being
+started); policy="torch": the same network and ring through torch ops (library GEMMs, five copy
+kernels), kept as the cross-check and for arbitrary modules.
 """
 from __future__ import annotations
 
@@ -50,6 +51,7 @@ class DQNRollout:
         self.graph = None
         self.steps_done = 0
         self.seed = int(seed)
+        self._primed = False
         fusable = self._fusable(self.qnet)
         if policy == "auto":
             policy = "fused" if fusable else "torch"
@@ -94,10 +96,36 @@ class DQNRollout:
                 greedy = t.where(u < self.epsilon, rnd, greedy)
             self.actions.copy_(greedy)
 
+    def _collect_fused(self, finish):
+        import ctypes as C
+        from . import _cabi
+
+        venv = self.venv
+        l1, l2 = self.qnet[0], self.qnet[2]
+        p = lambda x: C.c_void_p(x.data_ptr()) if x is not None else None
+        rew_f64 = None if venv.cfg.DISCRETE_REWARD else venv.reward
+        rew_i32 = venv.reward_i if venv.cfg.DISCRETE_REWARD else None
+        _cabi.check(_cabi.load().pvder_qnet_collect(
+            p(venv.obs), p(l1.weight), p(l1.bias), p(l2.weight), p(l2.bias), l1.out_features, self.epsilon,
+            self.seed & 0xFFFFFFFFFFFFFFFF, p(self.slot), p(self.actions), p(self.rb_obs), p(self.rb_next), p(self.rb_act),
+            p(self.rb_rew), p(self.rb_done), self.T, p(rew_f64), p(rew_i32), p(venv.done), 1 if finish else 0,
+            venv.num_envs, venv.env_offset, C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)))
+
     def _iteration(self):
         """One collect step for every env: policy -> step kernel -> replay write."""
         t = self.torch
         venv = self.venv
+        if self.policy == "fused":
+            # the action for the current obs is already in self.actions (prologue / previous iteration):
+            # env step, count the completed transition, then ONE kernel closes its ring slot, evaluates the
+            # policy on the new obs and opens the next slot
+            if not self._primed:
+                self._collect_fused(finish=False)
+                self._primed = True
+            venv.step(self.actions)
+            self.slot += 1
+            self._collect_fused(finish=True)
+            return
         slot = self.slot % self.T
         self.rb_obs.index_copy_(0, slot.view(1), venv.obs.unsqueeze(0))
         self._select_actions(venv.obs)

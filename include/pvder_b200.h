@@ -159,6 +159,17 @@ int pvder_qnet_policy(const float* obs_f32, const float* w1, const float* b1, co
                       int hidden, float epsilon, uint64_t seed, int64_t step_index, const int64_t* step_index_dev,
                       int32_t* action, float* q_out, int64_t n_envs, int64_t env_offset, void* stream);
 
+/* Collect step of the same demo with the replay-buffer writer fused in (SoA ring [ring_slots][n][..]): with
+ * t = *transitions_dev (device counter of completed transitions; the caller increments it after every env
+ * step), the transition the preceding env step completed (finish != 0) is closed in slot (t-1) mod ring_slots
+ * -- rb_next = obs, rb_rew = reward, rb_done = done -- and the new obs plus the action chosen for it open slot
+ * t mod ring_slots (rb_obs, rb_act).  The exploration stream is keyed by (global env, t). */
+int pvder_qnet_collect(const float* obs_f32, const float* w1, const float* b1, const float* w2, const float* b2,
+                       int hidden, float epsilon, uint64_t seed, const int64_t* transitions_dev, int32_t* action,
+                       float* rb_obs, float* rb_next, int32_t* rb_act, float* rb_rew, uint8_t* rb_done,
+                       int64_t ring_slots, const double* reward_f64, const int32_t* reward_i32, const uint8_t* done,
+                       int32_t finish, int64_t n_envs, int64_t env_offset, void* stream);
+
 /* Episode statistics (env_utilities.py:12-46) reduced over envs into 16 device doubles:
  * [0] sum return, [1] sum steps, [2] n done, [3] n failed, [4..8] action histogram,
  * [9] windup sub-steps, [10] n_envs, [11] sub-steps redone with library transcendentals. */

@@ -589,6 +589,16 @@ def test_fused_qnet_policy_kernel(cuda):
         res.append((v.sd.clone(), ro.rb_act.clone(), ro.rb_rew.clone()))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
     assert not torch.equal(res[0][1][0], res[0][1][1])
+    # fused replay writer (pvder_qnet_collect): 7 transitions completed, slot 7 opened; the ring is consistent --
+    # next-obs of transition t is the obs of transition t + 1, actions are what the env stepped with, rewards are
+    # the env's (discrete) rewards
+    assert int(ro.slot) == 7
+    for tr in range(6):
+        assert torch.equal(ro.rb_next[tr], ro.rb_obs[tr + 1])
+    assert torch.equal(ro.rb_act[7 % 8], ro.actions)
+    assert torch.equal(ro.rb_next[6], v.obs) and torch.equal(ro.rb_rew[6], v.reward_i.to(torch.float32))
+    assert torch.equal(ro.rb_done[6], v.done.view(torch.bool))
+    assert set(ro.rb_rew[:7].unique().tolist()) <= {1.0, -1.0, -5.0}
 
 
 def test_config3_subset_vs_tight_oracle(cuda):
