@@ -159,6 +159,16 @@ PVDER_DEV void make_gains(const Params& par, const RodasTab& tab, unsigned frz, 
   }
 }
 
+#ifndef PVDER_LAZY_GAINS
+#define PVDER_LAZY_GAINS 0   // 1: re-derive the effective gains from the clamp bits at every stage (selects on the idle ALU pipe)
+#endif                       //    instead of holding 9 doubles across the whole step (register-pressure experiment)
+PVDER_DEV unsigned opaque_bits(unsigned v) {
+#ifdef __CUDACC__
+  asm volatile("" : "+r"(v));     // the compiler must treat every call's result as a new value: no CSE, no hoisting
+#endif
+  return v;
+}
+
 // One half-cycle Rodas4 step.  `base` is the Aux record at y on entry and at the new y on exit.
 // Returns false (y, base untouched) when EXACT == false and a stage left the incremental range.
 // FREE: no clamp is active (frz == 0 in every lane that takes this instantiation): the effective gains are
@@ -168,6 +178,13 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
                            unsigned frz, Aux& base) {
   double gn[M::NGAIN];
   make_gains<M>(par, tab, FREE ? 0u : frz, gn);
+#if PVDER_LAZY_GAINS
+#define PVDER_WITH_GAINS(stmt) { double gs_[M::NGAIN]; make_gains<M>(par, tab, FREE ? 0u : opaque_bits(frz), gs_); stmt; }
+#define PVDER_GN gs_
+#else
+#define PVDER_WITH_GAINS(stmt) { stmt; }
+#define PVDER_GN gn
+#endif
   constexpr int NS = M::NS;
   bool oor = false;
   const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
@@ -178,7 +195,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], Y[NS];
   Aux ax;
   // stage 1
-  M::rhs(y, par, in, base, gn, K1);
+  PVDER_WITH_GAINS(M::rhs(y, par, in, base, PVDER_GN, K1))
   M::solve(lu, tab.luc, K1);
   // Stages 2-4: the sum of c_ij/h K_j is pre-loaded into K_i (newest term last, so that everything but one FMA
   // is off the critical path) and the right-hand side is accumulated onto it (rhs_acc: no separate adds).
@@ -190,7 +207,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
     K2[i] = PVDER_C(21) * K1[i];
   }
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
-  M::rhs_acc(Y, par, in, ax, gn, K2);
+  PVDER_WITH_GAINS(M::rhs_acc(Y, par, in, ax, PVDER_GN, K2))
   M::solve(lu, tab.luc, K2);
   // stage 3
 #pragma unroll
@@ -199,7 +216,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
     K3[i] = fma(PVDER_C(32), K2[i], PVDER_C(31) * K1[i]);
   }
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
-  M::rhs_acc(Y, par, in, ax, gn, K3);
+  PVDER_WITH_GAINS(M::rhs_acc(Y, par, in, ax, PVDER_GN, K3))
   M::solve(lu, tab.luc, K3);
   // stage 4
 #pragma unroll
@@ -208,7 +225,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
     K4[i] = fma(PVDER_C(43), K3[i], fma(PVDER_C(42), K2[i], PVDER_C(41) * K1[i]));
   }
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
-  M::rhs_acc(Y, par, in, ax, gn, K4);
+  PVDER_WITH_GAINS(M::rhs_acc(Y, par, in, ax, PVDER_GN, K4))
 #undef PVDER_C
   M::solve(lu, tab.luc, K4);
 #if PVDER_FOLD
@@ -224,7 +241,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   // stage 5: the right-hand side is accumulated onto the pre-loaded sum (rhs_acc folds the addend into each
   // row's last multiply: no separate adds)
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
-  M::rhs_acc(Y, par, in, ax, gn, K5);
+  PVDER_WITH_GAINS(M::rhs_acc(Y, par, in, ax, PVDER_GN, K5))
   M::solve(lu, tab.luc, K5);
   // stage 6 (Y6 = Y5 + K5; y+ = Y6 + K6: stiffly accurate)
 #pragma unroll
@@ -233,7 +250,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
     C6[i] = fma((M::unit_row(i) ? tab.cs65 : tab.c65), K5[i], C6[i]);
   }
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
-  M::rhs_acc(Y, par, in, ax, gn, C6);
+  PVDER_WITH_GAINS(M::rhs_acc(Y, par, in, ax, PVDER_GN, C6))
   M::solve(lu, tab.luc, C6);
 #pragma unroll
   for (int i = 0; i < NS; ++i) Y[i] += C6[i];
@@ -269,6 +286,8 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   base = ax;
   return true;
 }
+#undef PVDER_WITH_GAINS
+#undef PVDER_GN
 
 // Out-of-line slow path: library transcendentals at every stage.
 template <class M>
