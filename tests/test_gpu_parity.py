@@ -687,3 +687,40 @@ def test_step_after_done_is_a_no_op_inside_a_running_warp(cuda, mode):
     running = torch.tensor([i for i in range(n) if i % 3], device=cuda)
     assert bool((g.steps[running] == 4).all()) and bool(d1[running].all())
     assert float(traj[-1, :g.ns, running].sub(g.sd[:g.ns, running]).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("model_type,mode", [("model_1", "auto"), ("model_2", "split")])
+def test_host_handle_api_chunked_pipeline(cuda, model_type, mode):
+    """Large batch through pvder_env_step_host: the call is cut into quarter-wave chunks on two compute streams with the
+    copies overlapped; every env must come out bit-identical to the single-launch device API (chunk boundaries, the
+    remainder chunk, env offsets of the RNG keys), over several steps incl. obs64."""
+    import ctypes as C
+    import gym_pvder_b200 as G
+    from gym_pvder_b200 import _cabi
+
+    n = 300_001
+    cfg = G.EnvConfig(model_type=model_type, events_spec=H.SAG_SPEC, seed=5, balanced_three_phase=mode,
+                      DISCRETE_REWARD=False, n_sim_time_steps_per_env_step=4, max_sim_time=2.0)
+    lib = _cabi.load()
+    h = C.c_void_p()
+    _cabi.check(lib.pvder_env_create(C.byref(cfg.c), n, 7, C.byref(h)))
+    obs = np.zeros((n, 11), np.float32)
+    obs64 = np.zeros((n, 11), np.float64)
+    rew = np.zeros(n)
+    done = np.zeros(n, np.uint8)
+    _cabi.check(lib.pvder_env_reset_host(h, obs.ctypes.data, None))
+    g = _venv(cuda, n, env_offset=7, config=cfg)
+    g.reset()
+    for s in range(3):
+        a = twin.sample_actions_twin(5, s, n, 7)
+        _cabi.check(lib.pvder_env_step_host(h, a.ctypes.data, obs.ctypes.data, obs64.ctypes.data, rew.ctypes.data,
+                                            done.ctypes.data))
+        o2, r2, d2, _ = g.step(a)
+        np.testing.assert_array_equal(o2.cpu().numpy(), obs)
+        np.testing.assert_array_equal(g.obs64.cpu().numpy(), obs64)
+        np.testing.assert_array_equal(r2.cpu().numpy(), rew)
+        np.testing.assert_array_equal(d2.cpu().numpy().astype(np.uint8), done)
+    sd = np.zeros((_cabi.sd_fields(cfg.n_state), n))
+    _cabi.check(lib.pvder_env_state_host(h, sd.ctypes.data, None))
+    np.testing.assert_array_equal(sd, g.sd[:, :n].cpu().numpy())
+    _cabi.check(lib.pvder_env_destroy(h))
