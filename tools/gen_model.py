@@ -29,7 +29,8 @@ import sympy as sp
 # explicit inverse of the dense core (currents, Vdc, delta) instead of its LU: same flops per solve,
 # but a 4x4 mat-vec has a 3-deep dependency chain where the triangular solves have ~16.  Measured
 # on B200: 4 % SLOWER (register pressure), hence off by default.  Only for cores of <= 4 unknowns.
-CORE_INVERSE = os.environ.get("PVDER_GEN_CORE_INVERSE", "0") == "1"
+CORE_INVERSE = os.environ.get("PVDER_GEN_CORE_INVERSE", "0") != "0"   # "1": the whole core (<= 4 unknowns); "2"/"3": its last 2/3 pivots
+CORE_N = int(os.environ.get("PVDER_GEN_CORE_INVERSE", "0"))
 CONST_PIVOTS = os.environ.get("PVDER_GEN_CONST_PIVOTS", "off")   # off | reg | bank (measured slower)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
@@ -441,7 +442,7 @@ def generate(P, mult=1):
                     ops.append(("new", r, c, k))
     members = sorted(pat)
     nc = 2 * P + 2
-    core = order[-nc:] if (CORE_INVERSE and nc <= 4) else []
+    core = (order[-nc:] if CORE_N == 1 else order[-CORE_N:]) if (CORE_INVERSE and nc <= 4) else []
     coreset = set(core)
     # Launch-constant pivots: w_kk is still its initial value ghinv - J_kk when row k is pivoted and
     # J_kk depends on parameters only.  Their reciprocals come from a host-filled table (and a
