@@ -7,24 +7,35 @@
 //   compute_outputs<- PVDER.state :531-542, PVDER.reward_calc :231-301
 //   draw_event     <- generate_simulation_events :400-411 (pvder create_random_events, A.8)
 #pragma once
+#include <cstring>
 #include "pvder_common.cuh"
 
 namespace pvder {
 
-// ---- Rodas4 (Hairer & Wanner, Solving ODEs II, sec. IV.10) in the form
-//        (I/(h g) - J) K_i = f(Y_i) + sum_j (c_ij/h) K_j ,  Y_i = y + sum_j a_ij K_j ,  y+ = Y_6 + K_6
-// L-stable, stiffly accurate, order 4, one LU per step.  All 8 order conditions were checked
-// numerically for these digits (tools/integrator_study.py).
-#ifndef PVDER_FOLD
-#define PVDER_FOLD 1   // fold K1..K4 into the stage-5/6 sums early: same FMAs, 2 fewer live vectors (B200: 3.11 -> 3.04 ms)
+// ---- Half-cycle integrator: a Rosenbrock method in the transformed form (Hairer & Wanner, Solving ODEs II, IV.7)
+//        (I/(h g) - J) K_i = f(Y_i) + sum_j (c_ij/h) K_j ,  Y_i = y + sum_j a_ij K_j ,  y+ = y + sum_i m_i K_i
+// one LU per step, no Newton loop.  Two schemes are compiled from this file (PVDER_SCHEME):
+//   4 (default)  ROS4-L: the L-stable 4-stage order-4 method of Hairer & Wanner's ROS4 (gamma = 0.57282; stage 4
+//                re-uses f(Y_3): 3 right-hand sides + 4 solves per step).  On this model it is as accurate as Rodas4
+//                at the half-cycle step (tools/integrator_study.py: every state within 15 % of Rodas4's error against the
+//                tight oracle, incl. the PLL states) for 60 % of the arithmetic.
+//   6            Rodas4 (IV.10): L-stable, stiffly accurate, 6 stages, y+ = Y_6 + K_6.  The round-1 scheme, kept as the
+//                cross-check build.
+// The order conditions of both tableaux were checked numerically for these digits (tools/integrator_study.py).
+#ifndef PVDER_SCHEME
+#define PVDER_SCHEME 4
 #endif
-#ifndef PVDER_EXACT_BY_COPY
-#define PVDER_EXACT_BY_COPY 0   // 1: slow-path call on copies (experiment: keeps y/base out of local memory)
+#ifndef PVDER_FOLD
+#define PVDER_FOLD 1   // Rodas4: fold K1..K4 into the stage-5/6 sums early: same FMAs, 2 fewer live vectors (B200: 3.11 -> 3.04 ms)
 #endif
 #ifndef PVDER_FREE_PATH
-#define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the Rodas4 core, chosen per warp (experiment)
+#define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the stepper core, chosen per warp (experiment)
 #endif
+#if PVDER_SCHEME == 4
+constexpr double RG = 0.57282;
+#else
 constexpr double RG = 0.25;
+#endif
 struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant bank
   double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54;
   double c21, c31, c32, c41, c42, c43, c51, c52, c53, c54, c61, c62, c63, c64, c65;
@@ -35,12 +46,27 @@ struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant 
   double cs21, cs31, cs32, cs41, cs42, cs43, cs51, cs52, cs53, cs54, cs61, cs62, cs63, cs64, cs65;   // c_ij * gamma
   double kx, kdc, kq, kpll;   // Ki_GCC, Ki_DC, Ki_Q, Ki_PLL times h*gamma
   double du_free, du_frz;     // reciprocal pivot of a free / clamped u row: 1/(1/(h g) + wp), h g
+  // ROS4-L only: weights of y+ = y + sum m_i K_i, and d4j = (c4j - c3j)/h (stage 4 re-uses stage 3's right-hand side:
+  // b_4 = b_3 + d41 K1 + d42 K2 + c43/h K3); ds4j = the same times h*gamma for the unit-pivot rows
+  double m1, m2, m3, m4;
+  double d41, d42, ds41, ds42;
 };
 
 template <class M>
 inline RodasTab make_rodas_tab(const Params& par, double hinv) {
   static_assert(M::N_LUC <= 16, "luc table too small");
   RodasTab t;
+  std::memset(&t, 0, sizeof(t));
+#if PVDER_SCHEME == 4
+  t.a21 = 0.2000000000000000e+01;
+  t.a31 = 0.1867943637803922e+01; t.a32 = 0.2344449711399156e+00;
+  const double c41 = -0.2137148994382534e+01, c42 = -0.3214669691237626e+00, c31 = 0.2580708087951457e+01, c32 = 0.6515950076447975e+00;
+  t.c21 = -0.7137615036412310e+01 * hinv;
+  t.c31 = c31 * hinv; t.c32 = c32 * hinv;
+  t.c41 = c41 * hinv; t.c42 = c42 * hinv; t.c43 = -0.6949742501781779e+00 * hinv;
+  t.d41 = (c41 - c31) * hinv; t.d42 = (c42 - c32) * hinv;
+  t.m1 = 0.2255570073418735e+01; t.m2 = 0.2870493262186792e+00; t.m3 = 0.4353179431840180e+00; t.m4 = 0.1093502252409163e+01;
+#else
   t.a21 = 0.1544000000000000e+01;
   t.a31 = 0.9466785280815826e+00; t.a32 = 0.2557011698983284e+00;
   t.a41 = 0.3314825187068521e+01; t.a42 = 0.2896124015972201e+01; t.a43 = 0.9986419139977817e+00;
@@ -53,6 +79,7 @@ inline RodasTab make_rodas_tab(const Params& par, double hinv) {
   t.c54 = 0.1170890893206160e+02 * hinv;
   t.c61 = 0.8083246795921522e+01 * hinv; t.c62 = -0.7981132988064893e+01 * hinv; t.c63 = -0.3152159432874371e+02 * hinv;
   t.c64 = 0.1631930543123136e+02 * hinv; t.c65 = -0.6058818238834054e+01 * hinv;
+#endif
   t.ghinv = hinv * (1.0 / RG);
   const double hg = 1.0 / t.ghinv;
   t.cs21 = t.c21 * hg;
@@ -60,6 +87,7 @@ inline RodasTab make_rodas_tab(const Params& par, double hinv) {
   t.cs41 = t.c41 * hg; t.cs42 = t.c42 * hg; t.cs43 = t.c43 * hg;
   t.cs51 = t.c51 * hg; t.cs52 = t.c52 * hg; t.cs53 = t.c53 * hg; t.cs54 = t.c54 * hg;
   t.cs61 = t.c61 * hg; t.cs62 = t.c62 * hg; t.cs63 = t.c63 * hg; t.cs64 = t.c64 * hg; t.cs65 = t.c65 * hg;
+  t.ds41 = t.d41 * hg; t.ds42 = t.d42 * hg;
   t.kx = par.Ki_GCC * hg; t.kdc = par.Ki_DC * hg; t.kq = par.Ki_Q * hg; t.kpll = par.Ki_PLL * hg;
   t.du_free = 1.0 / (t.ghinv + par.wp);
   t.du_frz = hg;
@@ -169,12 +197,12 @@ PVDER_DEV unsigned opaque_bits(unsigned v) {
   return v;
 }
 
-// One half-cycle Rodas4 step.  `base` is the Aux record at y on entry and at the new y on exit.
+// One half-cycle step of the scheme PVDER_SCHEME selects.  `base` is the Aux record at y on entry and at the new y on exit.
 // Returns false (y, base untouched) when EXACT == false and a stage left the incremental range.
 // FREE: no clamp is active (frz == 0 in every lane that takes this instantiation): the effective gains are
 // the parameters themselves, read from the constant bank instead of occupying registers.
 template <class M, bool EXACT, bool FREE = false>
-PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
+PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
                            unsigned frz, Aux& base) {
   double gn[M::NGAIN];
   make_gains<M>(par, tab, FREE ? 0u : frz, gn);
@@ -192,11 +220,54 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   base.PoV = ppv_over_v_from_exp(par, in, base.E);
   typename M::LU lu;
   M::factor(y, par, in, base, gn, tab.ghinv, tab.luc, lu);
-  double K1[NS], K2[NS], K3[NS], K4[NS], K5[NS], Y[NS];
+  double K1[NS], K2[NS], K3[NS], K4[NS], Y[NS];
   Aux ax;
   // stage 1
   PVDER_WITH_GAINS(M::rhs(y, par, in, base, PVDER_GN, K1))
   M::solve(lu, tab.luc, K1);
+#if PVDER_SCHEME == 4
+  // ROS4-L.  The sum of c_ij/h K_j is pre-loaded into K_i (newest term last, so that everything but one FMA is off
+  // the critical path) and the right-hand side is accumulated onto it (rhs_acc: no separate adds).
+#define PVDER_C(nn) (M::unit_row(i) ? tab.cs##nn : tab.c##nn)
+#define PVDER_D(nn) (M::unit_row(i) ? tab.ds##nn : tab.d##nn)
+  // stage 2
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    Y[i] = fma(tab.a21, K1[i], y[i]);
+    K2[i] = PVDER_C(21) * K1[i];
+  }
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
+  PVDER_WITH_GAINS(M::rhs_acc(Y, par, in, ax, PVDER_GN, K2))
+  M::solve(lu, tab.luc, K2);
+  // stage 3; K1 and K2 are folded into everything that still needs them (Y3, the pre-loaded sums of stages 3 and 4,
+  // the new state) as soon as K2 exists
+  double yn[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    Y[i] = fma(tab.a32, K2[i], fma(tab.a31, K1[i], y[i]));
+    K3[i] = fma(PVDER_C(32), K2[i], PVDER_C(31) * K1[i]);
+    K4[i] = fma(PVDER_D(42), K2[i], PVDER_D(41) * K1[i]);
+    yn[i] = fma(tab.m2, K2[i], fma(tab.m1, K1[i], y[i]));
+  }
+  aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
+  PVDER_WITH_GAINS(M::rhs_acc(Y, par, in, ax, PVDER_GN, K3))
+  // stage 4 re-uses f(Y3): b_4 = b_3 + sum_j (c_4j - c_3j)/h K_j + c_43/h K_3
+#pragma unroll
+  for (int i = 0; i < NS; ++i) K4[i] += K3[i];
+  M::solve(lu, tab.luc, K3);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    K4[i] = fma(PVDER_C(43), K3[i], K4[i]);
+    yn[i] = fma(tab.m3, K3[i], yn[i]);
+  }
+#undef PVDER_C
+#undef PVDER_D
+  M::solve(lu, tab.luc, K4);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) Y[i] = fma(tab.m4, K4[i], yn[i]);
+  aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
+#else   // Rodas4
+  double K5[NS];
   // Stages 2-4: the sum of c_ij/h K_j is pre-loaded into K_i (newest term last, so that everything but one FMA
   // is off the critical path) and the right-hand side is accumulated onto it (rhs_acc: no separate adds).
 #define PVDER_C(nn) (M::unit_row(i) ? tab.cs##nn : tab.c##nn)
@@ -280,6 +351,7 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
   for (int i = 0; i < NS; ++i) Y[i] += K6[i];
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
 #endif
+#endif
   if (oor) return false;
 #pragma unroll
   for (int i = 0; i < NS; ++i) y[i] = Y[i];
@@ -289,15 +361,22 @@ PVDER_DEV bool rodas4_core(double (&y)[M::NS], const Params& par, const Inputs& 
 #undef PVDER_WITH_GAINS
 #undef PVDER_GN
 
-// Out-of-line slow path: library transcendentals at every stage.
+// Out-of-line slow path: library transcendentals at every stage.  Everything travels by value, so that nothing in
+// the caller's hot loop has its address taken (that would pin the state and the aux record to local memory: 18 doubles
+// stored and re-loaded per sub-step).
 template <class M>
-PVDER_NOINLINE void rodas4_exact(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
-                                 unsigned frz, Aux& base) {
-  rodas4_core<M, true>(y, par, in, tab, frz, base);
+struct StepState {
+  double y[M::NS];
+  Aux base;
+};
+template <class M>
+PVDER_NOINLINE StepState<M> ros_exact(StepState<M> s, const Params* par, Inputs in, const RodasTab* tab, unsigned frz) {
+  ros_core<M, true>(s.y, *par, in, *tab, frz, s.base);
+  return s;
 }
 
 template <class M>
-PVDER_DEV bool rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
+PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
                            unsigned frz, Aux& base) {
   // One instantiation serves clamped and unclamped envs (the clamp enters through the per-row
   // effective gains): with a random policy two thirds of the warps hold a clamped lane late in an
@@ -309,25 +388,20 @@ PVDER_DEV bool rodas4_step(double (&y)[M::NS], const Params& par, const Inputs& 
 #else
   const bool any_frz = frz != 0u;
 #endif
-  const bool ok = any_frz ? rodas4_core<M, false, false>(y, par, in, tab, frz, base)
-                          : rodas4_core<M, false, true>(y, par, in, tab, frz, base);
+  const bool ok = any_frz ? ros_core<M, false, false>(y, par, in, tab, frz, base)
+                          : ros_core<M, false, true>(y, par, in, tab, frz, base);
 #else
-  const bool ok = rodas4_core<M, false>(y, par, in, tab, frz, base);
+  const bool ok = ros_core<M, false>(y, par, in, tab, frz, base);
 #endif
   if (!ok) {
-#if PVDER_EXACT_BY_COPY
-    // the out-of-line call works on copies, so y and base never have their address taken in the hot loop
-    double yc[M::NS];
-    Aux bc = base;
+    StepState<M> s;
 #pragma unroll
-    for (int i = 0; i < M::NS; ++i) yc[i] = y[i];
-    rodas4_exact<M>(yc, par, in, tab, frz, bc);
+    for (int i = 0; i < M::NS; ++i) s.y[i] = y[i];
+    s.base = base;
+    s = ros_exact<M>(s, &par, in, &tab, frz);
 #pragma unroll
-    for (int i = 0; i < M::NS; ++i) y[i] = yc[i];
-    base = bc;
-#else
-    rodas4_exact<M>(y, par, in, tab, frz, base);
-#endif
+    for (int i = 0; i < M::NS; ++i) y[i] = s.y[i];
+    base = s.base;
     return false;
   }
   return true;
@@ -665,7 +739,7 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
       // the duty-cycle clamp acts on Re/Im parts per phase and would break the symmetry the
       // balanced representation relies on: report instead of integrating something else
       if (M::BALANCED3 && m_over) r.status = PVDER_STATUS_UNBALANCED;
-      if (!rodas4_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
+      if (!ros_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
       if (--m_left != 0) continue;
       // half-cycle boundary
       m_left = cfg.micro;

@@ -477,12 +477,12 @@ struct Split3 {
 };
 
 // ---------------------------------------------------------------------------------------------
-// Rodas4 half-cycle step on the lane-split state (same scheme, coefficients and incremental
-// side-inputs as rodas4_core).  K1..K4 are folded into the stage-5/6 sums as soon as K4 exists, so
+// Half-cycle step on the lane-split state (same scheme -- PVDER_SCHEME --, coefficients and incremental
+// side-inputs as ros_core).  Stage vectors are folded into the sums that need them as soon as they exist, so
 // at most five lane-vectors are live.
 // ---------------------------------------------------------------------------------------------
 template <bool EXACT, bool FREE, class LN>
-PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_config& cfg, const Inputs& in_s,
+PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_config& cfg, const Inputs& in_s,
                                  const Split3::In& in, const Split3::Consts& k, const RodasTab& tab,
                                  const Split3::Gains& g, Aux& base) {
   using S = Split3;
@@ -507,6 +507,50 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
 #define PVDER_EACH(ST)                                        \
   _Pragma("unroll") for (int i = 0; i < 6; ++i) { ST(p) }     \
   _Pragma("unroll") for (int i = 0; i < 5; ++i) { ST(s) }
+#if PVDER_SCHEME == 4
+  // ROS4-L (see ros_core): 3 right-hand sides, 4 solves; stage 4 re-uses stage 3's right-hand side
+#define DD(m, nn) (S::unit_##m(i) ? tab.ds##nn : tab.d##nn)
+  // stage 2
+#define ST(m) Y.m[i] = vfma(tab.a21, K1.m[i], y.m[i]);
+  PVDER_EACH(ST)
+#undef ST
+  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K2);
+#define ST(m) K2.m[i] = vfma(CC(m, 21), K1.m[i], K2.m[i]);
+  PVDER_EACH(ST)
+#undef ST
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K2);
+  // stage 3: K1, K2 are folded into Y3, the pre-loaded sums of stages 3 (-> K3) and 4 (-> K4) and the new state
+  // (-> K1) as soon as K2 exists
+#define ST(m)                                                                \
+  {                                                                          \
+    const auto k1 = K1.m[i], k2 = K2.m[i];                                   \
+    Y.m[i] = vfma(tab.a32, k2, vfma(tab.a31, k1, y.m[i]));                   \
+    K3.m[i] = vfma(CC(m, 32), k2, CC(m, 31) * k1);                           \
+    K4.m[i] = vfma(DD(m, 42), k2, DD(m, 41) * k1);                           \
+    K1.m[i] = vfma(tab.m2, k2, vfma(tab.m1, k1, y.m[i]));                    \
+  }
+  PVDER_EACH(ST)
+#undef ST
+  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K2);   // K2 = f(Y3)
+#define ST(m)                          \
+  K3.m[i] = K3.m[i] + K2.m[i];         \
+  K4.m[i] = K4.m[i] + K3.m[i];
+  PVDER_EACH(ST)
+#undef ST
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K3);
+#define ST(m)                                   \
+  K4.m[i] = vfma(CC(m, 43), K3.m[i], K4.m[i]);  \
+  K1.m[i] = vfma(tab.m3, K3.m[i], K1.m[i]);
+  PVDER_EACH(ST)
+#undef ST
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K4);
+#define ST(m) Y.m[i] = vfma(tab.m4, K4.m[i], K1.m[i]);
+  PVDER_EACH(ST)
+#undef ST
+#undef DD
+#else   // Rodas4
   // stage 2
 #define ST(m) Y.m[i] = vfma(tab.a21, K1.m[i], y.m[i]);
   PVDER_EACH(ST)
@@ -569,6 +613,7 @@ PVDER_DEV bool rodas4_core_split(const LN& ln, Split3::Vec& y, const pvder_env_c
 #define ST(m) Y.m[i] = Y.m[i] + K3.m[i];
   PVDER_EACH(ST)
 #undef ST
+#endif
 #undef PVDER_EACH
 #undef CC
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
@@ -584,11 +629,11 @@ struct SplitStepResult {
   Split3::Vec y;
   Aux base;
 };
-PVDER_NOINLINE SplitStepResult rodas4_exact_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
+PVDER_NOINLINE SplitStepResult ros_exact_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
                                                   Split3::In in, Split3::Consts k, const RodasTab* tab,
                                                   Split3::Gains g, Aux base) {
   SplitStepResult r;
-  rodas4_core_split<true, false>(ln, y, *cfg, in_s, in, k, *tab, g, base);
+  ros_core_split<true, false>(ln, y, *cfg, in_s, in, k, *tab, g, base);
   r.y = y;
   r.base = base;
   return r;
@@ -709,11 +754,11 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
       for (int m = 0; m < cfg.micro; ++m) {
         // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
         // come from the constant bank (fewer live registers, no spills in the common case)
-        const bool ok = ln.any_warp(g.any) ? rodas4_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base)
-                                           : rodas4_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base);
+        const bool ok = ln.any_warp(g.any) ? ros_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base)
+                                           : ros_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base);
         const LanesT<true> lx = ln.sub(!ok);
         if (!ok) {
-          const SplitStepResult res = rodas4_exact_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base);
+          const SplitStepResult res = ros_exact_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base);
           r.y = res.y;
           base = res.base;
           r.exact += 1;
