@@ -120,8 +120,8 @@ PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[
 //   and because every argument is O(h), the error terms are O(h^6) and beyond -- past the method's own
 //   order, so they do not change its convergence.  Outside the range (PLL pull-in right after reset) the
 //   step is redone by the EXACT instantiation, kept out of line so the hot loop stays small.
-// FULL = false (Rodas stages 2..6): only what the right-hand side reads -- sin, cos, E and Ppv/Vdc.  FULL = true (the
-// state the step ends in, base point of the next step's Jacobian): also 1/Vdc, Ppv and its slope.
+// FULL = false (inner stages): only what the right-hand side reads -- sin, cos, E and Ppv/Vdc.  FULL = true (the
+// state the step ends in, base point of the next step's Jacobian): sin, cos, E and 1/Vdc.
 template <bool EXACT, bool FULL = true>
 PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0, double dl,
                               double V, Aux& a, bool& out_of_range) {
@@ -147,13 +147,16 @@ PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b,
     pe = fma(pe, x, 0.5);
     pe = fma(pe, x, 1.0);
     a.E = fma(b.E * pe, x, b.E);                               // E0 * exp(x), exp to x^5/120
-    a.PoV = ppv_over_v_from_exp(par, in, a.E);
     if (FULL) {
       double r = b.inv_Vdc;
       r = fma(r, fma(-V, r, 1.0), r);
       r = fma(r, fma(-V, r, 1.0), r);
       a.inv_Vdc = r;
-      ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
+      // the PV part (Ppv, its slope, Ppv/Vdc) is evaluated from E at the start of the next step, with the inputs in
+      // force then (ros_core)
+      a.Ppv = a.dPpv = a.PoV = 0.0;
+    } else {
+      a.PoV = ppv_over_v_from_exp(par, in, a.E);
     }
   }
 }
