@@ -73,31 +73,32 @@ PVDER_DEV double vg_of_phase(const Inputs& in, int phases, int k) {
   return (phases == 1 || k == 0) ? in.vg : ((k == 1) ? in.vgb : in.vgc);
 }
 
-// Transcendental side-inputs of the model at one state: sin/cos of the PLL angle delta, the PV
-// array power and slope (which need exp(kappa*Vdc)) and 1/Vdc.  E = exp(kappa*Vdc) is kept so the
-// record can be advanced incrementally (pvder_env_step.cuh: aux_advance).
+// Transcendental side-inputs of the model at one state: sin/cos of the PLL angle delta and the PV array
+// current per pu (which needs E = exp(kappa*Vdc)).  E is kept so the record can be advanced incrementally
+// (pvder_env_step.cuh: aux_advance).
 struct Aux {
-  double sn, cs, Ppv, dPpv, inv_Vdc, E;
-  double PoV;   // Ppv / Vdc: all the DC-link equation needs at a Rodas stage (Ppv, dPpv, 1/Vdc: Jacobian only)
+  double sn, cs, E;
+  double PoV;    // Ppv / Vdc: what the DC-link equation reads at every stage
+  double dPoV;   // d(Ppv / Vdc) / dVdc: what its Jacobian reads (once per step)
 };
 
-// PV array power (pu) and its slope wrt Vdc from E = exp(kappa*Vdc).
-// Ipv = np_iph - Np Irs (E - 1) and Ppv = max(0, Ipv Vdc) pv_scale, written around the array current per pu
+// PV array: Ipv = np_iph - Np Irs (E - 1), Ppv = max(0, Ipv Vdc) pv_scale, written around the array
+// current per pu
 //   PoV = Ppv / Vdc = max(0, A - B E),  A = (np_iph + Np Irs) pv_scale (changes with the insolation events only),
-//   B = Np Irs pv_scale:  one FMA per Rodas stage; Ppv = PoV Vdc and dPpv/dVdc = (A - B E) - Vdc B kappa E are
-//   needed by the Jacobian only (once per step).  The DC-link equation (Ppv - P_inverter) / (C Vdc) reads PoV
-//   directly -- no multiplication by Vdc followed by one with 1/Vdc.
+//   B = Np Irs pv_scale:  one FMA per stage.  The DC-link equation (Ppv - P_inverter) / (C Vdc) =
+//   (PoV - P_inverter / Vdc) / C reads PoV directly and P_inverter / Vdc = Ps / 4 has no Vdc in it, so the
+//   equation's Vdc-derivative is dPoV / C with dPoV = -B kappa E: neither 1 / Vdc nor Ppv nor dPpv/dVdc is needed.
 PVDER_DEV double ppv_over_v_from_exp(const Params& par, const Inputs& in, double e) {
   const double raw = fma(-(par.np_irs * par.pv_scale), e, in.pvA);
   return raw > 0.0 ? raw : 0.0;
 }
 
-PVDER_DEV void ppv_from_exp(const Params& par, const Inputs& in, double Vdc, double e, double& P, double& dP) {
+PVDER_DEV void pov_from_exp(const Params& par, const Inputs& in, double e, double& PoV, double& dPoV) {
   const double B = par.np_irs * par.pv_scale;
   const double raw = fma(-B, e, in.pvA);
   const bool pos = raw > 0.0;
-  P = pos ? raw * Vdc : 0.0;
-  dP = pos ? fma(-(Vdc * (B * par.kappa)), e, raw) : 0.0;
+  PoV = pos ? raw : 0.0;
+  dPoV = pos ? -(B * par.kappa) * e : 0.0;
 }
 
 PVDER_DEV void ppv_eval(const Params& par, const Inputs& in, double Vdc, double& P,

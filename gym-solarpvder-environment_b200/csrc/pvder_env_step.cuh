@@ -101,9 +101,7 @@ inline RodasTab make_rodas_tab(const Params& par, double hinv) {
 PVDER_DEV void aux_exact_sv(const Params& par, const Inputs& in, double dl, double V, Aux& a) {
   sincos(dl, &a.sn, &a.cs);
   a.E = exp(par.kappa * V);
-  a.inv_Vdc = 1.0 / V;
-  ppv_from_exp(par, in, V, a.E, a.Ppv, a.dPpv);
-  a.PoV = ppv_over_v_from_exp(par, in, a.E);
+  pov_from_exp(par, in, a.E, a.PoV, a.dPoV);
 }
 
 template <class M>
@@ -112,16 +110,16 @@ PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[
 }
 
 // Aux record at (dl, V) close to the base point (angle dl0, DC voltage V0, record b):
-//   sin/cos(dl0 + d) by rotating (sn0, cs0) through d,  exp(kappa (V0 + dv)) = E0 * exp(kappa dv),
-//   1/V by two Newton steps from 1/V0 -- short Taylor polynomials instead of 3 library calls per Rodas
-//   stage.  Degrees are chosen against the integrator, not against the ulp: within the range
-//   |d|, |kappa dv| < 2^-4, |dv| < 2^-6 V0 the truncation is below 1e-10 relative (sin: d^7/5040, cos:
-//   d^6/720, exp: x^6/720, 1/V: (dv/V0)^4), three orders below the 1e-7 accuracy of a half-cycle Rodas4 step;
-//   and because every argument is O(h), the error terms are O(h^6) and beyond -- past the method's own
-//   order, so they do not change its convergence.  Outside the range (PLL pull-in right after reset) the
-//   step is redone by the EXACT instantiation, kept out of line so the hot loop stays small.
-// FULL = false (inner stages): only what the right-hand side reads -- sin, cos, E and Ppv/Vdc.  FULL = true (the
-// state the step ends in, base point of the next step's Jacobian): sin, cos, E and 1/Vdc.
+//   sin/cos(dl0 + d) by rotating (sn0, cs0) through d,  exp(kappa (V0 + dv)) = E0 * exp(kappa dv)
+//   -- short Taylor polynomials instead of 2 library calls per stage.  Degrees are chosen against the integrator,
+//   not against the ulp: within the range |d|, |kappa dv| < 2^-4 the truncation is below 1e-10 relative (sin:
+//   d^7/5040, cos: d^6/720, exp: x^6/720), three orders below the 1e-7 accuracy of a half-cycle step; and because
+//   every argument is O(h), the error terms are O(h^6) and beyond -- past the method's own order, so they do not
+//   change its convergence.  Outside the range (PLL pull-in right after reset) the step is redone by the EXACT
+//   instantiation, kept out of line so the hot loop stays small.
+// FULL = false (inner stages): sin, cos, E and the array current Ppv/Vdc the right-hand side reads.  FULL = true (the
+// state the step ends in, base point of the next step's Jacobian): sin, cos, E; the PV part is evaluated from E at
+// the start of the next step, with the inputs in force then (ros_core).
 template <bool EXACT, bool FULL = true>
 PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0, double dl,
                               double V, Aux& a, bool& out_of_range) {
@@ -133,7 +131,7 @@ PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b,
   const double dv = V - V0;
   const double x = par.kappa * dv;
   // outside the polynomial range the caller discards this step and redoes it with EXACT = true
-  out_of_range |= !(fabs(d) < 0.0625 && fabs(x) < 0.0625 && fabs(dv) < 0.015625 * V0);
+  out_of_range |= !(fabs(d) < 0.0625 && fabs(x) < 0.0625);
   {
     const double d2 = d * d;
     const double ps = fma(d2, 1.0 / 120.0, -1.0 / 6.0);
@@ -147,17 +145,8 @@ PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b,
     pe = fma(pe, x, 0.5);
     pe = fma(pe, x, 1.0);
     a.E = fma(b.E * pe, x, b.E);                               // E0 * exp(x), exp to x^5/120
-    if (FULL) {
-      double r = b.inv_Vdc;
-      r = fma(r, fma(-V, r, 1.0), r);
-      r = fma(r, fma(-V, r, 1.0), r);
-      a.inv_Vdc = r;
-      // the PV part (Ppv, its slope, Ppv/Vdc) is evaluated from E at the start of the next step, with the inputs in
-      // force then (ros_core)
-      a.Ppv = a.dPpv = a.PoV = 0.0;
-    } else {
-      a.PoV = ppv_over_v_from_exp(par, in, a.E);
-    }
+    if (FULL) a.PoV = a.dPoV = 0.0;
+    else a.PoV = ppv_over_v_from_exp(par, in, a.E);
   }
 }
 
@@ -191,8 +180,8 @@ PVDER_DEV void make_gains(const Params& par, const RodasTab& tab, unsigned frz, 
 }
 
 #ifndef PVDER_LAZY_GAINS
-#define PVDER_LAZY_GAINS 0   // 1: re-derive the effective gains from the clamp bits at every stage (selects on the idle ALU pipe)
-#endif                       //    instead of holding 9 doubles across the whole step (register-pressure experiment)
+#define PVDER_LAZY_GAINS 1   // 1: re-derive the effective gains from the clamp bits at every stage (selects on the idle ALU pipe)
+#endif                       //    instead of holding 9 doubles across the whole step: no spills left with ROS4-L (1.481 -> 1.468 ms)
 PVDER_DEV unsigned opaque_bits(unsigned v) {
 #ifdef __CUDACC__
   asm volatile("" : "+r"(v));     // the compiler must treat every call's result as a new value: no CSE, no hoisting
@@ -219,8 +208,7 @@ PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in,
   constexpr int NS = M::NS;
   bool oor = false;
   const double dl0 = y[M::IDX_DL], V0 = y[M::IDX_VDC];
-  ppv_from_exp(par, in, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
-  base.PoV = ppv_over_v_from_exp(par, in, base.E);
+  pov_from_exp(par, in, base.E, base.PoV, base.dPoV);      // inputs (insolation) may have changed
   typename M::LU lu;
   M::factor(y, par, in, base, gn, tab.ghinv, tab.luc, lu);
   double K1[NS], K2[NS], K3[NS], K4[NS], Y[NS];

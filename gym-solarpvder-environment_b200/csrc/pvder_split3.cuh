@@ -372,7 +372,7 @@ struct Split3 {
       f.piQ = piQ = f.g5h + par.Kp_Q;
     }
     const double qC = 0.25 * par.inv_C;
-    const double jVV = par.inv_C * ax.inv_Vdc * fma(-ax.Ppv, ax.inv_Vdc, ax.dPpv);
+    const double jVV = par.inv_C * ax.dPoV;
     // border matrix in u = (dQ, d vd, K_Vdc)
     const double m00 = fma(-RQ4, piQ, 1.0), m01 = -(RQ1 * piw), m02 = fma(piD, RQ3, -RQ2);
     const double m10 = -(Rv4 * piQ), m11 = fma(-f.vdd, pid, fma(-Rv1, piw, 1.0)), m12 = fma(piD, Rv3, -Rv2);
@@ -490,8 +490,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
   const Params& par = cfg.par;
   bool oor = false;
   const double dl0 = y.s[4], V0 = y.s[0];
-  ppv_from_exp(par, in_s, V0, base.E, base.Ppv, base.dPpv);      // inputs (insolation) may have changed
-  base.PoV = ppv_over_v_from_exp(par, in_s, base.E);
+  pov_from_exp(par, in_s, base.E, base.PoV, base.dPoV);      // inputs (insolation) may have changed
   Vec K1, K2, K3, K4, Y;
   Aux ax;
   S::Fac fac;

@@ -37,7 +37,7 @@ OUT = os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
 
 PAR = ["Rf", "Rt", "Xt", "inv_Lf", "inv_wb", "Kp_GCC", "Ki_GCC", "Kp_DC", "Ki_DC", "Kp_Q", "Ki_Q",
        "wp", "Kp_PLL", "Ki_PLL", "inv_C", "w0", "dw"]
-INP = ["vg", "vgb", "vgc", "Qref", "Vdcref", "Ppv", "dPpv"]
+INP = ["vg", "vgb", "vgc", "Qref", "Vdcref", "PoV", "dPoV"]
 
 
 def build(P, mult=1):
@@ -86,7 +86,7 @@ def build(P, mult=1):
         mR.append(p["Kp_GCC"] * uR + xR)
         mI.append(p["Kp_GCC"] * uI + xI)
         Q += mult * sp.Rational(1, 2) * (vI[k] * iR - vR[k] * iI)
-        Pinv += mult * sp.Rational(1, 4) * Vdc * (mR[k] * iR + mI[k] * iI)
+        Pinv += mult * sp.Rational(1, 4) * (mR[k] * iR + mI[k] * iI)          # P_inverter / Vdc
         ca, sa = alpha[k]
         ck = cs * ca + sn * sa       # cos(dl - a_k)
         sk = sn * ca - cs * sa       # sin(dl - a_k)
@@ -106,31 +106,28 @@ def build(P, mult=1):
         f[o + 3] = gs[4 * k + 1] * uI                                                # Ki_GCC
         f[o + 4] = gs[4 * k + 2] * (-uR + (rr * irefR - ri * irefI) - iR)           # wp
         f[o + 5] = gs[4 * k + 3] * (-uI + (ri * irefR + rr * irefI) - iI)           # wp
-    inv_Vdc = sp.Symbol("inv_Vdc")
-    f[base] = (inp["Ppv"] - Pinv) * p["inv_C"] * inv_Vdc
+    # DC link: (Ppv - P_inverter) / (C Vdc) = (Ppv / Vdc - P_inverter / Vdc) / C.  The array current per pu
+    # PoV = Ppv / Vdc = max(0, A - B exp(kappa Vdc)) and its slope dPoV = -B kappa exp(kappa Vdc) come from the
+    # Aux record: Vdc cancels in the second term, so neither the equation nor its Jacobian needs 1 / Vdc.
+    f[base] = (inp["PoV"] - Pinv) * p["inv_C"]
     f[base + 1] = gs[4 * P] * (inp["Vdcref"] - Vdc)                                  # Ki_DC
     f[base + 2] = -gs[4 * P + 1] * (inp["Qref"] - Q)                                 # Ki_Q
     f[base + 3] = gs[nfrz] * vd
     f[base + 4] = p["Kp_PLL"] * vd + xPLL + p["dw"]
     # Jacobian: chain rule through the helper symbols
-    helpers = {sn: sp.sin(dl), cs: sp.cos(dl), inv_Vdc: 1 / Vdc}
-    Ppv_f = sp.Function("Ppvf")(Vdc)
+    helpers = {sn: sp.sin(dl), cs: sp.cos(dl)}
+    Ppv_f = sp.Function("PoVf")(Vdc)
     J = {}
     for r in range(n):
-        fr = f[r].subs(inp["Ppv"], Ppv_f)
+        fr = f[r].subs(inp["PoV"], Ppv_f)
         fr_full = fr.subs(helpers)
         for c in range(n):
             d = sp.diff(fr_full, y[c])
             if d == 0:
                 continue
-            d = d.subs(sp.Derivative(Ppv_f, Vdc), inp["dPpv"]).subs(Ppv_f, inp["Ppv"])
+            d = d.subs(sp.Derivative(Ppv_f, Vdc), inp["dPoV"]).subs(Ppv_f, inp["PoV"])
             d = d.subs({sp.sin(dl): sn, sp.cos(dl): cs})
-            d = d.subs(1 / Vdc, inv_Vdc)
             d = sp.simplify(d) if P == 1 else d
-            d = d.subs(1 / Vdc, inv_Vdc).subs(Vdc ** -2, inv_Vdc ** 2)
-            # never emit a division: sympy may have rewritten Vdc as 1/inv_Vdc
-            d = d.replace(lambda e: e.is_Pow and e.base == inv_Vdc and e.exp.is_negative,
-                          lambda e: Vdc ** (-e.exp))
             if d != 0:
                 J[(r, c)] = d
     frozen_rows = []
@@ -147,7 +144,7 @@ def build(P, mult=1):
     for r in unit_rows:
         assert (r, r) not in J, r
     return dict(P=P, mult=mult, n=n, names=names, gs=gs, y=y, f=f, J=J, par=par, inp=inp, frozen=frozen_rows,
-                helpers=(sn, cs, inv_Vdc), unit_rows=unit_rows)
+                helpers=(sn, cs), unit_rows=unit_rows)
 
 
 def emit_rhs_structured(m, acc=False):
@@ -246,11 +243,6 @@ def check_structured_rhs(m, lines, acc=False):
         env[str(s_)] = v
         syms[s_] = v
     syms[sp.Symbol("SQ3")] = math.sqrt(3.0)
-    # the emitted code may use inv_Vdc * Vdc = 1
-    inv_sym = m["helpers"][2]
-    vdc_sym = m["y"][6 * m["P"]]
-    env[str(inv_sym)] = syms[inv_sym] = 1.0 / syms[vdc_sym]
-    env["in_PoV"] = syms[m["inp"]["Ppv"]] * syms[inv_sym]
     pre = [rnd.uniform(-1.0, 1.0) if acc else 0.0 for _ in range(m["n"])]
     f = list(pre)
     env["f"] = f
@@ -495,7 +487,7 @@ def generate(P, mult=1):
     A("    (void)in_vgb; (void)in_vgc;")
     A("    (void)in_Qref; (void)in_Vdcref;")
     A("    constexpr double SQ3 = 1.7320508075688772; (void)SQ3;")
-    A("    const double sn = aux.sn, cs = aux.cs, in_Ppv = aux.Ppv, in_dPpv = aux.dPpv, inv_Vdc = aux.inv_Vdc;")
+    A("    const double sn = aux.sn, cs = aux.cs, in_dPoV = aux.dPoV;")
     keys = sorted(J.keys())
     L.extend(gain_unpack)
     for (r, c) in keys:
