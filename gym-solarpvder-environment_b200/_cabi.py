@@ -88,6 +88,7 @@ SIGNATURES = {
     "pvder_env_set_refs_host": (C.c_int, [_vp, _vp]),
     "pvder_env_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "pvder_env_kernel_ms": (C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "pvder_env_pipeline_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(_dbl)]),
     "pvder_host_alloc": (_vp, [C.c_size_t]),
     "pvder_host_free": (None, [_vp]),
 }

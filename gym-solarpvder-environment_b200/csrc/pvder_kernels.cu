@@ -774,6 +774,7 @@ int pvder_fp64_peak(int iters, double* tflops, double* ms_out) {
 }
 
 // ---- host-buffer handle API ------------------------------------------------------------------
+constexpr int PVDER_MAX_CHUNKS = 12;
 struct pvder_env {
   pvder_env_config cfg;
   int64_t n, off, ld;
@@ -792,10 +793,13 @@ struct pvder_env {
                               // the SMs that the draining tail of chunk c leaves idle
   cudaStream_t copy_stream;   // D2H of finished chunks, overlapped with the next chunk's kernel
   cudaStream_t h2d_stream;    // H2D of the actions of later chunks, overlapped with the first chunk's kernel
-  cudaEvent_t act_ready[8];
+  cudaEvent_t act_ready[PVDER_MAX_CHUNKS];
   int64_t wave_envs;          // envs one full wave of resident CTAs processes (chunks are whole waves)
   cudaEvent_t e0, e1;
-  cudaEvent_t chunk_done[8];
+  cudaEvent_t chunk_done[PVDER_MAX_CHUNKS];
+  cudaEvent_t cp0, cp1;       // around the D2H copies of the bulk chunk: measures the copy time per env
+  int last_chunks;            // chunks of the last step_host call
+  double copy_ratio;          // D2H time / kernel time per env (running estimate; chunk sizes shrink by this factor)
   double ms_total;
   int64_t launches;
   int fresh;   // no reset_host() yet: the first one starts episode 0
@@ -817,8 +821,11 @@ int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_of
   CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-  for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
-  for (int c = 0; c < 8; ++c) CK(cudaEventCreateWithFlags(&h->act_ready[c], cudaEventDisableTiming));
+  for (int c = 0; c < PVDER_MAX_CHUNKS; ++c) CK(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
+  for (int c = 0; c < PVDER_MAX_CHUNKS; ++c) CK(cudaEventCreateWithFlags(&h->act_ready[c], cudaEventDisableTiming));
+  CK(cudaEventCreate(&h->cp0));
+  CK(cudaEventCreate(&h->cp1));
+  h->copy_ratio = 0.5;
   {
     // one wave = resident CTAs per SM x SMs x envs per CTA of the step kernel this config launches
     int dev = 0, sms = 148, per_sm = 2;
@@ -867,8 +874,9 @@ int pvder_env_destroy(pvder_env* h) {
   cudaFree(h->sd); cudaFree(h->si); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_obs64);
   cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_vtab); cudaFree(h->d_stab);
   cudaEventDestroy(h->e0); cudaEventDestroy(h->e1);
-  for (int c = 0; c < 8; ++c) cudaEventDestroy(h->chunk_done[c]);
-  for (int c = 0; c < 8; ++c) cudaEventDestroy(h->act_ready[c]);
+  for (int c = 0; c < PVDER_MAX_CHUNKS; ++c) cudaEventDestroy(h->chunk_done[c]);
+  for (int c = 0; c < PVDER_MAX_CHUNKS; ++c) cudaEventDestroy(h->act_ready[c]);
+  cudaEventDestroy(h->cp0); cudaEventDestroy(h->cp1);
   cudaStreamDestroy(h->h2d_stream);
   cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->copy_stream);
@@ -904,15 +912,16 @@ int pvder_env_reset_host(pvder_env* h, float* obs_out, double* obs64_out) {
 int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
                         uint8_t* done_out) {
   if (!h || !action) return PVDER_ERR_INVALID;
-  // Large batches are cut into up to 8 chunks (units of a quarter wave of resident CTAs) that run alternately
+  // Large batches are cut into up to 12 chunks (units of a quarter wave of resident CTAs) that run alternately
   // on two compute streams -- they touch disjoint envs, so the head of chunk c+1 fills the SMs the draining
   // tail of chunk c leaves idle -- while the action H2D copies (h2d stream) run ahead of the kernels and the
   // D2H copy of chunk c (copy stream) runs under the later kernels.  Schedule: a one-wave first chunk (its
-  // actions arrive after ~150 KB of H2D, so the GPU starts at once), the bulk, then chunks halving down to
-  // one wave and a final quarter wave, so that only ~0.5 MB of results is copied after the last kernel and
-  // every other copy hides under at least as much compute as produced it (D2H moves 53 B/env, ~3x faster
-  // than the kernel produces them on an idle host).
-  int64_t start[9];
+  // actions arrive after ~150 KB of H2D, so the GPU starts at once), then chunks that shrink geometrically by
+  // q = (D2H time) / (kernel time) per env: the copy of chunk c then takes as long as the kernel of chunk c+1, the
+  // copy engine never idles and only the last, smallest chunk is copied after the last kernel.  q is measured on
+  // the previous calls (events around the bulk chunk's copies against the kernel span) -- it depends on the model,
+  // on n_sim and on how many ranks share the host's memory system -- and is kept within [0.3, 0.9].
+  int64_t start[PVDER_MAX_CHUNKS + 1];
   int chunks = 0;
   start[0] = 0;
   const int64_t unit = h->wave_envs / 4;
@@ -921,35 +930,45 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
     start[1] = h->n;
     chunks = 1;
   } else {
-    int64_t tail[6];                               // sizes from the end: 1, 4, 8, 16, ... units
-    int k = 0;
-    int64_t rest = units - 4 - 1;                  // minus the first chunk (4 units) and the last (1 unit)
-    tail[k++] = 1;
-    int64_t w0 = (units - 5 + 62) / 63;            // six doubling chunks must be able to cover a very large batch
-    if (w0 < 4) w0 = 4;
-    for (int64_t w = w0; k < 6 && rest - w >= w; w *= 2) {
-      tail[k++] = w;
-      rest -= w;
+    const double q = h->copy_ratio;
+    const int64_t R = units - 4;                   // what follows the first chunk (4 units)
+    int m = PVDER_MAX_CHUNKS - 1;                  // geometric chunks: as many as keep the last one >= 1 unit
+    double s1 = 0.0;
+    for (; m > 1; --m) {
+      s1 = (double)R * (1.0 - q) / (1.0 - std::pow(q, m));
+      if (s1 * std::pow(q, m - 1) >= 1.0) break;
     }
+    if (m <= 1) s1 = (double)R;
+    int64_t size[PVDER_MAX_CHUNKS];
+    int64_t used = 0;
+    for (int c = m - 1; c >= 1; --c) {             // from the smallest up; the bulk takes what rounding leaves
+      int64_t w = (int64_t)(s1 * std::pow(q, c) + 0.5);
+      if (w < 1) w = 1;
+      size[c] = w;
+      used += w;
+    }
+    size[0] = R - used;
     int64_t pos = 4 * unit;
     start[++chunks] = pos;                         // first chunk: one wave
-    pos += rest * unit;
-    start[++chunks] = pos;                         // the bulk
-    for (int c = k - 1; c >= 1; --c) {
-      pos += tail[c] * unit;
+    for (int c = 0; c < m; ++c) {
+      pos += size[c] * unit;
       start[++chunks] = pos;
     }
-    start[++chunks] = h->n;                        // last quarter wave + the remainder (< 1 unit)
+    start[chunks] = h->n;                          // the last chunk also takes the remainder (< 1 unit)
   }
-  for (int c = 0; c < chunks; ++c) {
-    const int64_t lo = start[c], cnt = start[c + 1] - lo;
-    CK(cudaMemcpyAsync(h->d_action + lo, action + lo, sizeof(int32_t) * cnt, cudaMemcpyHostToDevice, h->h2d_stream));
-    CK(cudaEventRecord(h->act_ready[c], h->h2d_stream));
-  }
+  // Submission order: the first chunk's action copy and kernel go out before anything else is enqueued (the GPU
+  // starts ~10 us into the call instead of after ~100 API calls); the action copies of the other chunks follow at
+  // once -- they are small (4 B/env) and run ahead of the kernels on their own stream.
   CK(cudaEventRecord(h->e0, h->stream));
   for (int c = 0; c < chunks; ++c) {
     const int64_t lo = start[c], cnt = start[c + 1] - lo;
     cudaStream_t cs = (c & 1) ? h->stream2 : h->stream;
+    const int a_lo = (c == 0) ? 0 : 1, a_hi = (c == 0) ? 1 : ((c == 1) ? chunks : 0);   // actions of chunk 0; of all the others
+    for (int a = a_lo; a < a_hi; ++a) {
+      const int64_t alo = start[a], acnt = start[a + 1] - alo;
+      CK(cudaMemcpyAsync(h->d_action + alo, action + alo, sizeof(int32_t) * acnt, cudaMemcpyHostToDevice, h->h2d_stream));
+      CK(cudaEventRecord(h->act_ready[a], h->h2d_stream));
+    }
     if (c == 1) CK(cudaStreamWaitEvent(h->stream2, h->e0, 0));      // keep launch order: chunk 1 after the start mark
     CK(cudaStreamWaitEvent(cs, h->act_ready[c], 0));
     int rc = pvder_step(&h->cfg, h->sd + lo, h->si + lo, h->ld, h->d_action + lo, h->d_vtab ? h->d_vtab + lo : nullptr,
@@ -959,6 +978,7 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
     if (rc) return rc;
     CK(cudaEventRecord(h->chunk_done[c], cs));
     CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+    if (c == 1) CK(cudaEventRecord(h->cp0, h->copy_stream));
     if (obs_out)
       CK(cudaMemcpyAsync(obs_out + lo * PVDER_OBS_DIM, h->d_obs + lo * PVDER_OBS_DIM, sizeof(float) * PVDER_OBS_DIM * cnt,
                          cudaMemcpyDeviceToHost, h->copy_stream));
@@ -968,6 +988,7 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
     if (reward_out)
       CK(cudaMemcpyAsync(reward_out + lo, h->d_reward + lo, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
     if (done_out) CK(cudaMemcpyAsync(done_out + lo, h->d_done + lo, cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (c == 1) CK(cudaEventRecord(h->cp1, h->copy_stream));
   }
   // end mark of the kernel span: after the last chunk of either compute stream
   if (chunks > 1) CK(cudaStreamWaitEvent(h->stream, h->chunk_done[((chunks - 1) & 1) ? chunks - 1 : chunks - 2], 0));
@@ -979,6 +1000,19 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
   CK(cudaEventElapsedTime(&ms, h->e0, h->e1));
   h->ms_total += ms;
   h->launches += 1;
+  h->last_chunks = chunks;
+  if (chunks > 2 && ms > 0.f) {
+    // copy time per env (bulk chunk) over kernel time per env (whole span): next call's shrink factor
+    float cms = 0.f;
+    CK(cudaEventElapsedTime(&cms, h->cp0, h->cp1));
+    // 15 % on top: a ratio taken too small lets the copies fall behind the kernels and pile up after the last one,
+    // one taken too large only leaves the copy engine a little idle
+    const double r = 1.15 * ((double)cms / (double)(start[2] - start[1])) / ((double)ms / (double)h->n);
+    if (r > 0.0 && r < 100.0) {
+      double q = 0.5 * h->copy_ratio + 0.5 * r;
+      h->copy_ratio = q < 0.3 ? 0.3 : (q > 0.9 ? 0.9 : q);
+    }
+  }
   return PVDER_OK;
 }
 
@@ -1007,6 +1041,13 @@ int pvder_env_device_ptrs(pvder_env* h, double** sd, int32_t** si, int64_t* ld) 
   if (sd) *sd = h->sd;
   if (si) *si = h->si;
   if (ld) *ld = h->ld;
+  return PVDER_OK;
+}
+
+int pvder_env_pipeline_info(pvder_env* h, int32_t* chunks, double* copy_ratio) {
+  if (!h) return PVDER_ERR_INVALID;
+  if (chunks) *chunks = h->last_chunks;
+  if (copy_ratio) *copy_ratio = h->copy_ratio;
   return PVDER_OK;
 }
 

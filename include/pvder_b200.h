@@ -194,6 +194,9 @@ int pvder_env_set_refs_host(pvder_env* env, const double* sd_in);
 int pvder_env_device_ptrs(pvder_env* env, double** sd, int32_t** si, int64_t* ld);
 /* Average device time (ms) of the step kernel launches since the last call (CUDA events). */
 int pvder_env_kernel_ms(pvder_env* env, double* ms_total, int64_t* launches);
+/* Host-buffer pipeline of pvder_env_step_host: chunks of the last call and the running estimate of
+   (device->host copy time) / (kernel time) per env that sizes them. */
+int pvder_env_pipeline_info(pvder_env* env, int32_t* chunks, double* copy_ratio);
 void* pvder_host_alloc(size_t bytes);   /* pinned host memory */
 void pvder_host_free(void* p);
 

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE: loader for the plain-C++ build of the per-env device logic
 (tests/host_emul/emul.cpp).  Lets the CPU test tier check the *generated kernel source*
-(model RHS, symbolic LU, Rodas4, events, outputs) against the oracle without a GPU."""
+(model RHS, symbolic LU, the Rosenbrock stepper, events, outputs) against the oracle without a GPU."""
 import ctypes as C
 import os
 import subprocess

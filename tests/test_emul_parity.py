@@ -1,4 +1,4 @@
-"""CPU tier: the *kernel source itself* (generated model code, symbolic LU, Rodas4, events,
+"""CPU tier: the *kernel source itself* (generated model code, symbolic LU, Rosenbrock stepper, events,
 outputs) compiled as plain C++ (tests/host_emul) and checked against the oracle and the bit-exact
 twins.  This is what makes the CUDA path debuggable without a GPU; the GPU tier then asserts that
 the nvcc build of the same source agrees with this build to ~1e-11 (test_gpu_parity.py)."""

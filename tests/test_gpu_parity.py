@@ -691,7 +691,7 @@ def test_step_after_done_is_a_no_op_inside_a_running_warp(cuda, mode):
 
 @pytest.mark.parametrize("model_type,mode", [("model_1", "auto"), ("model_2", "split")])
 def test_host_handle_api_chunked_pipeline(cuda, model_type, mode):
-    """Large batch through pvder_env_step_host: the call is cut into quarter-wave chunks on two compute streams with the
+    """Large batch through pvder_env_step_host: the call is cut into geometrically shrinking chunks on two compute streams with the
     copies overlapped; every env must come out bit-identical to the single-launch device API (chunk boundaries, the
     remainder chunk, env offsets of the RNG keys), over several steps incl. obs64."""
     import ctypes as C
@@ -723,4 +723,8 @@ def test_host_handle_api_chunked_pipeline(cuda, model_type, mode):
     sd = np.zeros((_cabi.sd_fields(cfg.n_state), n))
     _cabi.check(lib.pvder_env_state_host(h, sd.ctypes.data, None))
     np.testing.assert_array_equal(sd, g.sd[:, :n].cpu().numpy())
+    # the call really was pipelined, with chunk sizes shrinking by the measured copy/kernel time ratio
+    chunks, ratio = C.c_int32(), C.c_double()
+    _cabi.check(lib.pvder_env_pipeline_info(h, C.byref(chunks), C.byref(ratio)))
+    assert 3 <= chunks.value <= 12 and 0.3 <= ratio.value <= 0.9
     _cabi.check(lib.pvder_env_destroy(h))

@@ -60,6 +60,54 @@ RODAS4 = dict(
 )
 
 
+# Hairer & Wanner's ROS4 code, "L-stable" coefficient set (IV.7, table 7.2): 4 stages, order 4, gamma = 0.57282,
+# stage 4 evaluated at Y3 (3 right-hand sides per step).  The kernel's scheme since round 1 (PVDER_SCHEME 4).
+ROS4L = dict(
+    g=0.57282,
+    A=[[0] * 4, [2.0, 0, 0, 0],
+       [0.1867943637803922e+01, 0.2344449711399156, 0, 0],
+       [0.1867943637803922e+01, 0.2344449711399156, 0, 0]],
+    C=[[0] * 4, [-0.7137615036412310e+01, 0, 0, 0],
+       [0.2580708087951457e+01, 0.6515950076447975, 0, 0],
+       [-0.2137148994382534e+01, -0.3214669691237626, -0.6949742501781779, 0]],
+    m=[0.2255570073418735e+01, 0.2870493262186792, 0.4353179431840180, 0.1093502252409163e+01],
+)
+# Kaps-Rentrop GRK4T: same cost, A(89.3 deg)-stable with |R(inf)| = 0.454 (fast transients decay slowly)
+GRK4T = dict(
+    g=0.231,
+    A=[[0] * 4, [2.0, 0, 0, 0],
+       [0.4524708207373116e+01, 0.4163528788597648e+01, 0, 0],
+       [0.4524708207373116e+01, 0.4163528788597648e+01, 0, 0]],
+    C=[[0] * 4, [-0.5071675338776316e+01, 0, 0, 0],
+       [0.6020152728650786e+01, 0.1597506846727117, 0, 0],
+       [-0.1856343618686113e+01, -0.8505380858179826e+01, -0.2084075136023187e+01, 0]],
+    m=[0.3957503746640777e+01, 0.4624892388363313e+01, 0.6174772638750108, 0.1282612945269037e+01],
+)
+
+
+def order_conditions(tab):
+    """Residuals of the eight order conditions up to order 4 (Hairer & Wanner IV.7, table 7.1) and R(inf), from the
+    transformed coefficients: Gamma^-1 = diag(1/gamma) - C, alpha = A Gamma, b = m Gamma."""
+    g = tab["g"]
+    A, Cm, m = np.array(tab["A"], float), np.array(tab["C"], float), np.array(tab["m"], float)
+    s = len(m)
+    Gam = np.linalg.inv(np.eye(s) / g - Cm)
+    al = A @ Gam
+    b = m @ Gam
+    be = al + Gam - g * np.eye(s)          # beta_ij = alpha_ij + gamma_ij, strictly lower part
+    ai, bi = al.sum(axis=1), be.sum(axis=1)
+    res = [b.sum() - 1.0,
+           b @ bi - (0.5 - g),
+           b @ ai ** 2 - 1.0 / 3.0,
+           b @ be @ bi - (1.0 / 6.0 - g + g * g),
+           b @ ai ** 3 - 0.25,
+           b @ (ai * (al @ bi)) - (0.125 - g / 3.0),
+           b @ be @ ai ** 2 - (1.0 / 12.0 - g / 3.0),
+           b @ be @ be @ bi - (1.0 / 24.0 - g / 2.0 + 1.5 * g * g - g ** 3)]
+    r_inf = 1.0 - b @ np.linalg.inv(al + Gam) @ np.ones(s)     # stability function R(z) = 1 + z b (I - z B)^-1 1 at infinity
+    return np.array(res), r_inf
+
+
 def rosenbrock_step(f, J, y, h, tab):
     g, A, C, m = tab["g"], tab["A"], tab["C"], tab["m"]
     s = len(m)
@@ -132,6 +180,8 @@ def sdirk4_step(f, J, y, h, newton=6):
 SCHEMES = {
     "rodas3": lambda f, J, y, h: rosenbrock_step(f, J, y, h, RODAS3),
     "rodas4": lambda f, J, y, h: rosenbrock_step(f, J, y, h, RODAS4),
+    "ros4l": lambda f, J, y, h: rosenbrock_step(f, J, y, h, ROS4L),
+    "grk4t": lambda f, J, y, h: rosenbrock_step(f, J, y, h, GRK4T),
     "rodas3x2": lambda f, J, y, h: rosenbrock_step(f, J, rosenbrock_step(f, J, y, h / 2, RODAS3), h / 2, RODAS3),
     "rodas4x2": lambda f, J, y, h: rosenbrock_step(f, J, rosenbrock_step(f, J, y, h / 2, RODAS4), h / 2, RODAS4),
     "sdirk4": sdirk4_step,
@@ -149,7 +199,11 @@ def order_check():
     def J(y):
         return np.array([[lam, lam * math.sin(y[1]) - math.cos(y[1])], [0.0, 0.0]])
 
-    for name in ("rodas3", "rodas4", "sdirk4", "radau5"):
+    for name, tab in (("rodas3", RODAS3), ("rodas4", RODAS4), ("ros4l", ROS4L), ("grk4t", GRK4T)):
+        res, r_inf = order_conditions(tab)
+        print(f"order conditions {name}: max |residual| orders 1-3 {np.abs(res[:4]).max():.1e}, order 4 "
+              f"{np.abs(res[4:]).max():.1e}; R(inf) = {r_inf:+.3f}")
+    for name in ("rodas3", "rodas4", "ros4l", "grk4t", "sdirk4", "radau5"):
         errs = []
         for N in (10, 20, 40, 80):
             y = np.array([1.0, 0.0])
