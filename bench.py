@@ -32,8 +32,24 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the single JSON line (NCCL prints its version there)
+
+
+# The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on the first
+# communicator), so file descriptor 1 points at stderr for the whole run and the line goes to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def _stdout_to_stderr():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    os.write(out, (json.dumps(line) + "\n").encode())
 
 # algorithmic flop per half-cycle sub-step: n = 11 -> 2.2 kflop, n = 23 -> 12.5 kflop.  The
 # balanced three-phase reduction integrates 11 states, so it is measured with the n = 11 yardstick.
@@ -222,7 +238,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample,
                                  "note": "restated reference path (pvder unavailable): oracle O2"},
                 "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import numpy as np
@@ -384,10 +400,11 @@ def main():
             "gpu_launches": K, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "episode_stats": {"envs": st[10], "windup_sub_steps": st[9], "exact_sub_steps": st[11], "failed": st[3],
                               "note": "counters of the episode in progress at the end of the run (auto-reset clears them)"}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
+    _stdout_to_stderr()
     main()
