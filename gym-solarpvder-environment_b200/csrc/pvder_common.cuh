@@ -31,7 +31,7 @@ namespace pvder {
 
 // Reciprocal of a well-scaled pivot (normal, positive, far from the ends of the exponent range): hardware
 // seed (2^-23) + two Newton steps = full double accuracy without the IEEE division's special-case
-// branches, which split the straight-line Rodas4 code into scheduling regions.
+// branches, which split the straight-line stepper code into scheduling regions.
 PVDER_DEV double pvder_rcp(double x) {
 #ifdef __CUDACC__
   double r;

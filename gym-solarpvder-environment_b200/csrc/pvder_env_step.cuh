@@ -1,4 +1,4 @@
-// Per-environment device logic of the PVDER-v0 step: Rodas4 half-cycle integrator, anti-windup
+// Per-environment device logic of the PVDER-v0 step: half-cycle Rosenbrock integrator, anti-windup
 // mode sampling, event draw, outputs (obs / reward).  Shared by the CUDA kernels
 // (pvder_kernels.cu) and -- compiled as plain C++ -- by the CPU-side test harness
 // tests/host_emul (test infrastructure only; the product path is the CUDA build).

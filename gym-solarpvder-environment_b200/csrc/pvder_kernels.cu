@@ -7,8 +7,8 @@
 // step kernel      <- PVDER.step            reference gym_PVDER/envs/PVDER_env.py:138-196
 //   action         <- PVDER.action_calc     :198-229
 //   integrator     <- sim.run_simulation()  :166 (pvder DynamicSimulation -> scipy odeint/LSODA,
-//                     SURVEY.md A.7) replaced by a fixed half-cycle Rodas4 (L-stable, stiffly
-//                     accurate Rosenbrock, 6 stages, order 4) on the generated model code
+//                     SURVEY.md A.7) replaced by a fixed half-cycle Rosenbrock step (ROS4-L: L-stable, 4 stages,
+//                     order 4; pvder_env_step.cuh) on the generated model code
 //   events/RNG     <- generate_simulation_events :400-411 (pvder create_random_events, A.8)
 //   reward         <- PVDER.reward_calc     :231-301
 //   observation    <- PVDER.state           :531-542

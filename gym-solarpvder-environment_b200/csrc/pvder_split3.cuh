@@ -3,7 +3,7 @@
 // shared tail (Vdc, xDC, xQ, xPLL, delta); the three phases couple only through three sums
 // (reactive power, inverter power, PLL d-axis voltage) that are formed with warp shuffles.
 //
-// Why: one thread cannot hold the 23-state Rodas4 working set (23 states, 174 LU entries, five stage
+// Why: one thread cannot hold the 23-state working set of a Rosenbrock step (23 states, 174 LU entries, 4-5 stage
 // vectors) in 255 registers -- the one-thread kernel moves 160 GB of spill traffic per 1 Mi-env launch
 // (profiles/r1d_step_kernel_3ph_general_ncu_full.csv).  Split by phase, a lane carries the same 11
 // values per vector as the single-phase kernel and no dense LU at all:
@@ -43,7 +43,7 @@ struct LanesT {
   PVDER_DEV unsigned m() const { return DYN ? mask : 0xffffffffu; }
   // Sum over the three phases, two shuffles: own + next + next-next.  Lane a gets (a + b) + c; the other
   // lanes get the same sum in a rotated order (last-bit differences), so every DECISION derived from a
-  // sum is taken group-wide (any3 / from_a) -- see gains() and the range flag of the Rodas4 core.
+  // sum is taken group-wide (any3 / from_a) -- see gains() and the range flag of the stepper core.
   PVDER_DEV double sum3(double v) const {
     const double b = __shfl_sync(m(), v, n1), c = __shfl_sync(m(), v, n2);
     return __dadd_rn(__dadd_rn(v, b), c);

@@ -84,6 +84,13 @@ class EmulVecEnv:
         return v, s
 
 
+def scheme(cfg):
+    """Integrator tableau compiled into the kernels: dict(scheme, gamma, a, c, m, d4, h_gamma)."""
+    out = np.zeros(34)
+    load().emul_scheme(C.byref(cfg.c), _p(out))
+    return dict(scheme=int(out[0]), gamma=out[1], a=out[2:12], c=out[12:27], m=out[27:31], d4=out[31:33], h_gamma=out[33])
+
+
 def rhs(cfg, y, inp4, frz=0):
     f = np.zeros(cfg.n_state)
     y = np.ascontiguousarray(y, dtype=np.float64)

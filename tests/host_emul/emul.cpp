@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY.  Plain-C++ build of the per-environment device logic
 // (csrc/pvder_env_step.cuh + the generated model headers) so the generated right-hand side,
-// symbolic LU, Rodas4 stepper, event draw and output/reward code can be checked against the
+// symbolic LU, Rosenbrock stepper, event draw and output/reward code can be checked against the
 // oracle on a machine without a GPU.  Never loaded by the product package.
 #include <cstring>
 
@@ -330,6 +330,25 @@ void emul_wsolve(const pvder_env_config* cfg, const double* y, const double* inp
 
 unsigned emul_freeze_bits(const pvder_env_config* cfg, const double* y, const double* inp4) {
   return cfg->phases == 1 ? frz_one<Model1ph>(*cfg, y, inp4) : frz_one<Model3ph>(*cfg, y, inp4);
+}
+
+// The integrator tableau the kernels are compiled with, un-scaled (c_ij and d_4j multiplied back by h):
+// out = [PVDER_SCHEME, gamma, a21 a31 a32 a41 a42 a43 a51 a52 a53 a54, c21 c31 c32 c41 c42 c43 c51 .. c54 c61 .. c65,
+//        m1 m2 m3 m4, d41 d42, cs21 / c21 (= h gamma)]
+void emul_scheme(const pvder_env_config* cfg, double* out) {
+  const double hinv = 120.0;
+  const RodasTab t = make_rodas_tab<Model1ph>(cfg->par, hinv);
+  const double h = 1.0 / hinv;
+  int k = 0;
+  out[k++] = (double)PVDER_SCHEME;
+  out[k++] = RG;
+  const double a[10] = {t.a21, t.a31, t.a32, t.a41, t.a42, t.a43, t.a51, t.a52, t.a53, t.a54};
+  for (double v : a) out[k++] = v;
+  const double c[15] = {t.c21, t.c31, t.c32, t.c41, t.c42, t.c43, t.c51, t.c52, t.c53, t.c54, t.c61, t.c62, t.c63, t.c64, t.c65};
+  for (double v : c) out[k++] = v * h;
+  out[k++] = t.m1; out[k++] = t.m2; out[k++] = t.m3; out[k++] = t.m4;
+  out[k++] = t.d41 * h; out[k++] = t.d42 * h;
+  out[k++] = t.cs21 / t.c21;
 }
 
 void emul_split_free_path(int on) { free_path = on != 0; }

@@ -93,6 +93,67 @@ def test_freeze_mask_matches_oracle(model_type):
     assert seen == {True, False}
 
 
+def test_compiled_tableau_satisfies_the_order_conditions():
+    """Known-answer test of the integrator: the coefficients the kernels are compiled with (ROS4-L, Hairer & Wanner IV.7)
+    satisfy all eight Rosenbrock order conditions up to order 4 (table 7.1 there) and give R(inf) = 0 (L-stability) to
+    the five digits gamma carries; stage 4 re-uses stage 3's right-hand side (d4j = c4j - c3j)."""
+    t = E.scheme(G.EnvConfig(model_type="model_1"))
+    assert t["scheme"] == 4 and t["gamma"] == 0.57282
+    g = t["gamma"]
+    a21, a31, a32 = t["a"][:3]
+    c21, c31, c32, c41, c42, c43 = t["c"][:6]
+    A = np.array([[0, 0, 0, 0], [a21, 0, 0, 0], [a31, a32, 0, 0], [a31, a32, 0, 0]], float)    # stage 4 at Y3
+    Cm = np.array([[0, 0, 0, 0], [c21, 0, 0, 0], [c31, c32, 0, 0], [c41, c42, c43, 0]], float)
+    m = t["m"]
+    np.testing.assert_allclose(t["d4"], [c41 - c31, c42 - c32], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(t["h_gamma"], g / 120.0, rtol=1e-15)
+    Gam = np.linalg.inv(np.eye(4) / g - Cm)          # transformed form: Gamma^-1 = diag(1/gamma) - C
+    al, b = A @ Gam, m @ Gam                         # alpha = A Gamma, b = m Gamma
+    be = al + Gam - g * np.eye(4)                    # beta_ij = alpha_ij + gamma_ij (strictly lower)
+    ai, bi = al.sum(axis=1), be.sum(axis=1)
+    res = [b.sum() - 1.0, b @ bi - (0.5 - g), b @ ai ** 2 - 1.0 / 3.0, b @ be @ bi - (1.0 / 6.0 - g + g * g),
+           b @ ai ** 3 - 0.25, b @ (ai * (al @ bi)) - (0.125 - g / 3.0), b @ be @ ai ** 2 - (1.0 / 12.0 - g / 3.0),
+           b @ be @ be @ bi - (1.0 / 24.0 - g / 2.0 + 1.5 * g * g - g ** 3)]
+    assert np.abs(res).max() < 5e-15, res
+    r_inf = 1.0 - b @ np.linalg.inv(al + Gam) @ np.ones(4)
+    assert abs(r_inf) < 1e-4
+
+
+def test_rodas4_cross_check_build_meets_the_same_tolerances(tmp_path):
+    """The kernel source compiled with the round-1 scheme (-DPVDER_SCHEME=6, Rodas4: 6 stages, stiffly accurate) passes
+    the same golden fixture with the same tolerances, and the two schemes agree with each other to those tolerances:
+    the integrator choice is not tuned to the fixture."""
+    import ctypes as C
+    import subprocess
+    lib6 = str(tmp_path / "libpvder_emul_rodas4.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                    "-DPVDER_SCHEME=6", "-o", lib6, E._SRC], check=True)
+    gold = np.load("tests/golden/golden_model_1.npz")
+    acts = gold["actions"]
+    n, nsteps = acts.shape
+    envs = []
+    for lib in (None, C.CDLL(lib6)):
+        em = E.EmulVecEnv(n, model_type="model_1", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True)
+        if lib is not None:
+            em.lib = lib
+        em.set_event_tables(gold["vgrid_tab"], gold["sinsol_tab"])
+        em.reset()
+        envs.append(em)
+    out = np.zeros(34)
+    envs[1].lib.emul_scheme(C.byref(envs[1].cfg.c), E._p(out))
+    assert int(out[0]) == 6 and out[1] == 0.25
+    for s in range(nsteps):
+        o4, r4, _, _ = envs[0].step(acts[:, s])
+        o6, r6, _, _ = envs[1].step(acts[:, s])
+        np.testing.assert_allclose(o6, gold["obs"][:, s], rtol=H.RTOL, atol=H.ATOL)
+        np.testing.assert_array_equal(r6, gold["reward"][:, s])
+        np.testing.assert_array_equal(r4, r6)
+        np.testing.assert_allclose(o4, o6, rtol=H.RTOL, atol=H.ATOL)
+        for i in range(n):
+            H.assert_state_close(envs[1].sd[:envs[1].ns, i], gold["state"][i, s], 1, what=f"rodas4 env{i} step{s}")
+            H.assert_state_close(envs[0].sd[:envs[0].ns, i], envs[1].sd[:envs[1].ns, i], 1, what=f"ros4l vs rodas4 env{i} step{s}")
+
+
 @pytest.mark.parametrize("model_type", ["model_1", "model_2"])
 def test_trajectory_vs_tight_oracle(model_type):
     ev = H.random_events(7)
