@@ -89,6 +89,7 @@ SIGNATURES = {
     "pvder_env_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
     "pvder_env_kernel_ms": (C.c_int, [_vp, C.POINTER(_dbl), C.POINTER(_i64)]),
     "pvder_env_pipeline_info": (C.c_int, [_vp, C.POINTER(C.c_int32), C.POINTER(_dbl)]),
+    "pvder_plan_chunks": (C.c_int, [_i64, _dbl, C.POINTER(_i64)]),
     "pvder_host_alloc": (_vp, [C.c_size_t]),
     "pvder_host_free": (None, [_vp]),
 }

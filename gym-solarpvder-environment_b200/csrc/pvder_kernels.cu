@@ -909,6 +909,37 @@ int pvder_env_reset_host(pvder_env* h, float* obs_out, double* obs64_out) {
   return PVDER_OK;
 }
 
+// Chunk plan of the host-buffer step for a batch of `units` quarter waves: sizes[0] = 4 (one wave), then up to 11
+// chunks shrinking geometrically by q (as many as keep the smallest >= 1 unit; the bulk chunk absorbs the rounding).
+// Fewer than 24 units: one chunk.  Pure host arithmetic (exported so that it can be checked without a GPU).
+int pvder_plan_chunks(int64_t units, double q, int64_t* sizes) {
+  if (units < 24) {
+    sizes[0] = units;
+    return 1;
+  }
+  if (!(q >= 0.3)) q = 0.3;
+  if (q > 0.9) q = 0.9;
+  const int64_t R = units - 4;                     // what follows the first chunk
+  for (int m = PVDER_MAX_CHUNKS - 1; m >= 2; --m) {
+    const double s1 = (double)R * (1.0 - q) / (1.0 - std::pow(q, m));
+    if (s1 * std::pow(q, m - 1) < 1.0) continue;   // smallest chunk below one unit: fewer chunks
+    int64_t used = 0;
+    for (int c = m - 1; c >= 1; --c) {             // from the smallest up
+      int64_t w = (int64_t)(s1 * std::pow(q, c) + 0.5);
+      if (w < 1) w = 1;
+      sizes[1 + c] = w;
+      used += w;
+    }
+    if (R - used < sizes[2]) continue;             // rounding ate the bulk chunk: fewer chunks
+    sizes[0] = 4;
+    sizes[1] = R - used;
+    return m + 1;
+  }
+  sizes[0] = 4;
+  sizes[1] = R;
+  return 2;
+}
+
 int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
                         uint8_t* done_out) {
   if (!h || !action) return PVDER_ERR_INVALID;
@@ -922,40 +953,12 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
   // the previous calls (events around the bulk chunk's copies against the kernel span) -- it depends on the model,
   // on n_sim and on how many ranks share the host's memory system -- and is kept within [0.3, 0.9].
   int64_t start[PVDER_MAX_CHUNKS + 1];
-  int chunks = 0;
-  start[0] = 0;
+  int64_t size[PVDER_MAX_CHUNKS];
   const int64_t unit = h->wave_envs / 4;
-  const int64_t units = h->n / unit;
-  if (h->n < (1 << 16) || units < 24) {
-    start[1] = h->n;
-    chunks = 1;
-  } else {
-    const double q = h->copy_ratio;
-    const int64_t R = units - 4;                   // what follows the first chunk (4 units)
-    int m = PVDER_MAX_CHUNKS - 1;                  // geometric chunks: as many as keep the last one >= 1 unit
-    double s1 = 0.0;
-    for (; m > 1; --m) {
-      s1 = (double)R * (1.0 - q) / (1.0 - std::pow(q, m));
-      if (s1 * std::pow(q, m - 1) >= 1.0) break;
-    }
-    if (m <= 1) s1 = (double)R;
-    int64_t size[PVDER_MAX_CHUNKS];
-    int64_t used = 0;
-    for (int c = m - 1; c >= 1; --c) {             // from the smallest up; the bulk takes what rounding leaves
-      int64_t w = (int64_t)(s1 * std::pow(q, c) + 0.5);
-      if (w < 1) w = 1;
-      size[c] = w;
-      used += w;
-    }
-    size[0] = R - used;
-    int64_t pos = 4 * unit;
-    start[++chunks] = pos;                         // first chunk: one wave
-    for (int c = 0; c < m; ++c) {
-      pos += size[c] * unit;
-      start[++chunks] = pos;
-    }
-    start[chunks] = h->n;                          // the last chunk also takes the remainder (< 1 unit)
-  }
+  const int chunks = pvder_plan_chunks(h->n < (1 << 16) ? 0 : h->n / unit, h->copy_ratio, size);
+  start[0] = 0;
+  for (int c = 0; c < chunks; ++c) start[c + 1] = start[c] + size[c] * unit;
+  start[chunks] = h->n;                            // the last chunk also takes the remainder (< 1 unit)
   // Submission order: the first chunk's action copy and kernel go out before anything else is enqueued (the GPU
   // starts ~10 us into the call instead of after ~100 API calls); the action copies of the other chunks follow at
   // once -- they are small (4 B/env) and run ahead of the kernels on their own stream.

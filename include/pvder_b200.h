@@ -197,6 +197,9 @@ int pvder_env_kernel_ms(pvder_env* env, double* ms_total, int64_t* launches);
 /* Host-buffer pipeline of pvder_env_step_host: chunks of the last call and the running estimate of
    (device->host copy time) / (kernel time) per env that sizes them. */
 int pvder_env_pipeline_info(pvder_env* env, int32_t* chunks, double* copy_ratio);
+/* The chunk plan pvder_env_step_host uses for a batch of `units` quarter waves of resident CTAs and a copy/kernel
+   time ratio q: writes up to 12 chunk sizes (in units), returns their number.  Pure host arithmetic. */
+int pvder_plan_chunks(int64_t units, double q, int64_t* sizes);
 void* pvder_host_alloc(size_t bytes);   /* pinned host memory */
 void pvder_host_free(void* p);
 

@@ -178,3 +178,24 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_host_buffer_chunk_plan_invariants():
+    """pvder_plan_chunks (pure host arithmetic behind pvder_env_step_host): the plan covers the batch exactly, starts with a
+    one-wave chunk, never has more than 12 chunks or a chunk below one unit, puts the largest chunk second and shrinks
+    from there by about the requested copy/kernel time ratio."""
+    import ctypes as C
+    from gym_pvder_b200 import _cabi
+    lib = _cabi.load()
+    sizes = (C.c_int64 * 12)()
+    assert lib.pvder_plan_chunks(0, 0.5, sizes) == 1 and sizes[0] == 0          # small batches: one launch
+    assert lib.pvder_plan_chunks(23, 0.5, sizes) == 1 and sizes[0] == 23
+    for units in list(range(24, 400)) + [1000, 4321, 100000]:
+        for q in (0.0, 0.3, 0.41, 0.5, 0.66, 0.8, 0.9, 1.7, float("nan")):
+            m = lib.pvder_plan_chunks(units, q, sizes)
+            s = [sizes[i] for i in range(m)]
+            assert 2 <= m <= 12 and sum(s) == units and s[0] == 4 and min(s) >= 1, (units, q, s)
+            assert all(s[i] >= s[i + 1] for i in range(1, m - 1)), (units, q, s)
+    m = lib.pvder_plan_chunks(110, 0.66, sizes)                                  # 1 Mi single-phase envs on a B200
+    s = [sizes[i] for i in range(m)]
+    assert m >= 9 and all(abs(s[i + 1] / s[i] - 0.66) < 0.2 for i in range(1, 6)), s
