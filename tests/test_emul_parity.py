@@ -170,6 +170,33 @@ def test_trajectory_vs_tight_oracle(model_type):
 
 
 @pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_n1_observations_two_substeps_after_steps_in_the_inputs(model_type):
+    """n_sim_time_steps_per_env_step = 1: every observation is taken only two half-cycle sub-steps after an action, and the
+    events at t = 1, 2, 3 s land right before one.  This is the hardest case for a Rosenbrock scheme that is not stiffly
+    accurate (ROS4-L): the stiff current modes are excited by the step and must be gone two steps later.  200 env
+    steps with random actions, sags to 0.90 pu and insolation steps against the tight oracle, same tolerances (PLL
+    pull-in, the first 0.25 s, excluded as everywhere), integer rewards equal throughout."""
+    import random
+    ev = H.random_events(11)
+    em = E.EmulVecEnv(1, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True,
+                      n_sim_time_steps_per_env_step=1, max_sim_time=4.0)
+    em.set_event_tables(*H.oracle_tables(ev, em.cfg.c))
+    orc = OraclePVDEREnv(model_type=model_type, solver="tight", events=ev, DISCRETE_REWARD=True,
+                         n_sim_time_steps_per_env_step=1, max_sim_time=4.0)
+    em.reset()
+    orc.reset()
+    rng = random.Random(5)
+    for s in range(200):
+        a = rng.randrange(5)
+        oo, orw, od, _ = orc.step(a)
+        eo, erw, ed, _ = em.step([a])
+        assert orw == erw[0] and od == ed[0]
+        if s >= 15:
+            np.testing.assert_allclose(eo[0], oo, rtol=H.RTOL, atol=H.ATOL, err_msg=f"step {s}")
+            H.assert_state_close(em.sd[:orc.model.n, 0], H.oracle_delta_state(orc), em.cfg.phases, what=f"{model_type} step {s}")
+
+
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
 def test_golden_fixture(model_type):
     gold = np.load(f"tests/golden/golden_{model_type}.npz")
     acts = gold["actions"]
