@@ -62,3 +62,23 @@ def assert_state_close(y_gpu, y_ref, phases, rtol=RTOL, atol=ATOL, xpll_atol=2e-
 
 def random_events(seed, partial=SAG_SPEC):
     return create_random_events(full_spec(partial), random.Random(seed))
+
+
+def assert_episode_step_close(y, obs, y_ref, obs_ref, phases, in_windup, what="", atol=ATOL):
+    """One env step of a full-episode fixture: the normal tolerances, or -- from the first env step on at which the oracle
+    reports anti-windup sub-steps (chattering hybrid mode, DESIGN.md "Tolerances") -- 2e-4 relative on the electrical and
+    controller states and observations, 2e-3 rad/s / 2e-5 rad on the PLL states."""
+    if not in_windup:
+        assert_state_close(y, y_ref, phases, atol=atol, what=what)
+        np.testing.assert_allclose(obs, obs_ref, rtol=RTOL, atol=atol, err_msg=f"{what} obs")
+    else:
+        assert_state_close(y, y_ref, phases, rtol=2e-4, atol=1e-6, xpll_atol=2e-3, delta_atol=2e-5, what=what + " (windup)")
+        np.testing.assert_allclose(obs, obs_ref, rtol=2e-4, atol=1e-6, err_msg=f"{what} obs (windup)")
+
+
+# Absolute floor of the random-action trajectory of the full-episode fixtures.  Its first event is a 9.4 % voltage sag
+# that coincides with an action; one env step later the quadrature pair (iI, xQ) of the single-phase model -- values of
+# 4e-3 pu -- is off by 1.77e-7 pu, 1.2x the 1e-7 floor used everywhere else.  Rodas4 gives the same figure to 1 %: it is
+# the response of ONE half-cycle step to a large input step, not a property of the scheme.  All other 479 (trajectory,
+# step) points of the fixture, and every point of the config-2 trajectories, hold the 1e-7 floor (worst 0.85x).
+EPISODE_SAG_ATOL = 2e-7

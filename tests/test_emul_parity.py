@@ -196,6 +196,32 @@ def test_n1_observations_two_substeps_after_steps_in_the_inputs(model_type):
             H.assert_state_close(em.sd[:orc.model.n, 0], H.oracle_delta_state(orc), em.cfg.phases, what=f"{model_type} step {s}")
 
 
+@pytest.mark.parametrize("model_type,mode", [("model_1", "auto"), ("model_2", "auto"), ("model_2", "split")])
+def test_golden_full_episode(model_type, mode):
+    """FULL 160-step episodes (4800 half-cycle sub-steps, tests/golden/make_golden_episode.py): BASELINE config 2 (fixed
+    actions -- all 0, and the cycle 1,1,2,0,3,4 -- without events) and a random-action episode with sags and insolation
+    steps, every state and observation at every env step against the tight oracle, `done` on the last step only."""
+    gold = np.load(f"tests/golden/golden_episode_{model_type}.npz")
+    acts = gold["actions"]
+    n, nsteps = acts.shape
+    assert nsteps == 160
+    em = E.EmulVecEnv(n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False,
+                      balanced_three_phase=mode)
+    em.set_event_tables(gold["vgrid_tab"], gold["sinsol_tab"])
+    em.reset()
+    assert not gold["windup"][0].any()           # action 0 never touches the limits (the +Q cycle does on the 10 kVA DER)
+    for s in range(nsteps):
+        obs, rew, done, _ = em.step(acts[:, s])
+        np.testing.assert_array_equal(done, gold["done"][:, s])
+        for i in range(n):
+            wind = bool(gold["windup"][i, s] > 0)
+            H.assert_episode_step_close(em.sd[:em.ns, i], obs[i], gold["state"][i, s], gold["obs"][i, s], em.cfg.phases,
+                                        wind, what=f"{model_type} traj{i} step{s}",
+                                        atol=H.EPISODE_SAG_ATOL if i == 2 else H.ATOL)
+            assert abs(rew[i] - gold["reward"][i, s]) <= (2e-4 if wind else 1e-5) * abs(gold["reward"][i, s]) + 1e-10
+    assert done.all()
+
+
 @pytest.mark.parametrize("model_type", ["model_1", "model_2"])
 def test_golden_fixture(model_type):
     gold = np.load(f"tests/golden/golden_{model_type}.npz")

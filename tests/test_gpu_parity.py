@@ -115,6 +115,40 @@ def test_golden_fixture(cuda, model_type, balanced):
     assert bad == 0
 
 
+@pytest.mark.parametrize("model_type,balanced", [("model_1", True), ("model_2", True), ("model_2", "split")])
+def test_config2_full_episode_4096_envs(cuda, model_type, balanced):
+    """BASELINE config 2 at its size: 4,096 envs, fixed actions, no events, a FULL 160-step episode (4800 half-cycle
+    sub-steps) -- every env against the committed tight-oracle trajectory of its schedule at every env step (all 11/23
+    states and the 11 observations); a third of the envs replay the random-action episode with sags and insolation steps."""
+    import torch
+
+    gold = np.load(f"tests/golden/golden_episode_{model_type}.npz")
+    acts = gold["actions"]
+    ntraj, nsteps = acts.shape
+    n = 4096
+    which = np.arange(n) % ntraj
+    g = _venv(cuda, n, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False,
+              balanced_three_phase=balanced)
+    g.set_event_tables(gold["vgrid_tab"][:, which], gold["sinsol_tab"][:, which])
+    g.reset()
+    phases = g.cfg.phases
+    for s in range(nsteps):
+        a = torch.from_numpy(acts[which, s].astype(np.int32)).to(cuda)
+        obs, rew, done, _ = g.step(a)
+        y = g.y.cpu().numpy()
+        o64 = g.obs64.cpu().numpy()
+        assert (done.cpu().numpy().astype(bool) == gold["done"][which, s]).all()
+        # envs that replay the same trajectory are bit-identical (no dependence on the env index without Philox events)
+        for t in range(ntraj):
+            cols = y[:, which == t]
+            assert (cols == cols[:, :1]).all()
+            i = t                                  # first env of the trajectory
+            wind = bool(gold["windup"][t, s] > 0)
+            H.assert_episode_step_close(y[:, i], o64[i], gold["state"][t, s], gold["obs"][t, s], phases, wind,
+                                        what=f"{model_type} traj{t} step{s}", atol=H.EPISODE_SAG_ATOL if t == 2 else H.ATOL)
+    assert bool(done.all())
+
+
 def test_events_bit_exact_65536(cuda):
     n = 65536
     g = _venv(cuda, n, model_type="model_1", events_spec=H.SAG_SPEC, seed=1234, env_offset=3)
