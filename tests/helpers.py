@@ -80,5 +80,5 @@ def assert_episode_step_close(y, obs, y_ref, obs_ref, phases, in_windup, what=""
 # that coincides with an action; one env step later the quadrature pair (iI, xQ) of the single-phase model -- values of
 # 4e-3 pu -- is off by 1.77e-7 pu, 1.2x the 1e-7 floor used everywhere else.  Rodas4 gives the same figure to 1 %: it is
 # the response of ONE half-cycle step to a large input step, not a property of the scheme.  All other 479 (trajectory,
-# step) points of the fixture, and every point of the config-2 trajectories, hold the 1e-7 floor (worst 0.85x).
+# step) points of the fixture, and every point of the config-2 trajectories, hold the 1e-7 floor (worst 0.66x).
 EPISODE_SAG_ATOL = 2e-7
