@@ -22,7 +22,6 @@ lib = f"/tmp/libpvder_emul_s{scheme}.so"
 subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                 f"-DPVDER_SCHEME={scheme}", "-o", lib, E._SRC], check=True)
 E._lib = C.CDLL(lib)
-E._declare(E._lib) if hasattr(E, "_declare") else None
 
 gold = np.load(f"tests/golden/golden_{model_type}.npz")
 acts = gold["actions"]
