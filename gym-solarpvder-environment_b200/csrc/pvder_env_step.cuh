@@ -28,6 +28,9 @@ namespace pvder {
 #ifndef PVDER_FOLD
 #define PVDER_FOLD 1   // Rodas4: fold K1..K4 into the stage-5/6 sums early: same FMAs, 2 fewer live vectors (B200: 3.11 -> 3.04 ms)
 #endif
+#ifndef PVDER_REFINE_INPUT_STEP
+#define PVDER_REFINE_INPUT_STEP 0   // 1: the half-cycle sub-step that follows a change of the inputs (action != 0, event) is taken as two
+#endif                              //    half-size steps (one-thread kernels; DESIGN.md "Input-step refinement": study, off)
 #ifndef PVDER_FREE_PATH
 #define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the stepper core, chosen per warp (experiment)
 #endif
@@ -53,10 +56,9 @@ struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant 
 };
 
 template <class M>
-inline RodasTab make_rodas_tab(const Params& par, double hinv) {
+PVDER_HD RodasTab make_rodas_tab(const Params& par, double hinv) {
   static_assert(M::N_LUC <= 16, "luc table too small");
-  RodasTab t;
-  std::memset(&t, 0, sizeof(t));
+  RodasTab t = {};
 #if PVDER_SCHEME == 4
   t.a21 = 0.2000000000000000e+01;
   t.a31 = 0.1867943637803922e+01; t.a32 = 0.2344449711399156e+00;
@@ -398,6 +400,16 @@ PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in,
   return true;
 }
 
+#if PVDER_REFINE_INPUT_STEP
+// One step of size 1/hinv2 with its own coefficient table, out of line (the hot loop keeps its constant-bank table).
+template <class M>
+PVDER_NOINLINE StepState<M> ros_refined(StepState<M> s, const Params* par, Inputs in, double hinv2, unsigned frz) {
+  const RodasTab th = make_rodas_tab<M>(*par, hinv2);
+  ros_step<M>(s.y, *par, in, th, frz, s.base);
+  return s;
+}
+#endif
+
 // pvder's clamping test np.sign(a) == np.sign(b)
 PVDER_DEV bool same_sign(double a, double b) {
   const int sa = (a > 0.0) - (a < 0.0);
@@ -723,6 +735,11 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
     const int total = cfg.n_sub_per_step * cfg.micro;
     int m_left = cfg.micro, s = 0;
     bool clamped = false;
+#if PVDER_REFINE_INPUT_STEP
+    // the inputs change at the start of this env step when the action moves a reference or an event instant falls on it
+    bool refine = act != 0 || (r.k >= cfg.ev_start_k && (r.k - cfg.ev_start_k) % cfg.ev_step_k == 0 &&
+                               (r.k - cfg.ev_start_k) / cfg.ev_step_k < cfg.ev_count);
+#endif
     for (int it = 0; it < total; ++it) {
       bool m_over;
       const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
@@ -730,6 +747,26 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
       // the duty-cycle clamp acts on Re/Im parts per phase and would break the symmetry the
       // balanced representation relies on: report instead of integrating something else
       if (M::BALANCED3 && m_over) r.status = PVDER_STATUS_UNBALANCED;
+#if PVDER_REFINE_INPUT_STEP
+      if (refine) {
+        // two half-size steps; the clamp mode is re-sampled in between like at every other step
+        refine = false;
+        const double hinv2 = 2.0 * cfg.substeps_per_sec * (double)cfg.micro;
+        StepState<M> st;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) st.y[i] = r.y[i];
+        st.base = base;
+        st = ros_refined<M>(st, &par, in, hinv2, frz);
+        bool m_over2;
+        const unsigned frz2 = freeze_bits<M>(st.y, par, in, m_over2);
+        clamped |= frz2 != 0u;
+        if (M::BALANCED3 && m_over2) r.status = PVDER_STATUS_UNBALANCED;
+        st = ros_refined<M>(st, &par, in, hinv2, frz2);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) r.y[i] = st.y[i];
+        base = st.base;
+      } else
+#endif
       if (!ros_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
       if (--m_left != 0) continue;
       // half-cycle boundary
@@ -744,6 +781,9 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
         in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
         j_next += 1;
         next_k += cfg.ev_step_k;
+#if PVDER_REFINE_INPUT_STEP
+        refine = true;
+#endif
       }
     }
     bool finite = true;

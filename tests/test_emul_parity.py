@@ -222,6 +222,31 @@ def test_golden_full_episode(model_type, mode):
     assert done.all()
 
 
+def test_input_step_refinement_build_holds_the_floor_everywhere(tmp_path):
+    """-DPVDER_REFINE_INPUT_STEP=1 (study build, off in the product: DESIGN.md open items): with the sub-step after an
+    action or event taken as two half-size steps, the single-phase full-episode fixture holds the standard 1e-7 floor
+    on every trajectory -- including the random/sag one that needs EPISODE_SAG_ATOL in the product build -- and the
+    anti-windup sub-step count of the +Q cycle still equals the oracle's."""
+    import ctypes as C
+    import subprocess
+    lib = str(tmp_path / "libpvder_emul_refine.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
+                    "-DPVDER_REFINE_INPUT_STEP=1", "-o", lib, E._SRC], check=True)
+    gold = np.load("tests/golden/golden_episode_model_1.npz")
+    acts = gold["actions"]
+    n, nsteps = acts.shape
+    em = E.EmulVecEnv(n, model_type="model_1", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False)
+    em.lib = C.CDLL(lib)
+    em.set_event_tables(gold["vgrid_tab"], gold["sinsol_tab"])
+    em.reset()
+    for s in range(nsteps):
+        obs, rew, done, _ = em.step(acts[:, s])
+        for i in range(n):
+            H.assert_state_close(em.sd[:em.ns, i], gold["state"][i, s], 1, what=f"refined traj{i} step{s}")
+            np.testing.assert_allclose(obs[i], gold["obs"][i, s], rtol=H.RTOL, atol=H.ATOL)
+    assert int(em.si[10, 1]) == int(gold["windup"][1, -1]) > 0
+
+
 @pytest.mark.parametrize("model_type", ["model_1", "model_2"])
 def test_golden_fixture(model_type):
     gold = np.load(f"tests/golden/golden_{model_type}.npz")
