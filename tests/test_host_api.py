@@ -180,6 +180,28 @@ def test_bench_reference_arm_contract():
     assert "workload" in d["config"]
 
 
+def test_bench_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches the reference arm like the GPU arm (torchrun, one rank per GPU): rank 0 alone runs and prints
+    the ONE JSON line, the other ranks exit 0 without work; nothing else reaches stdout."""
+    import json
+    import socket
+    import subprocess
+    import sys
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
 def test_host_buffer_chunk_plan_invariants():
     """pvder_plan_chunks (pure host arithmetic behind pvder_env_step_host): the plan covers the batch exactly, starts with a
     one-wave chunk, never has more than 12 chunks or a chunk below one unit, puts the largest chunk second and shrinks
