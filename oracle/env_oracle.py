@@ -15,6 +15,10 @@ Two integrator tiers:
   solver="tight": LSODA at rtol=1e-11/atol=1e-12 per half-cycle piece with the
       event values and anti-windup mode sampled at the piece start -- the
       numerical truth the CUDA trajectories are compared against.
+  solver="ros4l": the fixed-step twin of the kernel's integrator: ONE step of the 4-stage
+      L-stable Rosenbrock method ROS4-L (Hairer & Wanner, Solving ODEs II, IV.7) per half-cycle piece, on this
+      file's model with a dense numpy solve -- an independent implementation of the scheme the kernel codes with a
+      generated sparse LU and incremental side-inputs; the kernel source must agree with it to ~1e-10.
 """
 from __future__ import annotations
 
@@ -196,6 +200,10 @@ class OraclePVDEREnv:
             if any(mask):
                 self.windup_substeps += 1
             inp = self._inputs(t0, freeze=mask)
+            if self.solver == "ros4l":
+                self.y = ros4l_step(m, inp, self.y, t0, t1 - t0)
+                self.k += 1
+                continue
             sol, info = odeint(lambda y, t: m.rhs(y, t, inp), self.y, [t0, t1],
                                Dfun=lambda y, t: m.jac(y, t, inp), full_output=1, mxstep=200000,
                                atol=1e-12, rtol=1e-11)
@@ -216,6 +224,38 @@ class OraclePVDEREnv:
         out = self.model.outputs(self.y, self._inputs(self.t()))
         return (out["iaR"], out["iaI"], out["vaR"], out["vaI"], out["P_PCC"], out["Q_PCC"],
                 out["Vdc"], out["Ppv"], self.Vdc_ref, self.Q_ref, self.t() / self.max_sim_time)
+
+
+# ROS4-L in the transformed form (I/(h g) - J) K_i = f(Y_i) + sum_j c_ij/h K_j, Y_i = y + sum_j a_ij K_j,
+# y+ = y + sum_i m_i K_i; stage 4 is evaluated at Y_3 (coefficients: Hairer & Wanner's ROS4 code, "L-stable" set).
+ROS4L_GAMMA = 0.57282
+ROS4L_A = ((), (2.0,), (0.1867943637803922e+01, 0.2344449711399156e+00), (0.1867943637803922e+01, 0.2344449711399156e+00))
+ROS4L_C = ((), (-0.7137615036412310e+01,), (0.2580708087951457e+01, 0.6515950076447975e+00),
+           (-0.2137148994382534e+01, -0.3214669691237626e+00, -0.6949742501781779e+00))
+ROS4L_M = (0.2255570073418735e+01, 0.2870493262186792e+00, 0.4353179431840180e+00, 0.1093502252409163e+01)
+
+
+def ros4l_step(model, inp, y, t0, h):
+    """One ROS4-L step of size h from (t0, y) with the inputs `inp` frozen.  The model's last state is the PLL angle
+    wte; the step is taken on the autonomous form delta = wte - w_grid t, like the kernel's."""
+    n = model.n
+    w = 2.0 * math.pi * 60.0
+    ya = np.array(y, dtype=float)
+    ya[n - 1] -= w * t0
+
+    def f(z):
+        d = np.array(model.rhs(list(z), 0.0, inp), dtype=float)
+        d[n - 1] -= w
+        return d
+
+    W = np.eye(n) / (h * ROS4L_GAMMA) - np.array(model.jac(list(ya), 0.0, inp), dtype=float)
+    K = []
+    for i in range(4):
+        Y = ya + sum(a * k for a, k in zip(ROS4L_A[i], K))
+        K.append(np.linalg.solve(W, f(Y) + sum((c / h) * k for c, k in zip(ROS4L_C[i], K))))
+    out = ya + sum(mi * k for mi, k in zip(ROS4L_M, K))
+    out[n - 1] += w * (t0 + h)
+    return out
 
 
 def reward_from_outputs(out, goal, discrete, Q_ref, params):

@@ -93,6 +93,32 @@ def test_freeze_mask_matches_oracle(model_type):
     assert seen == {True, False}
 
 
+@pytest.mark.parametrize("model_type", ["model_1", "model_2"])
+def test_kernel_source_equals_the_numpy_ros4l_twin(model_type):
+    """SURVEY 8c's third oracle tier: an independent numpy implementation of the kernel's scheme (one ROS4-L step per
+    half-cycle on the ORACLE's model, dense solve, library sin/cos/exp: oracle/env_oracle.py solver="ros4l") against
+    the kernel source (generated model code, symbolic sparse LU, unit-pivot rows, incremental side-inputs, stage
+    re-use).  24 env steps = 720 sub-steps with a sag, insolation steps and a +Q policy that drives the single-phase DER
+    into anti-windup: same clamp decisions, same integer rewards, states within 5e-9 -- four orders below the
+    integrator's own accuracy, so a coefficient or scaling slip in the stepper cannot hide behind the 1e-5 tolerances."""
+    ev = H.random_events(7)
+    orc = OraclePVDEREnv(model_type=model_type, solver="ros4l", events=ev, DISCRETE_REWARD=True)
+    em = E.EmulVecEnv(1, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True)
+    em.set_event_tables(*H.oracle_tables(ev, em.cfg.c))
+    em.reset()
+    orc.reset()
+    for a in [3, 1, 0, 4, 2] + [1] * 19:
+        oo, orw, od, _ = orc.step(a)
+        eo, erw, ed, _ = em.step([a])
+        assert orw == erw[0] and od == ed[0]
+        y, yr = em.sd[:orc.model.n, 0], H.oracle_delta_state(orc)
+        np.testing.assert_allclose(y, yr, rtol=5e-9, atol=5e-12)
+        np.testing.assert_allclose(eo[0], oo, rtol=5e-9, atol=5e-12)
+    assert int(em.si[10, 0]) == orc.windup_substeps
+    if model_type == "model_1":
+        assert orc.windup_substeps > 0
+
+
 def test_compiled_tableau_satisfies_the_order_conditions():
     """Known-answer test of the integrator: the coefficients the kernels are compiled with (ROS4-L, Hairer & Wanner IV.7)
     satisfy all eight Rosenbrock order conditions up to order 4 (table 7.1 there) and give R(inf) = 0 (L-stability) to
