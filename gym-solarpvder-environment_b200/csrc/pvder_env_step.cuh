@@ -30,7 +30,8 @@ namespace pvder {
 #endif
 #ifndef PVDER_REFINE_INPUT_STEP
 #define PVDER_REFINE_INPUT_STEP 0   // 1: the half-cycle sub-step that follows a change of the inputs (action != 0, event) is taken as two
-#endif                              //    half-size steps (one-thread kernels; DESIGN.md "Input-step refinement": study, off)
+#endif                              //    half-size steps with a second coefficient table (one-thread kernels; DESIGN.md "Input-step
+                                    //    refinement": study build, off)
 #ifndef PVDER_FREE_PATH
 #define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the stepper core, chosen per warp (experiment)
 #endif
@@ -39,7 +40,8 @@ constexpr double RG = 0.57282;
 #else
 constexpr double RG = 0.25;
 #endif
-struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant bank
+template <int TAG>
+struct RodasCoefT {   // a_ij and c_ij/h, read by DFMA straight from the constant bank
   double a21, a31, a32, a41, a42, a43, a51, a52, a53, a54;
   double c21, c31, c32, c41, c42, c43, c51, c52, c53, c54, c61, c62, c63, c64, c65;
   double ghinv;     // 1/(h*gamma)
@@ -54,11 +56,18 @@ struct RodasTab {   // a_ij and c_ij/h, read by DFMA straight from the constant 
   double m1, m2, m3, m4;
   double d41, d42, ds41, ds42;
 };
+using RodasHalf = RodasCoefT<1>;
+// The kernels' coefficient table (a __grid_constant__ launch parameter); the study build with input-step refinement
+// carries a second set for steps of h/2.
+struct RodasTab : RodasCoefT<0> {
+#if PVDER_REFINE_INPUT_STEP
+  RodasHalf half;
+#endif
+};
 
-template <class M>
-PVDER_HD RodasTab make_rodas_tab(const Params& par, double hinv) {
+template <class M, class T>
+PVDER_HD void fill_rodas(T& t, const Params& par, double hinv) {
   static_assert(M::N_LUC <= 16, "luc table too small");
-  RodasTab t = {};
 #if PVDER_SCHEME == 4
   t.a21 = 0.2000000000000000e+01;
   t.a31 = 0.1867943637803922e+01; t.a32 = 0.2344449711399156e+00;
@@ -95,6 +104,15 @@ PVDER_HD RodasTab make_rodas_tab(const Params& par, double hinv) {
   t.du_frz = hg;
   for (int i = 0; i < 16; ++i) t.luc[i] = 0.0;
   M::lu_consts(par, t.ghinv, t.luc);
+}
+
+template <class M>
+PVDER_HD RodasTab make_rodas_tab(const Params& par, double hinv) {
+  RodasTab t = {};
+  fill_rodas<M>(t, par, hinv);
+#if PVDER_REFINE_INPUT_STEP
+  fill_rodas<M>(t.half, par, 2.0 * hinv);
+#endif
   return t;
 }
 
@@ -161,8 +179,8 @@ PVDER_DEV void aux_advance(const Params& par, const Inputs& in, const Aux& b, do
 // Effective gains of the freezable rows (bit order of freeze_bits): the parameter, or 0 while the row is
 // clamped; the unit-pivot rows (x, xDC, xQ) carry theirs pre-scaled by h*gamma, and gn[NFRZ] is the scaled
 // Ki_PLL.  Computed once per sub-step; the generated RHS/Jacobian take them as inputs.
-template <class M>
-PVDER_DEV void make_gains(const Params& par, const RodasTab& tab, unsigned frz, double (&gn)[M::NGAIN]) {
+template <class M, class TAB>
+PVDER_DEV void make_gains(const Params& par, const TAB& tab, unsigned frz, double (&gn)[M::NGAIN]) {
 #pragma unroll
   for (int k = 0; k < M::PHASES; ++k) {
     gn[4 * k] = (frz & (1u << (4 * k))) ? 0.0 : tab.kx;
@@ -195,8 +213,8 @@ PVDER_DEV unsigned opaque_bits(unsigned v) {
 // Returns false (y, base untouched) when EXACT == false and a stage left the incremental range.
 // FREE: no clamp is active (frz == 0 in every lane that takes this instantiation): the effective gains are
 // the parameters themselves, read from the constant bank instead of occupying registers.
-template <class M, bool EXACT, bool FREE = false>
-PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
+template <class M, bool EXACT, bool FREE = false, class TAB>
+PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in, const TAB& tab,
                            unsigned frz, Aux& base) {
   double gn[M::NGAIN];
   make_gains<M>(par, tab, FREE ? 0u : frz, gn);
@@ -362,14 +380,14 @@ struct StepState {
   double y[M::NS];
   Aux base;
 };
-template <class M>
-PVDER_NOINLINE StepState<M> ros_exact(StepState<M> s, const Params* par, Inputs in, const RodasTab* tab, unsigned frz) {
+template <class M, class TAB>
+PVDER_NOINLINE StepState<M> ros_exact(StepState<M> s, const Params* par, Inputs in, const TAB* tab, unsigned frz) {
   ros_core<M, true>(s.y, *par, in, *tab, frz, s.base);
   return s;
 }
 
-template <class M>
-PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in, const RodasTab& tab,
+template <class M, class TAB>
+PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in, const TAB& tab,
                            unsigned frz, Aux& base) {
   // One instantiation serves clamped and unclamped envs (the clamp enters through the per-row
   // effective gains): with a random policy two thirds of the warps hold a clamped lane late in an
@@ -399,16 +417,6 @@ PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in,
   }
   return true;
 }
-
-#if PVDER_REFINE_INPUT_STEP
-// One step of size 1/hinv2 with its own coefficient table, out of line (the hot loop keeps its constant-bank table).
-template <class M>
-PVDER_NOINLINE StepState<M> ros_refined(StepState<M> s, const Params* par, Inputs in, double hinv2, unsigned frz) {
-  const RodasTab th = make_rodas_tab<M>(*par, hinv2);
-  ros_step<M>(s.y, *par, in, th, frz, s.base);
-  return s;
-}
-#endif
 
 // pvder's clamping test np.sign(a) == np.sign(b)
 PVDER_DEV bool same_sign(double a, double b) {
@@ -749,22 +757,21 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
       if (M::BALANCED3 && m_over) r.status = PVDER_STATUS_UNBALANCED;
 #if PVDER_REFINE_INPUT_STEP
       if (refine) {
-        // two half-size steps; the clamp mode is re-sampled in between like at every other step
+        // two half-size steps with the h/2 table (its own inlined copy of the step body, executed about once per env
+        // step: the hot path below keeps its code and its constant-bank operands); the clamp mode is re-sampled in
+        // between like at every other step
         refine = false;
-        const double hinv2 = 2.0 * cfg.substeps_per_sec * (double)cfg.micro;
-        StepState<M> st;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) st.y[i] = r.y[i];
-        st.base = base;
-        st = ros_refined<M>(st, &par, in, hinv2, frz);
-        bool m_over2;
-        const unsigned frz2 = freeze_bits<M>(st.y, par, in, m_over2);
-        clamped |= frz2 != 0u;
-        if (M::BALANCED3 && m_over2) r.status = PVDER_STATUS_UNBALANCED;
-        st = ros_refined<M>(st, &par, in, hinv2, frz2);
-#pragma unroll
-        for (int i = 0; i < NS; ++i) r.y[i] = st.y[i];
-        base = st.base;
+        unsigned f2 = frz;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          if (hh) {
+            bool m_over2;
+            f2 = freeze_bits<M>(r.y, par, in, m_over2);
+            clamped |= f2 != 0u;
+            if (M::BALANCED3 && m_over2) r.status = PVDER_STATUS_UNBALANCED;
+          }
+          if (!ros_step<M>(r.y, par, in, tab.half, f2, base)) r.exact += 1;
+        }
       } else
 #endif
       if (!ros_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
