@@ -213,6 +213,8 @@ def main():
                     help="model_2 general/split only: grid magnitude of phases b, c relative to phase a")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (0: min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg", action="append", default=[], metavar="KEY=VALUE",
+                    help="EnvConfig override for kernel studies (e.g. --cfg refine_input_level=0); recorded in config")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -264,9 +266,16 @@ def main():
 
     n = args.envs_per_gpu
     K, Wm = args.steps, args.warmup
+    overrides = {}
+    for kv in args.cfg:
+        key, _, val = kv.partition("=")
+        overrides[key] = json.loads(val)
+    if overrides:
+        config["config_overrides"] = overrides
     cfg = G.EnvConfig(model_type=args.model, n_sim_time_steps_per_env_step=args.n_sim, max_sim_time=40.0,
                       DISCRETE_REWARD=False, goals_list=["voltage_regulation"], event_mode="philox", seed=2026,
-                      auto_reset=True, balanced_three_phase=args.three_phase_mode, grid_unbalance_ratio=tuple(args.grid_unbalance))
+                      auto_reset=True, balanced_three_phase=args.three_phase_mode, grid_unbalance_ratio=tuple(args.grid_unbalance),
+                      **overrides)
     fkey = "model_2_balanced" if (args.model == "model_2" and args.three_phase_mode in ("auto", "balanced")) else args.model
     env = G.PVDERVecEnv(n, device=dev, env_offset=rank * n, config=cfg)
     env.reset()

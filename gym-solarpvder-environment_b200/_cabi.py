@@ -17,12 +17,14 @@ SOURCES = ["pvder_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-diag-suppress", "177", "-shared", "-Xcompiler", "-fPIC"]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_STATES = 23
 OBS_DIM = 11
 N_ACTIONS = 5
+FINE_LEVELS = 3
 SI_K, SI_STEPS, SI_EPISODE, SI_STATUS, SI_DONE, SI_HIST, SI_WINDUP, SI_EXACT, SI_FIELDS = 0, 1, 2, 3, 4, 5, 10, 11, 12
 GOALS = {"voltage_regulation": 0, "Q_regulation": 1, "power_regulation": 2}
+REWARD_TERMS = {"voltage_error": 0, "Q_error": 1, "power_error": 2, "Vdc_error": 3}
 EVENT_MODES = {"none": 0, "philox": 1, "table": 2}
 STATUS_OK, STATUS_BAD_ACTION, STATUS_NONFINITE, STATUS_UNBALANCED = 0, 1, 2, 3
 THREE_PHASE_MODES = {"general": 0, "balanced": 1, "auto": 2, "split": 3}
@@ -46,10 +48,12 @@ class Params(C.Structure):
 class EnvConfigC(C.Structure):
     _fields_ = [
         ("par", Params),
-        ("phases", C.c_int32), ("n_sub_per_step", C.c_int32), ("micro", C.c_int32), ("done_substep", C.c_int32),
+        ("phases", C.c_int32), ("n_sub_per_step", C.c_int32), ("base_level", C.c_int32), ("done_substep", C.c_int32),
         ("discrete_reward", C.c_int32), ("goal", C.c_int32), ("auto_reset", C.c_int32), ("event_mode", C.c_int32),
         ("ev_start_k", C.c_int32), ("ev_step_k", C.c_int32), ("ev_count", C.c_int32),
         ("ev_voltage_enable", C.c_int32), ("ev_insol_enable", C.c_int32), ("balanced3", C.c_int32),
+        ("refine_input_level", C.c_int32), ("refine_on_action", C.c_int32), ("startup_substeps", C.c_int32),
+        ("startup_level", C.c_int32), ("reward_terms", C.c_int32 * 4),
         ("ev_v_min", C.c_double), ("ev_v_max", C.c_double), ("ev_s_min", C.c_double), ("ev_s_max", C.c_double),
         ("delQ_pu", C.c_double), ("delVdc_pu", C.c_double), ("max_sim_time", C.c_double),
         ("substeps_per_sec", C.c_double), ("seed", C.c_uint64), ("Q_ref0", C.c_double), ("Vdc_ref0", C.c_double),

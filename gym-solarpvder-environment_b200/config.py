@@ -47,11 +47,58 @@ VGRID_RATED = 20415.0
 Z2_ACTUAL = complex(1.61, 5.54)
 
 
+_REFERENCE_SECTIONS = ("basic_specs", "basic_options", "module_parameters", "inverter_ratings", "circuit_parameters",
+                       "controller_gains", "steadystate_values", "initial_states")
+
+
+def read_der_config(der_id, config_file=None):
+    """One DER parameter set as a flat dict.  Accepts this project's flat ``der_config.json`` and the REFERENCE's own
+    file format (config_der.json: nested sections per derId, ``parent_config`` inheritance -- a child entry such as
+    "50_type1" (config_der.json:23-26) names its parent and overrides single keys of single sections), which is what
+    the reference hands to ``DERModel(configFile=...)`` (PVDER_env.py:374-378)."""
+    with open(config_file or DER_CONFIG_FILE) as fh:
+        table = json.load(fh)
+    der_id = str(der_id)
+    if der_id not in table:
+        raise ValueError(f"DER id {der_id!r} is not in {config_file or DER_CONFIG_FILE}")
+    entry = table[der_id]
+    if "phases" in entry:                       # flat layout
+        return dict(entry)
+    # reference layout: resolve the parent chain (root first), merge section by section
+    chain, seen = [], set()
+    cur = der_id
+    while cur:
+        if cur in seen:
+            raise ValueError(f"parent_config cycle at DER id {cur!r}")
+        if cur not in table:
+            raise ValueError(f"parent_config {cur!r} of DER id {der_id!r} is not in the file")
+        seen.add(cur)
+        chain.append(table[cur])
+        cur = table[cur].get("parent_config", "")
+    merged = {}
+    for ent in reversed(chain):
+        for sec in _REFERENCE_SECTIONS:
+            merged.setdefault(sec, {}).update(ent.get(sec, {}))
+    flat = {}
+    for sec in _REFERENCE_SECTIONS[1:]:
+        flat.update(merged[sec])
+    model = merged["basic_specs"].get("model_type", "")
+    if not model:
+        raise ValueError(f"DER id {der_id!r}: basic_specs.model_type is missing")
+    flat["phases"] = 1 if "SinglePhase" in model else 3
+    flat["wte0"] = flat.pop("wte", 6.28)
+    missing = [k for k in ("Np", "Ns", "Vdcmpp0", "Srated", "Ioverload", "Vrmsrated", "Rf_actual", "Lf_actual", "C_actual",
+                           "R1_actual", "X1_actual", "Kp_GCC", "Ki_GCC", "Kp_DC", "Ki_DC", "Kp_Q", "Ki_Q", "wp")
+               if k not in flat]
+    if missing:
+        raise ValueError(f"DER id {der_id!r}: missing parameters {missing}")
+    return flat
+
+
 def load_der_parameters(der_id, config_file=None):
     """Per-unit parameters of one DER as a filled ``pvder_params`` struct plus a dict of
     bases/extras (values of reference config_der.json:2-21, :66-84)."""
-    with open(config_file or DER_CONFIG_FILE) as fh:
-        raw = json.load(fh)[str(der_id)]
+    raw = read_der_config(der_id, config_file)
     wbase = 2.0 * math.pi * 60.0
     Zbase = VBASE * VBASE / SBASE
     Lbase = Zbase / wbase
@@ -130,6 +177,24 @@ def validate_goals(goals):
     return list(goals)
 
 
+def validate_reward_list(goal, reward_list):
+    """env_goal_spec[goal]['reward']['my_spec'] (PVDER_env.py:78-93, :249, :445-452): the goal's required terms first,
+    then any of its optional ones.  'Vdc_error' is accepted only where the reference can evaluate it (its target is
+    defined for power_regulation alone, :242-244; elsewhere the reference raises NameError)."""
+    spec = GOAL_SPEC[goal]["reward"]
+    if reward_list is None:
+        return list(spec["required"])
+    terms = list(reward_list)
+    allowed = spec["required"] + spec["optional"]
+    if (len(terms) > 4 or len(set(terms)) != len(terms) or not set(spec["required"]).issubset(terms)
+            or not set(terms).issubset(allowed)):
+        raise ValueError("Reward list:{} is invalid for goal {}: required {}, optional {}".format(
+            terms, goal, spec["required"], spec["optional"]))
+    if "Vdc_error" in terms and goal != "power_regulation":
+        raise ValueError("Vdc_error has no target outside the power_regulation goal (reference PVDER_env.py:242-244)")
+    return terms
+
+
 def validate_events_spec(spec):
     out = copy.deepcopy(DEFAULT_EVENTS_SPEC)
     for kind, params in (spec or {}).items():
@@ -158,6 +223,9 @@ class EnvConfig:
     max_sim_time: float = 40.0
     DISCRETE_REWARD: bool = True
     goals_list: list = field(default_factory=lambda: list(DEFAULT_GOAL))
+    # env_goal_spec[goal]['reward']['my_spec'] (PVDER_env.py:249): None = the goal's required term (what update_env_goal
+    # (None, None) installs, :445-452); a list = required + chosen optional terms, summed in list order
+    reward_list: list | None = None
     events_spec: dict = field(default_factory=lambda: copy.deepcopy(DEFAULT_EVENTS_SPEC))
     event_mode: str = "philox"
     seed: int = 0
@@ -173,7 +241,17 @@ class EnvConfig:
     # pvder Grid(unbalance_ratio_b, unbalance_ratio_c): magnitude of the phase-b/c grid voltage relative
     # to phase a.  The reference env always builds Grid(events=...) with 1.0 (PVDER_env.py:372).
     grid_unbalance_ratio: tuple = (1.0, 1.0)
-    config_file: str | None = None
+    config_file: str | None = None       # DER parameter file: this project's flat layout or the reference's config_der.json
+    der_id: str | None = None            # overrides the derId of env_model_spec (PVDER_env.py:56-58), e.g. "50_type1"
+    # Fine steps on the fixed half-cycle grid (level L: 2^L integrator steps of h / 2^L for that sub-step, 0 = off).
+    # The reference's LSODA (PVDER_env.py:166) adapts its step where the solution moves fast; the kernel refines exactly
+    # those sub-steps: the one whose inputs changed at its start (an event instant, or -- refine_on_action -- an action
+    # that moved Q_ref / Vdc_ref) and the PLL pull-in of the first startup_substeps sub-steps after reset (wte0 = 6.28
+    # is ~90 degrees from lock, config_der.json:18).  Defaults: DESIGN.md "Fine steps".
+    refine_input_level: int = 1
+    refine_on_action: bool = False
+    startup_substeps: int = 12
+    startup_level: int = 3
 
     def __post_init__(self):
         if self.model_type not in MODEL_SPEC:
@@ -186,8 +264,10 @@ class EnvConfig:
         self.DISCRETE_REWARD = validate_discrete(self.DISCRETE_REWARD)
         self.goals_list = validate_goals(self.goals_list)
         self.events_spec = validate_events_spec(self.events_spec)
-        self.par, self.extras = load_der_parameters(MODEL_SPEC[self.model_type]["derId"], self.config_file)
+        self.par, self.extras = load_der_parameters(self.der_id or MODEL_SPEC[self.model_type]["derId"], self.config_file)
         self.phases = self.extras["phases"]
+        if self.phases != (1 if self.model_type == "model_1" else 3):
+            raise ValueError(f"DER id {self.der_id!r} has {self.phases} phase(s); {self.model_type} needs the other kind")
         self.n_state = 6 * self.phases + 5
         self.c = self._pack()
 
@@ -219,10 +299,15 @@ class EnvConfig:
         n = self.n_sim_time_steps_per_env_step
         c.phases = self.phases
         c.n_sub_per_step = 2 * n
-        c.micro = int(self.micro)
+        if self.micro not in (1, 2, 4, 8):
+            raise ValueError("micro (integrator steps per half-cycle sub-step) must be 1, 2, 4 or 8")
+        c.base_level = {1: 0, 2: 1, 4: 2, 8: 3}[self.micro]
         c.done_substep = int(math.ceil(self.max_sim_time * SUBSTEPS_PER_SEC - 1e-9))
         c.discrete_reward = int(self.DISCRETE_REWARD)
         c.goal = _cabi.GOALS[self.goals_list[0]]                          # PVDER_env.py:234
+        self.reward_list = validate_reward_list(self.goals_list[0], self.reward_list)
+        for t in range(4):
+            c.reward_terms[t] = _cabi.REWARD_TERMS[self.reward_list[t]] if t < len(self.reward_list) else -1
         c.auto_reset = int(self.auto_reset)
         v, s = self.events_spec["voltage"], self.events_spec["insolation"]
         enabled = bool(v["ENABLE"] or s["ENABLE"])
@@ -251,6 +336,14 @@ class EnvConfig:
         self.three_phase_mode = b3 if self.phases == 3 else "single_phase"
         c.balanced3 = _cabi.THREE_PHASE_MODES[b3] if self.phases == 3 else 0
         c.vg_ratio_b, c.vg_ratio_c = rb, rc
+        for name in ("refine_input_level", "startup_level"):
+            lv = getattr(self, name)
+            if isinstance(lv, bool) or not isinstance(lv, int) or not 0 <= lv <= _cabi.FINE_LEVELS:
+                raise ValueError(f"{name} must be an integer in [0, {_cabi.FINE_LEVELS}]")
+        if isinstance(self.startup_substeps, bool) or not isinstance(self.startup_substeps, int) or self.startup_substeps < 0:
+            raise ValueError("startup_substeps must be a non-negative integer")
+        c.refine_input_level, c.refine_on_action = self.refine_input_level, int(bool(self.refine_on_action))
+        c.startup_substeps, c.startup_level = self.startup_substeps, self.startup_level
         c.ev_v_min, c.ev_v_max = float(v["min"]), float(v["max"])
         c.ev_s_min, c.ev_s_max = float(s["min"]), float(s["max"])
         c.delQ_pu = self.delQref / self.extras["Sbase"]                   # PVDER_env.py:225

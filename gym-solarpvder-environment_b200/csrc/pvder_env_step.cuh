@@ -28,10 +28,6 @@ namespace pvder {
 #ifndef PVDER_FOLD
 #define PVDER_FOLD 1   // Rodas4: fold K1..K4 into the stage-5/6 sums early: same FMAs, 2 fewer live vectors (B200: 3.11 -> 3.04 ms)
 #endif
-#ifndef PVDER_REFINE_INPUT_STEP
-#define PVDER_REFINE_INPUT_STEP 0   // 1: the half-cycle sub-step that follows a change of the inputs (action != 0, event) is taken as two
-#endif                              //    half-size steps with a second coefficient table (one-thread kernels; DESIGN.md "Input-step
-                                    //    refinement": study build, off)
 #ifndef PVDER_FREE_PATH
 #define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the stepper core, chosen per warp (experiment)
 #endif
@@ -56,13 +52,13 @@ struct RodasCoefT {   // a_ij and c_ij/h, read by DFMA straight from the constan
   double m1, m2, m3, m4;
   double d41, d42, ds41, ds42;
 };
-using RodasHalf = RodasCoefT<1>;
-// The kernels' coefficient table (a __grid_constant__ launch parameter); the study build with input-step refinement
-// carries a second set for steps of h/2.
-struct RodasTab : RodasCoefT<0> {
-#if PVDER_REFINE_INPUT_STEP
-  RodasHalf half;
-#endif
+using RodasCoef = RodasCoefT<0>;
+// The kernels' coefficient table (a __grid_constant__ launch parameter): the set for the half-cycle step h that the hot
+// loop reads straight from the constant bank, and PVDER_FINE_LEVELS sets for steps of h/2, h/4, h/8 used by the
+// out-of-line fine-step path (ros_slow): the sub-step that follows a change of the inputs and the PLL pull-in right
+// after reset are taken as 2^level shorter steps (pvder_env_config.refine_input_level / startup_level).
+struct RodasTab : RodasCoef {
+  RodasCoef fine[PVDER_FINE_LEVELS];
 };
 
 template <class M, class T>
@@ -110,9 +106,7 @@ template <class M>
 PVDER_HD RodasTab make_rodas_tab(const Params& par, double hinv) {
   RodasTab t = {};
   fill_rodas<M>(t, par, hinv);
-#if PVDER_REFINE_INPUT_STEP
-  fill_rodas<M>(t.half, par, 2.0 * hinv);
-#endif
+  for (int l = 0; l < PVDER_FINE_LEVELS; ++l) fill_rodas<M>(t.fine[l], par, (double)(2 << l) * hinv);
   return t;
 }
 
@@ -372,23 +366,69 @@ PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in,
 #undef PVDER_WITH_GAINS
 #undef PVDER_GN
 
-// Out-of-line slow path: library transcendentals at every stage.  Everything travels by value, so that nothing in
-// the caller's hot loop has its address taken (that would pin the state and the aux record to local memory: 18 doubles
-// stored and re-loaded per sub-step).
+// Out-of-line slow path.  Everything travels by value, so that nothing in the caller's hot loop has its address taken
+// (that would pin the state and the aux record to local memory: 18 doubles stored and re-loaded per sub-step).
+//   level == 0: the half-cycle step redone with library transcendentals at every stage (a stage left the range of the
+//               incremental side-inputs);
+//   level  > 0: the sub-step taken as 2^level steps of h / 2^level with the coefficient set tab->fine[level - 1] (read
+//               through the pointer: this path is cold, the hot loop keeps its constant-bank operands).  The clamp mode is
+//               re-sampled before every fine step, like before every other integrator step.
 template <class M>
-struct StepState {
+struct StepState {   // <= 128 bytes for the single-phase models: travels in registers both ways
   double y[M::NS];
-  Aux base;
+  double sn, cs, E;    // the aux record without its PV part (ros_core re-derives that from E and the inputs)
+  int exact;           // steps that needed library transcendentals
+  int flags;           // bit 0: an anti-windup clamp was active in one of the fine steps, bit 1: duty-cycle limit exceeded
 };
-template <class M, class TAB>
-PVDER_NOINLINE StepState<M> ros_exact(StepState<M> s, const Params* par, Inputs in, const TAB* tab, unsigned frz) {
-  ros_core<M, true>(s.y, *par, in, *tab, frz, s.base);
+template <class M>
+PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, const Inputs& in, bool& m_over_out);
+#ifndef PVDER_SLOW_INLINE
+#define PVDER_SLOW_INLINE 1   // 1: the slow path is inlined into the (cold) segment loop, so its fine-step tables are constant-bank
+#endif                        //    operands too (B200: 1.569 -> 1.510 ms per 1 Mi-env step against the noinline function, whose
+                              //    generic loads from the parameter space made a fine step cost several hot steps)
+#if PVDER_SLOW_INLINE
+#define PVDER_SLOW_LINKAGE PVDER_DEV
+#else
+#define PVDER_SLOW_LINKAGE PVDER_NOINLINE
+#endif
+template <class M>
+PVDER_SLOW_LINKAGE StepState<M> ros_slow(StepState<M> s, const Params* par, Inputs in, const RodasTab* tab, unsigned frz,
+                                         int level) {
+  s.exact = 0;
+  s.flags = 0;
+  Aux base;
+  base.sn = s.sn; base.cs = s.cs; base.E = s.E;
+  base.PoV = base.dPoV = 0.0;
+  if (level <= 0) {
+    ros_core<M, true>(s.y, *par, in, static_cast<const RodasCoef&>(*tab), frz, base);
+    s.exact = 1;
+    s.sn = base.sn; s.cs = base.cs; s.E = base.E;
+    return s;
+  }
+  const RodasCoef& ft = tab->fine[level - 1];
+  const int nf = 1 << level;
+#pragma unroll 1
+  for (int j = 0; j < nf; ++j) {
+    if (j) {
+      bool m_over;
+      frz = freeze_bits<M>(s.y, *par, in, m_over);
+      s.flags |= (frz != 0u ? 1 : 0) | (m_over ? 2 : 0);
+    }
+    if (!ros_core<M, false>(s.y, *par, in, ft, frz, base)) {
+      ros_core<M, true>(s.y, *par, in, ft, frz, base);
+      s.exact += 1;
+    }
+  }
+  s.sn = base.sn; s.cs = base.cs; s.E = base.E;
   return s;
 }
 
+// One half-cycle sub-step of the hot loop: the inlined step.  Returns false (y, base untouched) when a stage left the
+// incremental range: the caller leaves the hot loop and redoes the sub-step out of line (ros_slow_substep, level 0) --
+// the hot loop itself contains no call, so nothing in it is bound by the calling convention's register classes.
 template <class M, class TAB>
 PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in, const TAB& tab,
-                           unsigned frz, Aux& base) {
+                        unsigned frz, Aux& base) {
   // One instantiation serves clamped and unclamped envs (the clamp enters through the per-row
   // effective gains): with a random policy two thirds of the warps hold a clamped lane late in an
   // episode, so a separate divergent code path for them cost 2x there.
@@ -399,23 +439,28 @@ PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in,
 #else
   const bool any_frz = frz != 0u;
 #endif
-  const bool ok = any_frz ? ros_core<M, false, false>(y, par, in, tab, frz, base)
-                          : ros_core<M, false, true>(y, par, in, tab, frz, base);
+  return any_frz ? ros_core<M, false, false>(y, par, in, tab, frz, base)
+                 : ros_core<M, false, true>(y, par, in, tab, frz, base);
 #else
-  const bool ok = ros_core<M, false>(y, par, in, tab, frz, base);
+  return ros_core<M, false>(y, par, in, tab, frz, base);
 #endif
-  if (!ok) {
-    StepState<M> s;
+}
+
+// One half-cycle sub-step through the out-of-line path: level 0 = the step redone with library transcendentals, level > 0
+// = refined into 2^level fine steps.  Returns the steps that used library transcendentals; flags: see StepState.
+template <class M, class TAB>
+PVDER_DEV int ros_slow_substep(double (&y)[M::NS], const Params& par, const Inputs& in, const TAB& tab,
+                               unsigned frz, Aux& base, int level, int& flags) {
+  StepState<M> s;
 #pragma unroll
-    for (int i = 0; i < M::NS; ++i) s.y[i] = y[i];
-    s.base = base;
-    s = ros_exact<M>(s, &par, in, &tab, frz);
+  for (int i = 0; i < M::NS; ++i) s.y[i] = y[i];
+  s.sn = base.sn; s.cs = base.cs; s.E = base.E;
+  s = ros_slow<M>(s, &par, in, &tab, frz, level);
 #pragma unroll
-    for (int i = 0; i < M::NS; ++i) y[i] = s.y[i];
-    base = s.base;
-    return false;
-  }
-  return true;
+  for (int i = 0; i < M::NS; ++i) y[i] = s.y[i];
+  base.sn = s.sn; base.cs = s.cs; base.E = s.E;
+  flags |= s.flags;
+  return s.exact;
 }
 
 // pvder's clamping test np.sign(a) == np.sign(b)
@@ -583,20 +628,32 @@ PVDER_DEV void finish_outputs(const pvder_env_config& cfg, const Inputs& in, dou
   o.obs[0] = iaR; o.obs[1] = iaI; o.obs[2] = vaR; o.obs[3] = vaI; o.obs[4] = Ppcc; o.obs[5] = Qpcc;
   o.obs[6] = Vdc; o.obs[7] = Ppv; o.obs[8] = Vdcref; o.obs[9] = Qref;
   o.obs[10] = __ddiv_rn(__ddiv_rn((double)k, cfg.substeps_per_sec), cfg.max_sim_time);
-  double x, target, hi;
-  if (cfg.goal == PVDER_GOAL_VOLTAGE) { x = Vrms; target = par.Vrms_ref; hi = 0.05; }
-  else if (cfg.goal == PVDER_GOAL_Q) { x = Qpcc; target = par.q_target; hi = 0.05; }
-  else { x = Ppcc; target = par.p_target; hi = 0.03; }
-  if (cfg.discrete_reward) {
-    if (cfg.goal == PVDER_GOAL_Q && target == 0.0) target = 1e-6;
-    const double err = __ddiv_rn(fabs(__dadd_rn(x, -target)), fabs(target));
-    o.reward_i = (err <= 0.01) ? 1 : ((err >= hi) ? -5 : -1);
-    o.reward = (double)o.reward_i;
-  } else {
-    const double d = __dadd_rn(x, -target);
-    o.reward = -__dmul_rn(d, d);
-    o.reward_i = 0;
+  // PVDER_env.py:249-299: the reward is the sum over the goal's reward list (`my_spec`: the goal's required term, plus
+  // optional ones) of one term per entry, Python's sum() starting from 0.
+  double rsum = 0.0;
+  int isum = 0;
+#pragma unroll
+  for (int t = 0; t < PVDER_MAX_REWARD_TERMS; ++t) {
+    const int id = cfg.reward_terms[t];
+    if (id < 0) break;
+    double x, target, lo = 0.01, hi = 0.05;
+    if (id == PVDER_TERM_VOLTAGE) { x = Vrms; target = par.Vrms_ref; }                         // :276-287
+    else if (id == PVDER_TERM_Q) {                                                             // :263-275, target :238-241
+      x = Qpcc;
+      target = (cfg.goal == PVDER_GOAL_VOLTAGE) ? Qref : par.q_target;
+      if (cfg.discrete_reward && target == 0.0) target = 1e-6;
+    } else if (id == PVDER_TERM_POWER) { x = Ppcc; target = par.p_target; hi = 0.03; }         // :290-299
+    else { x = Vdc; target = Vdcref; lo = 0.02; }                                              // :251-262 (Vdc_error)
+    if (cfg.discrete_reward) {
+      const double err = __ddiv_rn(fabs(__dadd_rn(x, -target)), fabs(target));
+      isum += (err <= lo) ? 1 : ((err >= hi) ? -5 : -1);
+    } else {
+      const double d = __dadd_rn(x, -target);
+      rsum = __dadd_rn(rsum, -__dmul_rn(d, d));
+    }
   }
+  o.reward_i = cfg.discrete_reward ? isum : 0;
+  o.reward = cfg.discrete_reward ? (double)isum : rsum;
 }
 
 template <int P, bool UNBAL = true>
@@ -712,7 +769,7 @@ PVDER_DEV void init_env(const pvder_env_config& cfg, double (&y)[M::NS], double&
 // One env step for one env (everything between the state load and the state store).
 // Returns true when the env advanced (state must be written back).  hist_inc: action whose
 // histogram counter must be incremented (-1: none); hist_clear: auto-reset happened.
-template <class M>
+template <class M, bool RECORD = true>
 PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, EnvRegs<M>& r, int act, bool active, const double* vtab,
                            const double* stab, int64_t ld, int64_t e, uint32_t env_glob, Outputs& o, int& done_out,
                            int& hist_inc, bool& hist_clear, double* traj = nullptr, int64_t traj_ld = 0) {
@@ -732,67 +789,90 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
     const double dV = (act == 3) ? cfg.delVdc_pu : ((act == 4) ? -cfg.delVdc_pu : 0.0);
     r.Qref = __dadd_rn(r.Qref, dQ);                          // PVDER_env.py:225
     r.Vdcref = __dadd_rn(r.Vdcref, dV);                      // PVDER_env.py:229
-    int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
-    int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
     Aux base;
     Inputs in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);   // changes only when an event fires
     aux_exact<M>(par, in, r.y, base);         // library sincos/exp/div once per env step, then incremental
-    // One loop over the integrator steps (micro per half-cycle, normally 1).  The clamp mode is sampled right
-    // before every step, in the same basic block as the step itself: freeze_bits uses the expression trees of the
-    // generated right-hand side, so stage 1 reuses its vR, vI, m, Q, iref instead of recomputing them.
-    const int total = cfg.n_sub_per_step * cfg.micro;
-    int m_left = cfg.micro, s = 0;
-    bool clamped = false;
-#if PVDER_REFINE_INPUT_STEP
-    // the inputs change at the start of this env step when the action moves a reference or an event instant falls on it
-    bool refine = act != 0 || (r.k >= cfg.ev_start_k && (r.k - cfg.ev_start_k) % cfg.ev_step_k == 0 &&
-                               (r.k - cfg.ev_start_k) / cfg.ev_step_k < cfg.ev_count);
-#endif
-    for (int it = 0; it < total; ++it) {
-      bool m_over;
-      const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
-      clamped |= frz != 0u;
-      // the duty-cycle clamp acts on Re/Im parts per phase and would break the symmetry the
-      // balanced representation relies on: report instead of integrating something else
-      if (M::BALANCED3 && m_over) r.status = PVDER_STATUS_UNBALANCED;
-#if PVDER_REFINE_INPUT_STEP
-      if (refine) {
-        // two half-size steps with the h/2 table (its own inlined copy of the step body, executed about once per env
-        // step: the hot path below keeps its code and its constant-bank operands); the clamp mode is re-sampled in
-        // between like at every other step
-        refine = false;
-        unsigned f2 = frz;
-#pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          if (hh) {
-            bool m_over2;
-            f2 = freeze_bits<M>(r.y, par, in, m_over2);
-            clamped |= f2 != 0u;
-            if (M::BALANCED3 && m_over2) r.status = PVDER_STATUS_UNBALANCED;
-          }
-          if (!ros_step<M>(r.y, par, in, tab.half, f2, base)) r.exact += 1;
-        }
-      } else
-#endif
-      if (!ros_step<M>(r.y, par, in, tab, frz, base)) r.exact += 1;
-      if (--m_left != 0) continue;
-      // half-cycle boundary
-      m_left = cfg.micro;
-      if (clamped) r.windup += 1;
-      clamped = false;
-      if (traj) record_substep<M>(traj, traj_ld, s, r.y, r.Vgrid, r.Sinsol);
-      s += 1;
-      r.k += 1;
-      if (r.k == next_k && j_next < cfg.ev_count) {
-        apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
-        in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
-        j_next += 1;
-        next_k += cfg.ev_step_k;
-#if PVDER_REFINE_INPUT_STEP
-        refine = true;
-#endif
-      }
+    // The sub-steps of this env step run in SEGMENTS: a refined sub-step (fine-step level > 0: the inputs changed at
+    // its start -- an event instant, or with refine_on_action an action that moved a reference --, or the PLL pull-in of
+    // the first startup_substeps after reset, or base_level > 0) goes through the out-of-line path; everything up to the
+    // next event instant / the end of the env step is one run of the hot loop, which carries two integers and contains
+    // no call (a sub-step whose stages leave the incremental range ends the run and is redone out of line) -- the
+    // stepper needs every other register.  In the hot loop the clamp mode is sampled
+    // right before every step, in the same basic block as the step itself: freeze_bits uses the expression trees of
+    // the generated right-hand side, so stage 1 reuses its vR, vI, m, Q, iref instead of recomputing them.
+    const int k0 = r.k, k_end = r.k + cfg.n_sub_per_step;
+    constexpr int NO_EVENT = 1 << 30;
+    int ev_left;   // sub-steps until the next event instant (it fires at the END of a sub-step)
+    {
+      const int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
+      ev_left = (j_next < cfg.ev_count) ? cfg.ev_start_k + j_next * cfg.ev_step_k - r.k : NO_EVENT;
     }
+    const bool ev_here = r.k >= cfg.ev_start_k && (r.k - cfg.ev_start_k) % cfg.ev_step_k == 0 &&
+                         (r.k - cfg.ev_start_k) / cfg.ev_step_k < cfg.ev_count;
+    int lvl_in = ((cfg.refine_on_action && act != 0) || ev_here) ? cfg.refine_input_level : 0;
+    bool redo = false;   // the hot loop stopped at a sub-step that needs library transcendentals
+    auto event_due = [&]() {
+      if (ev_left != 0) return;
+      const int j = (r.k - cfg.ev_start_k) / cfg.ev_step_k;
+      apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j, r.Vgrid, r.Sinsol);
+      in = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
+      ev_left = (j + 1 < cfg.ev_count) ? cfg.ev_step_k : NO_EVENT;
+      lvl_in = cfg.refine_input_level;
+    };
+    do {
+      // [A] one sub-step through the slow path, if this one needs it.  No `else`: lanes that diverge here (an action
+      // refined in some envs of the warp only) rejoin the others for the hot run below instead of serialising it.
+      {
+        const int lvl_st = (r.k < cfg.startup_substeps) ? cfg.startup_level : cfg.base_level;
+        const int lvl = lvl_in > lvl_st ? lvl_in : lvl_st;
+        lvl_in = 0;
+        if (lvl != 0 || redo) {
+          redo = false;
+          bool m_over;
+          const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
+          int flags = (frz != 0u ? 1 : 0) | (m_over ? 2 : 0);
+          r.exact += ros_slow_substep<M>(r.y, par, in, tab, frz, base, lvl, flags);
+          r.windup += flags & 1;
+          if (M::BALANCED3 && (flags & 2)) r.status = PVDER_STATUS_UNBALANCED;
+          if (RECORD) {
+            if (traj) record_substep<M>(traj, traj_ld, r.k - k0, r.y, r.Vgrid, r.Sinsol);
+          }
+          r.k += 1;
+          ev_left -= 1;
+          event_due();
+        }
+      }
+      // [B] the run of plain sub-steps that follows: up to the next event instant, the end of the start-up phase or
+      // the end of the env step (empty when the next sub-step is refined again)
+      int seg = k_end - r.k;
+      if (ev_left < seg) seg = ev_left;
+      if (r.k < cfg.startup_substeps) {
+        if (cfg.startup_level != 0) seg = 0;
+        else if (cfg.startup_substeps - r.k < seg) seg = cfg.startup_substeps - r.k;   // base_level starts there
+      } else if (cfg.base_level != 0) seg = 0;
+      if (lvl_in != 0) seg = 0;
+      if (seg > 0) {
+        // hot loop: a countdown and the clamped-sub-step counter are all the integers it carries
+        int left = seg, wind = 0;
+        do {
+          bool m_over;
+          const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
+          if (!ros_step<M>(r.y, par, in, tab, frz, base)) break;
+          wind += frz != 0u ? 1 : 0;
+          // the duty-cycle clamp acts on Re/Im parts per phase and would break the symmetry the
+          // balanced representation relies on: report instead of integrating something else
+          if (M::BALANCED3 && m_over) r.status = PVDER_STATUS_UNBALANCED;
+          if (RECORD) {
+            if (traj) record_substep<M>(traj, traj_ld, r.k + (seg - left) - k0, r.y, r.Vgrid, r.Sinsol);
+          }
+        } while (--left != 0);
+        redo = left != 0;
+        r.k += seg - left;
+        ev_left -= seg - left;
+        r.windup += wind;
+        event_due();
+      }
+    } while (r.k != k_end);
     bool finite = true;
 #pragma unroll
     for (int i = 0; i < NS; ++i) finite &= (bool)isfinite(r.y[i]);
@@ -836,6 +916,7 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
 
 // Three-phase "auto" mode: a balanced state (the only kind the env itself creates) is integrated by
 // the 11-state balanced model, anything else by the general 23-state model.
+template <bool RECORD = true>
 PVDER_DEV bool advance_env_auto3(const pvder_env_config& cfg, const RodasTab& tab, EnvRegs<Model3ph>& r, int act,
                                  bool active, const double* vtab, const double* stab, int64_t ld, int64_t e,
                                  uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear,
@@ -849,7 +930,7 @@ PVDER_DEV bool advance_env_auto3(const pvder_env_config& cfg, const RodasTab& ta
     b.Qref = r.Qref; b.Vdcref = r.Vdcref; b.Vgrid = r.Vgrid; b.Sinsol = r.Sinsol; b.ret = r.ret;
     b.last_reward = r.last_reward; b.k = r.k; b.steps = r.steps; b.episode = r.episode; b.status = r.status;
     b.done = r.done; b.windup = r.windup; b.exact = r.exact;
-    const bool run = advance_env<Model3phBal>(cfg, tab, b, act, active, vtab, stab, ld, e, env_glob, o, done_out,
+    const bool run = advance_env<Model3phBal, RECORD>(cfg, tab, b, act, active, vtab, stab, ld, e, env_glob, o, done_out,
                                               hist_inc, hist_clear, traj, traj_ld);
     expand_balanced(b.y, r.y);
     r.Qref = b.Qref; r.Vdcref = b.Vdcref; r.Vgrid = b.Vgrid; r.Sinsol = b.Sinsol; r.ret = b.ret;
@@ -857,7 +938,7 @@ PVDER_DEV bool advance_env_auto3(const pvder_env_config& cfg, const RodasTab& ta
     r.done = b.done; r.windup = b.windup; r.exact = b.exact;
     return run;
   }
-  return advance_env<Model3ph>(cfg, tab, r, act, active, vtab, stab, ld, e, env_glob, o, done_out, hist_inc, hist_clear,
+  return advance_env<Model3ph, RECORD>(cfg, tab, r, act, active, vtab, stab, ld, e, env_glob, o, done_out, hist_inc, hist_clear,
                                traj, traj_ld);
 }
 

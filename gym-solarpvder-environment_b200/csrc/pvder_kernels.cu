@@ -92,7 +92,7 @@ __device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const O
 #define PVDER_STEP_BOUNDS(M) __launch_bounds__(BLOCK, min_blocks<M>())
 #endif
 
-template <class M, bool AUTO3 = false>
+template <class M, bool AUTO3 = false, bool RECORD = false>
 __global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_env_config cfg,
                                                      const __grid_constant__ RodasTab tab, const StepArgs a) {
   constexpr int NS = M::NS_STORE;   // rows of the stored state (the balanced model integrates 11 of 23)
@@ -123,13 +123,14 @@ __global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_e
   int done_out, hist_inc;
   bool hist_clear;
   bool run;
-  double* traj = traj_column(a, e, active);
+  // RECORD = false (every launch but pvder_step_record's): no trajectory pointer lives through the sub-step loop
+  double* traj = RECORD ? traj_column(a, e, active) : nullptr;
   if constexpr (AUTO3)
-    run = advance_env_auto3(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o, done_out,
-                            hist_inc, hist_clear, traj, a.traj_n);
+    run = advance_env_auto3<RECORD>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
+                                    done_out, hist_inc, hist_clear, traj, a.traj_n);
   else
-    run = advance_env<M>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o, done_out,
-                         hist_inc, hist_clear, traj, a.traj_n);
+    run = advance_env<M, RECORD>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
+                                 done_out, hist_inc, hist_clear, traj, a.traj_n);
 
   if (active) {
     if (a.reward_f64) a.reward_f64[e] = o.reward;
@@ -522,7 +523,7 @@ static int cuda_fail(cudaError_t e) {
 static int check_cfg(const pvder_env_config* c) {
   if (!c) return PVDER_ERR_INVALID;
   if (c->phases != 1 && c->phases != 3) return PVDER_ERR_INVALID;
-  if (c->n_sub_per_step < 1 || c->micro < 1 || c->ev_step_k < 1 || c->ev_count < 0) return PVDER_ERR_INVALID;
+  if (c->n_sub_per_step < 1 || c->ev_step_k < 1 || c->ev_count < 0) return PVDER_ERR_INVALID;
   if (c->goal < 0 || c->goal > 2) return PVDER_ERR_INVALID;
   if (c->balanced3 < 0 || c->balanced3 > 3) return PVDER_ERR_INVALID;
   if (!(c->vg_ratio_b > 0.0) || !(c->vg_ratio_c > 0.0)) return PVDER_ERR_INVALID;
@@ -530,6 +531,16 @@ static int check_cfg(const pvder_env_config* c) {
       (c->phases != 3 || c->balanced3 == PVDER_3PH_BALANCED || c->balanced3 == PVDER_3PH_AUTO))
     return PVDER_ERR_INVALID;   /* an unbalanced grid needs the general or the split three-phase mode */
   if (c->event_mode < 0 || c->event_mode > 2) return PVDER_ERR_INVALID;
+  if (c->refine_input_level < 0 || c->refine_input_level > PVDER_FINE_LEVELS || c->startup_level < 0 ||
+      c->startup_level > PVDER_FINE_LEVELS || c->startup_substeps < 0 || c->base_level < 0 ||
+      c->base_level > PVDER_FINE_LEVELS)
+    return PVDER_ERR_INVALID;
+  if (c->reward_terms[0] < 0) return PVDER_ERR_INVALID;   /* at least the goal's required term */
+  for (int t = 0; t < PVDER_MAX_REWARD_TERMS; ++t) {
+    if (c->reward_terms[t] > PVDER_TERM_VDC) return PVDER_ERR_INVALID;
+    /* Vdc_error needs the power_regulation goal: the reference defines its target only there (PVDER_env.py:242-244) */
+    if (c->reward_terms[t] == PVDER_TERM_VDC && c->goal != PVDER_GOAL_POWER) return PVDER_ERR_INVALID;
+  }
   return PVDER_OK;
 }
 
@@ -645,17 +656,21 @@ static int launch_step(const pvder_env_config* cfg, double* sd, int32_t* si, int
              traj, traj_n, traj_stride};
   const unsigned grid = (unsigned)((n_envs + BLOCK - 1) / BLOCK);
   cudaStream_t st = (cudaStream_t)stream;
-  const double hinv = cfg->substeps_per_sec * (double)cfg->micro;
-  if (cfg->phases == 1) step_kernel<Model1ph><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model1ph>(cfg->par, hinv), a);
-  else if (cfg->balanced3 == PVDER_3PH_BALANCED)
-    step_kernel<Model3phBal><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3phBal>(cfg->par, hinv), a);
-  else if (cfg->balanced3 == PVDER_3PH_AUTO)
-    step_kernel<Model3ph, true><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3ph>(cfg->par, hinv), a);
+  const double hinv = cfg->substeps_per_sec;
+#define PVDER_LAUNCH1(M, AUTO)                                                                                      \
+  do {                                                                                                              \
+    if (traj) step_kernel<M, AUTO, true><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<M>(cfg->par, hinv), a);       \
+    else step_kernel<M, AUTO, false><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<M>(cfg->par, hinv), a);           \
+  } while (0)
+  if (cfg->phases == 1) PVDER_LAUNCH1(Model1ph, false);
+  else if (cfg->balanced3 == PVDER_3PH_BALANCED) PVDER_LAUNCH1(Model3phBal, false);
+  else if (cfg->balanced3 == PVDER_3PH_AUTO) PVDER_LAUNCH1(Model3ph, true);
   else if (cfg->balanced3 == PVDER_3PH_SPLIT) {
     const unsigned grid3 = (unsigned)((n_envs + SPLIT_ENVS_PER_BLOCK - 1) / SPLIT_ENVS_PER_BLOCK);
     step_kernel_split3<<<grid3, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Split3>(cfg->par, hinv), a);
   }
-  else step_kernel<Model3ph><<<grid, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Model3ph>(cfg->par, hinv), a);
+  else PVDER_LAUNCH1(Model3ph, false);
+#undef PVDER_LAUNCH1
   CK(cudaGetLastError());
   return PVDER_OK;
 }

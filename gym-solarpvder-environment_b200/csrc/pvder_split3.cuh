@@ -481,14 +481,16 @@ struct Split3 {
 // side-inputs as ros_core).  Stage vectors are folded into the sums that need them as soon as they exist, so
 // at most five lane-vectors are live.
 // ---------------------------------------------------------------------------------------------
-template <bool EXACT, bool FREE, class LN>
+template <bool EXACT, bool FREE, class LN, class TAB>
 PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_config& cfg, const Inputs& in_s,
-                                 const Split3::In& in, const Split3::Consts& k, const RodasTab& tab,
-                                 const Split3::Gains& g, Aux& base) {
+                                 const Split3::In& in, const Split3::Consts& k, const TAB& tab,
+                                 const Split3::Gains& g, Aux& base, bool discard = false) {
+  // discard: this group only keeps its warp converged through the hot step (its sub-step is refined out of line):
+  // treated like a stage out of range -- y and base stay untouched, false is returned
   using S = Split3;
   using Vec = S::Vec;
   const Params& par = cfg.par;
-  bool oor = false;
+  bool oor = discard;
   const double dl0 = y.s[4], V0 = y.s[0];
   pov_from_exp(par, in_s, base.E, base.PoV, base.dPoV);      // inputs (insolation) may have changed
   Vec K1, K2, K3, K4, Y;
@@ -622,17 +624,40 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
   return true;
 }
 
-// Out-of-line slow path (library transcendentals at every stage).  Everything travels by value so
-// that nothing in the caller's hot loop has its address taken (that would pin it to local memory).
+// Out-of-line slow path (see ros_slow in pvder_env_step.cuh): level 0 = the half-cycle step redone with library
+// transcendentals at every stage; level > 0 = the sub-step as 2^level steps of h / 2^level with tab->fine[level - 1], the
+// clamp mode re-sampled before every fine step.  Everything travels by value so that nothing in the caller's hot loop
+// has its address taken (that would pin it to local memory).  Entered by the lanes in ln.mask (whole groups).
 struct SplitStepResult {
   Split3::Vec y;
   Aux base;
+  int exact;
+  int clamped;
 };
-PVDER_NOINLINE SplitStepResult ros_exact_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
-                                                  Split3::In in, Split3::Consts k, const RodasTab* tab,
-                                                  Split3::Gains g, Aux base) {
+PVDER_NOINLINE SplitStepResult ros_slow_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
+                                              Split3::In in, Split3::Consts k, const RodasTab* tab,
+                                              Split3::Gains g, Aux base, int level) {
   SplitStepResult r;
-  ros_core_split<true, false>(ln, y, *cfg, in_s, in, k, *tab, g, base);
+  r.exact = 0;
+  r.clamped = 0;
+  if (level <= 0) {
+    ros_core_split<true, false>(ln, y, *cfg, in_s, in, k, static_cast<const RodasCoef&>(*tab), g, base);
+    r.exact = 1;
+  } else {
+    const RodasCoef& ft = tab->fine[level - 1];
+    const int nf = 1 << level;
+#pragma unroll 1
+    for (int j = 0; j < nf; ++j) {
+      // gains carry h-scaled entries: rebuilt with this level's constants (also for the first fine step)
+      bool m_over;
+      g = Split3::gains(ln, cfg->par, k, in, y, ft.luc, m_over);
+      r.clamped |= g.any ? 1 : 0;
+      if (!ros_core_split<false, false>(ln, y, *cfg, in_s, in, k, ft, g, base)) {
+        ros_core_split<true, false>(ln, y, *cfg, in_s, in, k, ft, g, base);
+        r.exact += 1;
+      }
+    }
+  }
   r.y = y;
   r.base = base;
   return r;
@@ -738,41 +763,56 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
   const bool any_run = ln.any_warp(run);                     // warp-uniform
   if (any_run) {
     const int status_in = r.status;
-    int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
-    int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
     Aux base;
     Inputs in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);   // changes only when an event fires
     S::In in = S::inputs(ln, kc, in_s);
     aux_exact_sv(par, in_s, r.y.s[4], r.y.s[0], base);
-    // (two nested loops and a clamp decision with its own Q sum: merging the loops as in the one-thread kernels, or
-    // sharing one point record between the clamp decision and stage 1, cost 2-2.5 % here -- register pressure)
-    for (int s = 0; s < cfg.n_sub_per_step; ++s) {
+    // same loop as advance_env (few loop-carried integers; the clamp mode is sampled before every sub-step).  The
+    // fine-step level is warp-uniform only in lock-step batches, so the choice between the hot step and the out-of-line
+    // path is made per group under a ballot mask.
+    const int k0 = r.k, k_end = r.k + cfg.n_sub_per_step;
+    int ev_left;
+    {
+      const int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
+      ev_left = (j_next < cfg.ev_count) ? cfg.ev_start_k + j_next * cfg.ev_step_k - r.k : 0;
+    }
+    const bool ev_here = r.k >= cfg.ev_start_k && (r.k - cfg.ev_start_k) % cfg.ev_step_k == 0 &&
+                         (r.k - cfg.ev_start_k) / cfg.ev_step_k < cfg.ev_count;
+    int lvl_in = ((cfg.refine_on_action && act != 0 && run) || ev_here) ? cfg.refine_input_level : 0;
+    do {
+      const int lvl_st = (r.k < cfg.startup_substeps) ? cfg.startup_level : cfg.base_level;
+      const int lvl = lvl_in > lvl_st ? lvl_in : lvl_st;
       bool m_over;
       const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
-      if (g.any) r.windup += 1;
-      for (int m = 0; m < cfg.micro; ++m) {
-        // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
-        // come from the constant bank (fewer live registers, no spills in the common case)
-        const bool ok = ln.any_warp(g.any) ? ros_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base)
-                                           : ros_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base);
-        const LanesT<true> lx = ln.sub(!ok);
-        if (!ok) {
-          const SplitStepResult res = ros_exact_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base);
-          r.y = res.y;
-          base = res.base;
-          r.exact += 1;
-        }
+      bool clamped = g.any;
+      // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
+      // come from the constant bank (fewer live registers, no spills in the common case).  A warp in which every
+      // group is refined skips the hot step; a refined group in a mixed warp only keeps it converged (discard).
+      bool ok = false;
+      if (ln.any_warp(lvl == 0))
+        ok = ln.any_warp(g.any) ? ros_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base, lvl != 0)
+                                : ros_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base, lvl != 0);
+      const LanesT<true> lx = ln.sub(!ok);
+      if (!ok) {
+        const SplitStepResult res = ros_slow_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base, lvl);
+        r.y = res.y;
+        base = res.base;
+        r.exact += res.exact;
+        clamped |= res.clamped != 0;
       }
-      if (traj && run) record_substep_split(ln, traj, traj_ld, s, r.y, r.Vgrid, r.Sinsol);   // not the keep-converged dummy work
+      if (clamped) r.windup += 1;
+      lvl_in = 0;
+      if (traj && run) record_substep_split(ln, traj, traj_ld, r.k - k0, r.y, r.Vgrid, r.Sinsol);   // not the keep-converged dummy work
       r.k += 1;
-      if (r.k == next_k && j_next < cfg.ev_count) {
-        apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
+      if (--ev_left == 0) {
+        const int j = (r.k - cfg.ev_start_k) / cfg.ev_step_k;
+        apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j, r.Vgrid, r.Sinsol);
         in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
         in = S::inputs(ln, kc, in_s);
-        j_next += 1;
-        next_k += cfg.ev_step_k;
+        ev_left = (j + 1 < cfg.ev_count) ? cfg.ev_step_k : 0;
+        lvl_in = cfg.refine_input_level;
       }
-    }
+    } while (r.k != k_end);
     auto bad = vnonfinite(r.y.p[0]);
 #pragma unroll
     for (int i = 1; i < 6; ++i) bad = vor(bad, vnonfinite(r.y.p[i]));

@@ -29,7 +29,9 @@ class PVDERVecEnv:
                  n_sim_time_steps_per_env_step=15, max_sim_time=40.0, DISCRETE_REWARD=True,
                  goals_list=("voltage_regulation",), events_spec=None, event_mode="philox", auto_reset=False,
                  obs_f64=False, micro=1, balanced_three_phase="auto", grid_unbalance_ratio=(1.0, 1.0),
-                 config=None):
+                 config=None, **config_kwargs):
+        """config_kwargs: further EnvConfig fields (reward_list, der_id, config_file, refine_input_level,
+        refine_on_action, startup_substeps, startup_level, max_episode_steps)."""
         import torch
 
         self.torch = torch
@@ -37,13 +39,18 @@ class PVDERVecEnv:
         if not torch.cuda.is_available():
             raise RuntimeError("PVDERVecEnv needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("PVDERVecEnv needs a CUDA device (sm_100a); there is no CPU fallback")
+        if self.device.index is None:      # 'cuda' != 'cuda:0' for torch: compare like with like in step()
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._obs_f64 = bool(obs_f64)
         self.cfg = config or EnvConfig(model_type=model_type,
                                        n_sim_time_steps_per_env_step=n_sim_time_steps_per_env_step,
                                        max_sim_time=max_sim_time, DISCRETE_REWARD=DISCRETE_REWARD,
                                        goals_list=list(goals_list), events_spec=events_spec,
                                        event_mode=event_mode, seed=seed, auto_reset=auto_reset, micro=micro,
                                        balanced_three_phase=balanced_three_phase,
-                                       grid_unbalance_ratio=tuple(grid_unbalance_ratio))
+                                       grid_unbalance_ratio=tuple(grid_unbalance_ratio), **config_kwargs)
         self.num_envs = int(num_envs)
         self.env_offset = int(env_offset)
         self.ns = self.cfg.n_state
@@ -100,11 +107,11 @@ class PVDERVecEnv:
         t = self.torch
         if not isinstance(actions, t.Tensor):
             actions = t.as_tensor(np.asarray(actions), device=self.device)
+        if actions.numel() != self.num_envs or actions.dim() > 2:     # checked BEFORE any copy: nothing is broadcast
+            raise ValueError(f"actions must have num_envs = {self.num_envs} elements, got shape {tuple(actions.shape)}")
         if actions.dtype != t.int32 or actions.device != self.device or not actions.is_contiguous():
-            self._actions.copy_(actions.to(self.device))
+            self._actions.copy_(actions.to(self.device).reshape(self.num_envs))
             actions = self._actions
-        if actions.numel() != self.num_envs:
-            raise ValueError("actions must have num_envs elements")
         with t.cuda.device(self.device):
             if self.traj is None:
                 _cabi.check(self.lib.pvder_step(self._cfgp(), _ptr(self.sd), _ptr(self.si), self.ld, _ptr(actions),
@@ -228,3 +235,81 @@ class PVDERVecEnv:
 
     def close(self):
         pass
+
+    # ---- goals (PVDER_env.py:445-456) and the return sweep (:458-497) -----------------------
+    def update_env_goal(self, goal_type=None, goal_spec=None):
+        """PVDER.update_env_goal.  (None, None) installs every goal's required reward/action terms, like the reference
+        (:447-452).  Otherwise ``goal_spec = {"reward": [...]}`` selects the reward list (`my_spec`, :249) of
+        ``goal_type`` -- its required term plus optional ones (env_goal_spec :78-93) -- the part the reference left
+        "under construction" (:454-456); it takes effect at once if goal_type is the current goal."""
+        from ..config import GOAL_SPEC, validate_reward_list
+
+        if goal_type is None and goal_spec is None:
+            self._goal_rewards = {}
+            reward_list = None
+        else:
+            if goal_type not in GOAL_SPEC:
+                raise ValueError("{} is not a valid goal!".format(goal_type))
+            extra = set(goal_spec or {}) - {"reward"}
+            if extra:
+                raise ValueError("{} is not a valid goal spec entry!".format(sorted(extra)))
+            reward_list = validate_reward_list(goal_type, (goal_spec or {}).get("reward"))
+            if not hasattr(self, "_goal_rewards"):
+                self._goal_rewards = {}
+            self._goal_rewards[goal_type] = reward_list
+            if goal_type != self.cfg.goals_list[0]:
+                return
+        self._set_goal(self.cfg.goals_list[0], reward_list)
+
+    def _set_goal(self, goal, reward_list=None):
+        import dataclasses
+
+        if reward_list is None:
+            reward_list = getattr(self, "_goal_rewards", {}).get(goal)
+        fields = {f.name: getattr(self.cfg, f.name) for f in dataclasses.fields(self.cfg)}
+        fields.update(goals_list=[goal], reward_list=reward_list)
+        self.cfg = EnvConfig(**fields)
+
+    def calc_returns(self, n_episodes=2, action_specs=("random", "inc", "dec", "no_change"), goals=None):
+        """PVDER.calc_returns (PVDER_env.py:458-497) as a BATCHED evaluation: for every goal, the fixed policies
+        'random' / 'inc' / 'dec' / 'no_change' x n_episodes run as ONE vector env (env j = spec j // n_episodes, episode
+        j % n_episodes), one launch per env step, so the whole sweep costs 3 x episode_steps launches instead of
+        3 x 4 x n_episodes serial episodes.  Same action mapping as the reference ('inc' -> 0, 'dec' -> 1, 'no_change'
+        -> 2, :480-486).  Env j draws the events and random actions of GLOBAL env index env_offset + j, so a serial
+        N = 1 run with env_offset = j reproduces its number.  Returns {goal: {spec: {'return', 'ref'}}} and stores it in
+        ``env_average_return``."""
+        from ..config import GOAL_SPEC
+        import dataclasses
+
+        t = self.torch
+        specs = list(action_specs)
+        fixed = {"inc": 0, "dec": 1, "no_change": 2}
+        for sp in specs:
+            if sp != "random" and sp not in fixed:
+                raise ValueError(f"unknown action spec {sp!r}")
+        n = len(specs) * int(n_episodes)
+        ex = self.cfg.extras
+        out = {}
+        for goal in (goals or GOAL_SPEC):
+            fields = {f.name: getattr(self.cfg, f.name) for f in dataclasses.fields(self.cfg)}
+            fields.update(goals_list=[goal], reward_list=getattr(self, "_goal_rewards", {}).get(goal), auto_reset=False)
+            env = PVDERVecEnv(n, device=self.device, env_offset=self.env_offset, config=EnvConfig(**fields))
+            env.reset()
+            acts = t.zeros(n, dtype=t.int32, device=self.device)
+            rand = t.zeros(n, dtype=t.int32, device=self.device)
+            is_random = t.tensor([specs[j // n_episodes] == "random" for j in range(n)], device=self.device)
+            const = t.tensor([fixed.get(specs[j // n_episodes], 0) for j in range(n)], dtype=t.int32, device=self.device)
+            ret = t.zeros(n, dtype=t.float64, device=self.device)
+            for _ in range(env.cfg.episode_steps):
+                env.sample_actions(rand)
+                t.where(is_random, rand, const, out=acts)
+                _, rew, done, _ = env.step(acts)
+                ret += rew.to(t.float64)
+            assert bool(done.all())
+            env.check_status()
+            ret = ret.view(len(specs), n_episodes).mean(dim=1).cpu().numpy()
+            vdc = (env.field("Vdc_ref").view(len(specs), n_episodes)[:, -1] * ex["Vbase"]).cpu().numpy()
+            q = (env.field("Q_ref").view(len(specs), n_episodes)[:, -1] * ex["Sbase"]).cpu().numpy()
+            out[goal] = {sp: {"return": float(ret[i]), "ref": [float(vdc[i]), float(q[i])]} for i, sp in enumerate(specs)}
+        self.env_average_return = out
+        return out

@@ -20,10 +20,11 @@
 extern "C" {
 #endif
 
-#define PVDER_ABI_VERSION 2
+#define PVDER_ABI_VERSION 3
 #define PVDER_OBS_DIM 11          /* PVDER_env.py:44-51 observed_quantities */
 #define PVDER_N_ACTIONS 5         /* PVDER_env.py:50 Discrete(5) */
 #define PVDER_MAX_STATES 23
+#define PVDER_FINE_LEVELS 3       /* fine-step levels: sub-steps of h/2, h/4, h/8 (refine_input_level, startup_level) */
 
 /* ---- sd field offsets (rows of the double state matrix), ns = number of ODE states ---- */
 #define PVDER_SD_Y 0              /* rows 0..ns-1: ODE state, order SURVEY.md A.1, last = delta = wte - w*t */
@@ -47,6 +48,9 @@ extern "C" {
 #define PVDER_SI_FIELDS 12
 
 enum { PVDER_GOAL_VOLTAGE = 0, PVDER_GOAL_Q = 1, PVDER_GOAL_POWER = 2 };      /* PVDER_env.py:78-93 */
+/* reward terms (PVDER_env.py:67-71 reward_list 'valid'; evaluated at :251-299) */
+enum { PVDER_TERM_VOLTAGE = 0, PVDER_TERM_Q = 1, PVDER_TERM_POWER = 2, PVDER_TERM_VDC = 3 };
+#define PVDER_MAX_REWARD_TERMS 4
 enum { PVDER_EVENTS_NONE = 0, PVDER_EVENTS_PHILOX = 1, PVDER_EVENTS_TABLE = 2 };
 enum { PVDER_STATUS_OK = 0, PVDER_STATUS_BAD_ACTION = 1, PVDER_STATUS_NONFINITE = 2,
        PVDER_STATUS_UNBALANCED = 3 /* balanced3 mode met a per-phase duty-cycle clamp */ };
@@ -79,7 +83,7 @@ typedef struct pvder_env_config {
   pvder_params par;
   int32_t phases;            /* 1: model_1 / derId 10, 3: model_2 / derId 50 (PVDER_env.py:56-58) */
   int32_t n_sub_per_step;    /* half-cycle sub-steps per env step = 2 * n_sim_time_steps_per_env_step */
-  int32_t micro;             /* integrator steps per half-cycle sub-step (1) */
+  int32_t base_level;        /* fine-step level of every sub-step: 2^base_level integrator steps per half-cycle (0) */
   int32_t done_substep;      /* done when k >= done_substep  (tStop >= max_sim_time, PVDER_env.py:183) */
   int32_t discrete_reward;   /* DISCRETE_REWARD (PVDER_env.py:590-600) */
   int32_t goal;              /* PVDER_GOAL_* = goals_list[0] (PVDER_env.py:234) */
@@ -89,6 +93,17 @@ typedef struct pvder_env_config {
   int32_t ev_voltage_enable, ev_insol_enable;
   int32_t balanced3;         /* phases == 3: PVDER_3PH_*: general 23-state integration, balanced set on phase a
                                 (b, c = rotated copies), or per-env auto-detection */
+  /* Fine steps (level L = 2^L integrator steps of h/2^L instead of one of h = 1/120 s; 0 = off, max PVDER_FINE_LEVELS).
+     The reference's LSODA (PVDER_env.py:166) adapts its step to input steps and to the PLL pull-in after
+     reset; the fixed half-cycle grid refines exactly those sub-steps. */
+  int32_t refine_input_level; /* the sub-step whose inputs changed at its start: an event instant, or (refine_on_action)
+                                 an action that moved Q_ref / Vdc_ref */
+  int32_t refine_on_action;
+  int32_t startup_substeps;   /* sub-steps k < startup_substeps of every episode (PLL pull-in: wte0 = 6.28 is ~90 degrees */
+  int32_t startup_level;      /* from lock, config_der.json:18) are taken at startup_level */
+  int32_t reward_terms[PVDER_MAX_REWARD_TERMS]; /* PVDER_TERM_* in the order of env_goal_spec[goal]['reward']['my_spec']
+                                 (PVDER_env.py:249), -1 terminated: the reward is their sum.  Default: the goal's
+                                 required term (:451) */
   double ev_v_min, ev_v_max, ev_s_min, ev_s_max;
   double delQ_pu, delVdc_pu; /* per-step reference increments (PVDER_env.py:617-618, :225, :229) */
   double max_sim_time;       /* PVDER_env.py:561-575 */

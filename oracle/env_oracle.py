@@ -15,6 +15,15 @@ Two integrator tiers:
   solver="tight": LSODA at rtol=1e-11/atol=1e-12 per half-cycle piece with the
       event values and anti-windup mode sampled at the piece start -- the
       numerical truth the CUDA trajectories are compared against.
+  solver="tight_continuous": like "tight", but with the anti-windup clamp decided (nearly) continuously, as pvder
+      does inside its right-hand side, instead of once per half-cycle.  Evaluating the clamp inside
+      the RHS (freeze=None) makes the system a discontinuous (Filippov) one that CHATTERS on the switching surface
+      |i_ref| = iref_limit -- a tight LSODA stalls there ("excess work", 2e6 steps in one half-cycle), and the
+      reference's own loose LSODA call fails sporadically in the same regime (bench.py counts those).  The converged
+      behaviour is the sliding (Filippov) solution, which a zero-order-hold of the clamp decision approaches as its
+      period goes to zero: this tier samples the clamp ``clamp_m`` (default 64) times per half-cycle, each piece
+      integrated by the tight LSODA.  Used to MEASURE the gap between the kernel's half-cycle clamp sampling
+      ("tight", clamp_m = 1) and the continuous clamp (tests/test_oracle_known_answers.py).
   solver="ros4l": the fixed-step twin of the kernel's integrator: ONE step of the 4-stage
       L-stable Rosenbrock method ROS4-L (Hairer & Wanner, Solving ODEs II, IV.7) per half-cycle piece, on this
       file's model with a dense numpy solve -- an independent implementation of the scheme the kernel codes with a
@@ -95,9 +104,9 @@ def create_random_events(spec, rng: random.Random) -> EventTable:
     return tab
 
 
-def discrete_class(err_rel: float, hi: float) -> int:
-    """PVDER_env.py:280-285 (and 268-273, 292-297)."""
-    if err_rel <= 0.01:
+def discrete_class(err_rel: float, hi: float, lo: float = 0.01) -> int:
+    """PVDER_env.py:280-285 (and 268-273, 292-297; Vdc_error :255-260 uses lo = 0.02)."""
+    if err_rel <= lo:
         return 1
     if err_rel >= hi:
         return -5
@@ -110,12 +119,13 @@ class OraclePVDEREnv:
     def __init__(self, n_sim_time_steps_per_env_step=15, max_sim_time=40.0, DISCRETE_REWARD=True,
                  goals_list=("voltage_regulation",), model_type="model_2", solver="reference",
                  events_spec=None, events: EventTable | None = None, seed=None,
-                 max_episode_steps=500, vg_ratio=(1.0, 1.0, 1.0), pll_mode="abc_dq0"):
+                 max_episode_steps=500, vg_ratio=(1.0, 1.0, 1.0), pll_mode="abc_dq0", reward_list=None):
         self.n = int(n_sim_time_steps_per_env_step)
         limit = max_episode_steps * self.n * TINC
         self.max_sim_time = min(max(float(max_sim_time), 1.0), limit)   # PVDER_env.py:561-575
         self.DISCRETE_REWARD = bool(DISCRETE_REWARD)
         self.goal = list(goals_list)[0]
+        self.reward_list = list(reward_list) if reward_list else None   # env_goal_spec[goal]['reward']['my_spec']
         self.params = load_der_params(MODEL_SPEC[model_type])
         self.params.vg_ratio = tuple(float(r) for r in vg_ratio)    # pvder Grid(unbalance_ratio_b/c); env default 1.0
         self.params.pll_mode = pll_mode
@@ -133,6 +143,13 @@ class OraclePVDEREnv:
         # reference path raises the cap (documented deviation).
         self.mxstep = 500
         self.max_nst = 0
+        # fine steps of the kernel's half-cycle grid (solver="ros4l" only; EnvConfig defaults, DESIGN.md "Fine steps"):
+        # 2^level steps of h / 2^level for the sub-step that follows an event instant (and, with refine_on_action, an
+        # action that moved a reference) and for the first startup_substeps sub-steps of an episode
+        self.refine_input_level, self.refine_on_action = 1, False
+        self.startup_substeps, self.startup_level = 12, 3
+        self._inputs_changed = False
+        self.clamp_m = 64             # solver="tight_continuous": clamp decisions per half-cycle
 
     # -- reset (PVDER_env.py:316-334, 366-398) --
     def reset(self, y0=None):
@@ -167,6 +184,7 @@ class OraclePVDEREnv:
         self.Q_ref = self.Q_ref + dQ                                 # :225
         self.Vdc_ref = self.Vdc_ref + dV                             # :229
         self.steps += 1
+        self._inputs_changed = action != 0
         ok = self._integrate(2 * self.n)
         assert ok, "Convergence flag should be true to calculate reward!"   # :177
         self._reward = self.reward_calc()
@@ -199,9 +217,25 @@ class OraclePVDEREnv:
             mask = m.freeze_mask(self.y, self._inputs(t0))
             if any(mask):
                 self.windup_substeps += 1
+            if self.solver == "tight_continuous":
+                # events frozen per half-cycle, clamp decision re-sampled clamp_m times inside it
+                y = self.y
+                for j in range(self.clamp_m):
+                    ta = t0 + (t1 - t0) * j / self.clamp_m
+                    tb = t0 + (t1 - t0) * (j + 1) / self.clamp_m
+                    inp = self._inputs(t0, freeze=m.freeze_mask(y, self._inputs(t0)))
+                    sol, info = odeint(lambda y_, t: m.rhs(y_, t, inp), y, [ta, tb],
+                                       Dfun=lambda y_, t: m.jac(y_, t, inp), full_output=1, mxstep=200000,
+                                       atol=1e-12, rtol=1e-11)
+                    if info["message"] != "Integration successful.":
+                        return False
+                    y = sol[-1]
+                self.y = y
+                self.k += 1
+                continue
             inp = self._inputs(t0, freeze=mask)
             if self.solver == "ros4l":
-                self.y = ros4l_step(m, inp, self.y, t0, t1 - t0)
+                self.y = self._ros4l_substep(inp, t0, t1)
                 self.k += 1
                 continue
             sol, info = odeint(lambda y, t: m.rhs(y, t, inp), self.y, [t0, t1],
@@ -213,10 +247,29 @@ class OraclePVDEREnv:
             self.k += 1
         return True
 
+    def _ros4l_substep(self, inp, t0, t1):
+        """Kernel twin: one half-cycle sub-step as 2^level ROS4-L steps, clamp mode re-sampled before every fine step."""
+        m = self.model
+        ev_here = any(abs(T - t0) < 1e-9 for T, _ in self.events.grid + self.events.solar)
+        lvl = self.refine_input_level if (ev_here or (self._inputs_changed and self.refine_on_action)) else 0
+        self._inputs_changed = False
+        if self.k < self.startup_substeps:
+            lvl = max(lvl, self.startup_level)
+        nf = 1 << lvl
+        h = (t1 - t0) / nf
+        y = self.y
+        for j in range(nf):
+            if j:
+                mask = m.freeze_mask(y, self._inputs(t0))
+                inp = self._inputs(t0, freeze=mask)
+            y = ros4l_step(m, inp, y, t0 + j * h, h)
+        return y
+
     # -- reward (PVDER_env.py:231-301) --
     def reward_calc(self):
         out = self.model.outputs(self.y, self._inputs(self.t()))
-        return reward_from_outputs(out, self.goal, self.DISCRETE_REWARD, self.Q_ref, self.params)
+        return reward_from_outputs(out, self.goal, self.DISCRETE_REWARD, self.Q_ref, self.params, self.reward_list,
+                                   self.Vdc_ref)
 
     # -- obs (PVDER_env.py:531-542) --
     @property
@@ -258,18 +311,32 @@ def ros4l_step(model, inp, y, t0, h):
     return out
 
 
-def reward_from_outputs(out, goal, discrete, Q_ref, params):
-    """PVDER_env.py:231-301 for the 'required' reward of each goal (:249, :451)."""
-    if goal == "voltage_regulation":
-        x, target, hi = out["Vrms"], params.Vrms_ref, 0.05
-    elif goal == "Q_regulation":
-        x, target, hi = out["Q_PCC"], Q_REF_VAR / params.Sbase, 0.05
-    elif goal == "power_regulation":
-        x, target, hi = out["P_PCC"], P_REF_W / params.Sbase, 0.03
-    else:
+REQUIRED_TERM = {"voltage_regulation": "voltage_error", "Q_regulation": "Q_error", "power_regulation": "power_error"}
+
+
+def reward_from_outputs(out, goal, discrete, Q_ref, params, reward_list=None, Vdc_ref=None):
+    """PVDER_env.py:231-301: sum over the goal's reward list (`my_spec`, :249; default = the required term, :451)."""
+    if goal not in REQUIRED_TERM:
         raise ValueError(goal)
-    if discrete:
-        if goal == "Q_regulation" and target == 0.0:
-            target = 1e-6
-        return discrete_class(abs(x - target) / abs(target), hi)
-    return -((x - target) ** 2)
+    rewards = []
+    for term in (reward_list or [REQUIRED_TERM[goal]]):
+        lo, hi = 0.01, 0.05
+        if term == "voltage_error":                                          # :276-287
+            x, target = out["Vrms"], params.Vrms_ref
+        elif term == "Q_error":                                              # :263-275, target :238-241
+            x = out["Q_PCC"]
+            target = Q_ref if goal == "voltage_regulation" else Q_REF_VAR / params.Sbase
+            if discrete and target == 0.0:
+                target = 1e-6
+        elif term == "power_error":                                          # :290-299
+            x, target, hi = out["P_PCC"], P_REF_W / params.Sbase, 0.03
+        elif term == "Vdc_error":                                            # :251-262 (target defined at :243 only)
+            assert goal == "power_regulation", "Vdctarget is undefined for this goal (reference NameError)"
+            x, target, lo = out["Vdc"], Vdc_ref, 0.02
+        else:
+            raise ValueError(term)
+        if discrete:
+            rewards.append(discrete_class(abs(x - target) / abs(target), hi, lo))
+        else:
+            rewards.append(-((x - target) ** 2))
+    return sum(rewards)

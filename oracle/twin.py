@@ -81,7 +81,7 @@ def sample_actions_twin(seed, step_index, n_envs, env_offset):
     return ((r[0] * np.uint64(5)) >> np.uint64(32)).astype(np.int32)
 
 
-def outputs_twin(par, phases, y, Qref, Vdcref, Vgrid, Sinsol, k, max_sim_time, goal, discrete):
+def outputs_twin(par, phases, y, Qref, Vdcref, Vgrid, Sinsol, k, max_sim_time, goal, discrete, reward_terms=None):
     """par: object with Rt, Xt, vgs, Vrms_ref, p_target, q_target, np_iph100, np_irs, kappa, pv_scale.
     y: [ns, N].  Returns (obs[N,11] float64, reward[N] float64, Vrms[N])."""
     y = np.asarray(y, dtype=np.float64)
@@ -108,18 +108,25 @@ def outputs_twin(par, phases, y, Qref, Vdcref, Vgrid, Sinsol, k, max_sim_time, g
     Ppv = np.maximum(Ipv * y[B] * par.pv_scale, 0.0)
     obs = np.stack([y[0], y[1], vaR, vaI, P, Q, y[B], Ppv, np.broadcast_to(Vdcref, P.shape),
                     np.broadcast_to(Qref, P.shape), (np.asarray(k, dtype=np.float64) / 120.0) / max_sim_time], axis=1)
-    if goal == 0:
-        x, target, hi = Vrms, par.Vrms_ref, 0.05
-    elif goal == 1:
-        x, target, hi = Q, par.q_target, 0.05
-    else:
-        x, target, hi = P, par.p_target, 0.03
-    if discrete:
-        if goal == 1 and target == 0.0:
-            target = 1e-6
-        err = np.abs(x + (-target)) / abs(target)
-        reward = np.where(err <= 0.01, 1.0, np.where(err >= hi, -5.0, -1.0))
-    else:
-        d = x + (-target)
-        reward = -(d * d)
-    return obs, reward, Vrms
+    terms = reward_terms if reward_terms is not None else (goal,)      # default: the goal's required term (ids coincide)
+    rsum = np.zeros(P.shape)
+    for tid in terms:
+        lo, hi = 0.01, 0.05
+        if tid == 0:
+            x, target = Vrms, par.Vrms_ref
+        elif tid == 1:
+            x = Q
+            target = np.asarray(Qref, dtype=np.float64) if goal == 0 else par.q_target
+            if discrete:
+                target = np.where(target == 0.0, 1e-6, target)
+        elif tid == 2:
+            x, target, hi = P, par.p_target, 0.03
+        else:
+            x, target, lo = y[B], np.asarray(Vdcref, dtype=np.float64), 0.02
+        if discrete:
+            err = np.abs(x + (-target)) / np.abs(target)
+            rsum = rsum + np.where(err <= lo, 1.0, np.where(err >= hi, -5.0, -1.0))
+        else:
+            d = x + (-target)
+            rsum = rsum + (-(d * d))
+    return obs, rsum, Vrms

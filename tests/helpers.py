@@ -74,11 +74,3 @@ def assert_episode_step_close(y, obs, y_ref, obs_ref, phases, in_windup, what=""
     else:
         assert_state_close(y, y_ref, phases, rtol=2e-4, atol=1e-6, xpll_atol=2e-3, delta_atol=2e-5, what=what + " (windup)")
         np.testing.assert_allclose(obs, obs_ref, rtol=2e-4, atol=1e-6, err_msg=f"{what} obs (windup)")
-
-
-# Absolute floor of the random-action trajectory of the full-episode fixtures.  Its first event is a 9.4 % voltage sag
-# that coincides with an action; one env step later the quadrature pair (iI, xQ) of the single-phase model -- values of
-# 4e-3 pu -- is off by 1.77e-7 pu, 1.2x the 1e-7 floor used everywhere else.  Rodas4 gives the same figure to 1 %: it is
-# the response of ONE half-cycle step to a large input step, not a property of the scheme.  All other 479 (trajectory,
-# step) points of the fixture, and every point of the config-2 trajectories, hold the 1e-7 floor (worst 0.66x).
-EPISODE_SAG_ATOL = 2e-7

@@ -20,7 +20,7 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
                      const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
                      uint8_t* done, int64_t n, int64_t off) {
   constexpr int NS = M::NS_STORE;
-  const RodasTab tab = make_rodas_tab<M>(cfg.par, cfg.substeps_per_sec * (double)cfg.micro);
+  const RodasTab tab = make_rodas_tab<M>(cfg.par, cfg.substeps_per_sec);
   for (int64_t e = 0; e < n; ++e) {
     EnvRegs<M> r;
     load_state<M>(sd, ld, e, r.y);
@@ -164,7 +164,7 @@ static void step_all_split(const pvder_env_config& cfg, double* sd, int32_t* si,
                            const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
                            uint8_t* done, int64_t n, int64_t off) {
   constexpr int NS = 23;
-  const RodasTab tab = make_rodas_tab<Split3>(cfg.par, cfg.substeps_per_sec * (double)cfg.micro);
+  const RodasTab tab = make_rodas_tab<Split3>(cfg.par, cfg.substeps_per_sec);
   const Lanes3 ln;
   for (int64_t e = 0; e < n; ++e) {
     EnvRegsSplit r;

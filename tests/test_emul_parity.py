@@ -200,8 +200,9 @@ def test_n1_observations_two_substeps_after_steps_in_the_inputs(model_type):
     """n_sim_time_steps_per_env_step = 1: every observation is taken only two half-cycle sub-steps after an action, and the
     events at t = 1, 2, 3 s land right before one.  This is the hardest case for a Rosenbrock scheme that is not stiffly
     accurate (ROS4-L): the stiff current modes are excited by the step and must be gone two steps later.  200 env
-    steps with random actions, sags to 0.90 pu and insolation steps against the tight oracle, same tolerances (PLL
-    pull-in, the first 0.25 s, excluded as everywhere), integer rewards equal throughout."""
+    steps with random actions, sags to 0.90 pu and insolation steps against the tight oracle, same tolerances FROM THE
+    FIRST ENV STEP ON (the PLL pull-in of the first 0.1 s is integrated with fine steps: startup_substeps/startup_level),
+    integer rewards equal throughout."""
     import random
     ev = H.random_events(11)
     em = E.EmulVecEnv(1, model_type=model_type, events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=True,
@@ -217,9 +218,8 @@ def test_n1_observations_two_substeps_after_steps_in_the_inputs(model_type):
         oo, orw, od, _ = orc.step(a)
         eo, erw, ed, _ = em.step([a])
         assert orw == erw[0] and od == ed[0]
-        if s >= 15:
-            np.testing.assert_allclose(eo[0], oo, rtol=H.RTOL, atol=H.ATOL, err_msg=f"step {s}")
-            H.assert_state_close(em.sd[:orc.model.n, 0], H.oracle_delta_state(orc), em.cfg.phases, what=f"{model_type} step {s}")
+        np.testing.assert_allclose(eo[0], oo, rtol=H.RTOL, atol=H.ATOL, err_msg=f"step {s}")
+        H.assert_state_close(em.sd[:orc.model.n, 0], H.oracle_delta_state(orc), em.cfg.phases, what=f"{model_type} step {s}")
 
 
 @pytest.mark.parametrize("model_type,mode", [("model_1", "auto"), ("model_2", "auto"), ("model_2", "split")])
@@ -242,35 +242,39 @@ def test_golden_full_episode(model_type, mode):
         for i in range(n):
             wind = bool(gold["windup"][i, s] > 0)
             H.assert_episode_step_close(em.sd[:em.ns, i], obs[i], gold["state"][i, s], gold["obs"][i, s], em.cfg.phases,
-                                        wind, what=f"{model_type} traj{i} step{s}",
-                                        atol=H.EPISODE_SAG_ATOL if i == 2 else H.ATOL)
+                                        wind, what=f"{model_type} traj{i} step{s}")
             assert abs(rew[i] - gold["reward"][i, s]) <= (2e-4 if wind else 1e-5) * abs(gold["reward"][i, s]) + 1e-10
     assert done.all()
 
 
-def test_input_step_refinement_build_holds_the_floor_everywhere(tmp_path):
-    """-DPVDER_REFINE_INPUT_STEP=1 (study build, off in the product: DESIGN.md open items): with the sub-step after an
-    action or event taken as two half-size steps, the single-phase full-episode fixture holds the standard 1e-7 floor
-    on every trajectory -- including the random/sag one that needs EPISODE_SAG_ATOL in the product build -- and the
-    anti-windup sub-step count of the +Q cycle still equals the oracle's."""
-    import ctypes as C
-    import subprocess
-    lib = str(tmp_path / "libpvder_emul_refine.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                    "-DPVDER_REFINE_INPUT_STEP=1", "-o", lib, E._SRC], check=True)
+def test_fine_steps_are_what_holds_the_floor():
+    """The fine steps are not decoration: with refine_input_level = 0 the env step after the 9.4 % sag of the random/sag
+    episode leaves the quadrature pair (iI, xQ) 1.2x outside the 1e-7 floor, with startup_level = 0 the PLL states miss
+    their bounds during the first 0.1 s at n = 1; the defaults (test_golden_full_episode, test_n1_observations...) hold
+    both.  The anti-windup sub-step count of the +Q cycle equals the oracle's either way."""
     gold = np.load("tests/golden/golden_episode_model_1.npz")
     acts = gold["actions"]
     n, nsteps = acts.shape
-    em = E.EmulVecEnv(n, model_type="model_1", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False)
-    em.lib = C.CDLL(lib)
+    em = E.EmulVecEnv(n, model_type="model_1", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False,
+                      refine_input_level=0)
     em.set_event_tables(gold["vgrid_tab"], gold["sinsol_tab"])
     em.reset()
+    worst = 0.0
     for s in range(nsteps):
-        obs, rew, done, _ = em.step(acts[:, s])
-        for i in range(n):
-            H.assert_state_close(em.sd[:em.ns, i], gold["state"][i, s], 1, what=f"refined traj{i} step{s}")
-            np.testing.assert_allclose(obs[i], gold["obs"][i, s], rtol=H.RTOL, atol=H.ATOL)
+        em.step(acts[:, s])
+        if not gold["windup"][2, s]:
+            y, yr = em.sd[:em.ns, 2], gold["state"][2, s]
+            worst = max(worst, float((np.abs(y - yr)[:9] / (H.RTOL * np.abs(yr[:9]) + H.ATOL)).max()))
+    assert 1.0 < worst < 1.5
     assert int(em.si[10, 1]) == int(gold["windup"][1, -1]) > 0
+    em = E.EmulVecEnv(1, model_type="model_1", events_spec={"voltage": {"ENABLE": False}}, n_sim_time_steps_per_env_step=1,
+                      startup_level=0)
+    orc = OraclePVDEREnv(model_type="model_1", solver="tight", events=EventTable(), n_sim_time_steps_per_env_step=1)
+    em.reset()
+    orc.reset()
+    em.step([0])
+    orc.step(0)
+    assert abs(em.sd[10, 0] - H.oracle_delta_state(orc)[10]) > 100 * 5e-6     # delta: > 100x its bound without the fine steps
 
 
 @pytest.mark.parametrize("model_type", ["model_1", "model_2"])

@@ -145,7 +145,7 @@ def test_config2_full_episode_4096_envs(cuda, model_type, balanced):
             i = t                                  # first env of the trajectory
             wind = bool(gold["windup"][t, s] > 0)
             H.assert_episode_step_close(y[:, i], o64[i], gold["state"][t, s], gold["obs"][t, s], phases, wind,
-                                        what=f"{model_type} traj{t} step{s}", atol=H.EPISODE_SAG_ATOL if t == 2 else H.ATOL)
+                                        what=f"{model_type} traj{t} step{s}")
     assert bool(done.all())
 
 

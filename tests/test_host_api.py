@@ -29,7 +29,7 @@ def test_struct_layout_matches_header():
     """ctypes mirror and C struct agree (size is checked through a host-only call using the struct)."""
     cfg = G.EnvConfig(model_type="model_1")
     assert C.sizeof(_cabi.Params) == 29 * 8
-    assert C.sizeof(_cabi.EnvConfigC) == 29 * 8 + 14 * 4 + 11 * 8 + 23 * 8 + 2 * 8
+    assert C.sizeof(_cabi.EnvConfigC) == 29 * 8 + 22 * 4 + 11 * 8 + 23 * 8 + 2 * 8
     assert _cabi.load().pvder_config_size() == C.sizeof(_cabi.EnvConfigC)
     assert list(cfg.c.y0)[:11] == cfg.y0 and cfg.c.y0[10] == 6.28
 
