@@ -22,7 +22,7 @@ MAX_STATES = 23
 OBS_DIM = 11
 N_ACTIONS = 5
 FINE_LEVELS = 3
-SI_K, SI_STEPS, SI_EPISODE, SI_STATUS, SI_DONE, SI_HIST, SI_WINDUP, SI_EXACT, SI_FIELDS = 0, 1, 2, 3, 4, 5, 10, 11, 12
+SI_K, SI_STEPS, SI_EPISODE, SI_STATUS, SI_DONE, SI_HIST, SI_WINDUP, SI_EXACT, SI_REDO_LIST, SI_REDO_CTRL, SI_FIELDS = 0, 1, 2, 3, 4, 5, 10, 11, 12, 13, 14
 GOALS = {"voltage_regulation": 0, "Q_regulation": 1, "power_regulation": 2}
 REWARD_TERMS = {"voltage_error": 0, "Q_error": 1, "power_error": 2, "Vdc_error": 3}
 EVENT_MODES = {"none": 0, "philox": 1, "table": 2}
@@ -85,6 +85,7 @@ SIGNATURES = {
     "pvder_fp64_peak": (C.c_int, [C.c_int, C.POINTER(_dbl), C.POINTER(_dbl)]),
     "pvder_env_create": (C.c_int, [_cfgp, _i64, _i64, C.POINTER(_vp)]),
     "pvder_env_destroy": (C.c_int, [_vp]),
+    "pvder_env_reconfigure": (C.c_int, [_vp, _cfgp]),
     "pvder_env_set_event_tables": (C.c_int, [_vp, _vp, _vp]),
     "pvder_env_reset_host": (C.c_int, [_vp, _vp, _vp]),
     "pvder_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -914,32 +914,4 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
 }
 
 
-// Three-phase "auto" mode: a balanced state (the only kind the env itself creates) is integrated by
-// the 11-state balanced model, anything else by the general 23-state model.
-template <bool RECORD = true>
-PVDER_DEV bool advance_env_auto3(const pvder_env_config& cfg, const RodasTab& tab, EnvRegs<Model3ph>& r, int act,
-                                 bool active, const double* vtab, const double* stab, int64_t ld, int64_t e,
-                                 uint32_t env_glob, Outputs& o, int& done_out, int& hist_inc, bool& hist_clear,
-                                 double* traj = nullptr, int64_t traj_ld = 0) {
-  if (is_balanced(r.y)) {
-    EnvRegs<Model3phBal> b;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) b.y[i] = r.y[i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) b.y[6 + i] = r.y[18 + i];
-    b.Qref = r.Qref; b.Vdcref = r.Vdcref; b.Vgrid = r.Vgrid; b.Sinsol = r.Sinsol; b.ret = r.ret;
-    b.last_reward = r.last_reward; b.k = r.k; b.steps = r.steps; b.episode = r.episode; b.status = r.status;
-    b.done = r.done; b.windup = r.windup; b.exact = r.exact;
-    const bool run = advance_env<Model3phBal, RECORD>(cfg, tab, b, act, active, vtab, stab, ld, e, env_glob, o, done_out,
-                                              hist_inc, hist_clear, traj, traj_ld);
-    expand_balanced(b.y, r.y);
-    r.Qref = b.Qref; r.Vdcref = b.Vdcref; r.Vgrid = b.Vgrid; r.Sinsol = b.Sinsol; r.ret = b.ret;
-    r.last_reward = b.last_reward; r.k = b.k; r.steps = b.steps; r.episode = b.episode; r.status = b.status;
-    r.done = b.done; r.windup = b.windup; r.exact = b.exact;
-    return run;
-  }
-  return advance_env<Model3ph, RECORD>(cfg, tab, r, act, active, vtab, stab, ld, e, env_glob, o, done_out, hist_inc, hist_clear,
-                               traj, traj_ld);
-}
-
 }  // namespace pvder

@@ -18,6 +18,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <new>
 
 #include "pvder_common.cuh"
@@ -92,9 +93,14 @@ __device__ __forceinline__ void store_obs_block(float* __restrict__ obs, const O
 #define PVDER_STEP_BOUNDS(M) __launch_bounds__(BLOCK, min_blocks<M>())
 #endif
 
+// AUTO3 (M = Model3phBal, PVDER_3PH_AUTO): every env whose stored 23-state vector is a balanced set is integrated on
+// phase a; an env that is not -- or whose per-phase duty-cycle clamp engages during the step, which the reduction
+// cannot represent -- is left untouched and its index appended to the redo list in si (PVDER_SI_REDO_*): the
+// three-lane kernel launched right behind this one (step_kernel_split3<true>) steps those envs with the general model.
 template <class M, bool AUTO3 = false, bool RECORD = false>
 __global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_env_config cfg,
                                                      const __grid_constant__ RodasTab tab, const StepArgs a) {
+  static_assert(!AUTO3 || M::BALANCED3, "the auto mode runs on the balanced reduction");
   constexpr int NS = M::NS_STORE;   // rows of the stored state (the balanced model integrates 11 of 23)
   __shared__ float stage[BLOCK * PVDER_OBS_DIM];
   const int64_t block_first = (int64_t)blockIdx.x * BLOCK;
@@ -103,7 +109,19 @@ __global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_e
   const int64_t ec = active ? e : (a.n - 1);   // inactive lanes shadow the last env and never store
 
   EnvRegs<M> r;
-  load_state<M>(a.sd, a.ld, ec, r.y);
+  bool mine = active;                          // this kernel steps the env (AUTO3: only while it is a balanced set)
+  if constexpr (AUTO3) {
+    double z[23];
+#pragma unroll
+    for (int i = 0; i < 23; ++i) z[i] = a.sd[(int64_t)i * a.ld + ec];
+    mine = active && is_balanced(z);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.y[i] = z[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) r.y[6 + i] = z[18 + i];
+  } else {
+    load_state<M>(a.sd, a.ld, ec, r.y);
+  }
   r.Qref = a.sd[(int64_t)PVDER_SD_QREF(NS) * a.ld + ec];
   r.Vdcref = a.sd[(int64_t)PVDER_SD_VDCREF(NS) * a.ld + ec];
   r.Vgrid = a.sd[(int64_t)PVDER_SD_VGRID(NS) * a.ld + ec];
@@ -118,21 +136,26 @@ __global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_e
   r.windup = a.si[(int64_t)PVDER_SI_WINDUP * a.ld + ec];
   r.exact = a.si[(int64_t)PVDER_SI_EXACT * a.ld + ec];
   const int act = a.action[ec];
+  const int status_in = r.status;
 
   Outputs o;
   int done_out, hist_inc;
   bool hist_clear;
-  bool run;
   // RECORD = false (every launch but pvder_step_record's): no trajectory pointer lives through the sub-step loop
   double* traj = RECORD ? traj_column(a, e, active) : nullptr;
-  if constexpr (AUTO3)
-    run = advance_env_auto3<RECORD>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
+  bool run = advance_env<M, RECORD>(cfg, tab, r, act, mine, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
                                     done_out, hist_inc, hist_clear, traj, a.traj_n);
-  else
-    run = advance_env<M, RECORD>(cfg, tab, r, act, active, a.vtab, a.stab, a.ld, ec, (uint32_t)(a.env_offset + ec), o,
-                                 done_out, hist_inc, hist_clear, traj, a.traj_n);
+  if constexpr (AUTO3) {
+    if (active && (!mine || (run && status_in != PVDER_STATUS_UNBALANCED && r.status == PVDER_STATUS_UNBALANCED))) {
+      // hand the env to the general model: nothing of it is stored here, the three-lane kernel redoes the env step
+      const int slot = atomicAdd(a.si + (int64_t)PVDER_SI_REDO_CTRL * a.ld, 1);
+      a.si[(int64_t)PVDER_SI_REDO_LIST * a.ld + slot] = (int32_t)e;
+      mine = false;
+      run = false;
+    }
+  }
 
-  if (active) {
+  if (mine) {
     if (a.reward_f64) a.reward_f64[e] = o.reward;
     if (a.reward_i32) a.reward_i32[e] = o.reward_i;
     if (a.done) a.done[e] = (uint8_t)done_out;
@@ -157,11 +180,12 @@ __global__ void PVDER_STEP_BOUNDS(M) step_kernel(const __grid_constant__ pvder_e
       for (int h = 0; h < PVDER_N_ACTIONS; ++h) a.si[(int64_t)(PVDER_SI_HIST + h) * a.ld + e] = 0;
     }
   }
-  if (active) a.si[(int64_t)PVDER_SI_STATUS * a.ld + e] = r.status;
-  if (a.obs_f64 && active) {
+  if (mine) a.si[(int64_t)PVDER_SI_STATUS * a.ld + e] = r.status;
+  if (a.obs_f64 && mine) {
 #pragma unroll
     for (int j = 0; j < PVDER_OBS_DIM; ++j) a.obs_f64[e * PVDER_OBS_DIM + j] = o.obs[j];
   }
+  // (AUTO3: the rows of handed-over envs are written here too and overwritten by the three-lane kernel behind)
   if (a.obs_f32) store_obs_block(a.obs_f32, o, block_first, a.n, stage);
 }
 
@@ -181,6 +205,10 @@ constexpr int SPLIT_ENVS_PER_BLOCK = SPLIT_ENVS_PER_WARP * (BLOCK / 32);
 #else
 #define PVDER_SPLIT_BOUNDS __launch_bounds__(BLOCK, PVDER_MINBLOCKS_SPLIT)
 #endif
+// LIST = true (second launch of PVDER_3PH_AUTO): the envs to step are the entries of the redo list the balanced kernel
+// filled (si rows PVDER_SI_REDO_*); a small fixed grid walks the list -- it is empty in normal operation, the kernel
+// then costs one launch latency -- and the last CTA to finish clears the list for the next env step.
+template <bool LIST>
 __global__ void PVDER_SPLIT_BOUNDS
     step_kernel_split3(const __grid_constant__ pvder_env_config cfg, const __grid_constant__ RodasTab tab, const StepArgs a) {
   constexpr int NS = 23;
@@ -188,11 +216,16 @@ __global__ void PVDER_SPLIT_BOUNDS
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const Lanes3 ln = make_lanes(lane);
   const int g = ln.base / 3, p = ln.p;
-  const int64_t block_first = (int64_t)blockIdx.x * SPLIT_ENVS_PER_BLOCK;
   const int slot = warp * SPLIT_ENVS_PER_WARP + g;
-  const int64_t e = block_first + slot;
-  const bool active = e < a.n;
-  const int64_t ec = active ? e : (a.n - 1);   // inactive groups shadow the last env and never store
+  int32_t* ctrl = a.si + (int64_t)PVDER_SI_REDO_CTRL * a.ld;
+  const int64_t total = LIST ? (int64_t)ctrl[0] : a.n;
+  for (int64_t block_first = (int64_t)blockIdx.x * SPLIT_ENVS_PER_BLOCK; block_first < total;
+       block_first += (int64_t)gridDim.x * SPLIT_ENVS_PER_BLOCK) {
+  const int64_t idx = block_first + slot;
+  const bool active = idx < total;
+  const int64_t ic = active ? idx : (total - 1);   // inactive groups shadow the last env and never store
+  const int64_t e = LIST ? (int64_t)a.si[(int64_t)PVDER_SI_REDO_LIST * a.ld + ic] : ic;
+  const int64_t ec = e;
   const bool writer = active && lane < 30;
   const bool owner = writer && p == 0;
 
@@ -263,16 +296,36 @@ __global__ void PVDER_SPLIT_BOUNDS
 #pragma unroll
     for (int j = 0; j < PVDER_OBS_DIM; ++j) a.obs_f64[e * PVDER_OBS_DIM + j] = o.obs[j];
   }
-  if (a.obs_f32) {   // coalesced store of the block's obs rows through shared memory
-    if (lane < 30 && p == 0) {
+  if (a.obs_f32) {
+    if constexpr (LIST) {   // scattered envs: each owner lane writes its row
+      if (owner) {
 #pragma unroll
-      for (int j = 0; j < PVDER_OBS_DIM; ++j) stage[slot * PVDER_OBS_DIM + j] = (float)o.obs[j];
+        for (int j = 0; j < PVDER_OBS_DIM; ++j) a.obs_f32[e * PVDER_OBS_DIM + j] = (float)o.obs[j];
+      }
+    } else {                // coalesced store of the block's obs rows through shared memory
+      if (lane < 30 && p == 0) {
+#pragma unroll
+        for (int j = 0; j < PVDER_OBS_DIM; ++j) stage[slot * PVDER_OBS_DIM + j] = (float)o.obs[j];
+      }
+      __syncthreads();
+      const int64_t rows = min((int64_t)SPLIT_ENVS_PER_BLOCK, a.n - block_first);
+      const int total_f = (int)rows * PVDER_OBS_DIM;
+      float* dst = a.obs_f32 + block_first * PVDER_OBS_DIM;
+      for (int i2 = threadIdx.x; i2 < total_f; i2 += BLOCK) dst[i2] = stage[i2];
+      __syncthreads();
     }
+  }
+  }
+  if constexpr (LIST) {
+    // every CTA has read ctrl[0] before it takes a ticket; the last one clears list length and ticket
     __syncthreads();
-    const int64_t rows = min((int64_t)SPLIT_ENVS_PER_BLOCK, a.n - block_first);
-    const int total = (int)rows * PVDER_OBS_DIM;
-    float* dst = a.obs_f32 + block_first * PVDER_OBS_DIM;
-    for (int idx = threadIdx.x; idx < total; idx += BLOCK) dst[idx] = stage[idx];
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(ctrl + 1, 1) == (int)gridDim.x - 1) {
+        ctrl[0] = 0;
+        ctrl[1] = 0;
+      }
+    }
   }
 }
 
@@ -295,6 +348,10 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const __grid_constant__ pv
   constexpr int NS = M::NS;
   const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (e >= a.n) return;
+  if (a.init) {   // first reset after allocation: the PVDER_3PH_AUTO scratch rows start empty
+    a.si[(int64_t)PVDER_SI_REDO_LIST * a.ld + e] = 0;
+    a.si[(int64_t)PVDER_SI_REDO_CTRL * a.ld + e] = 0;
+  }
   if (a.mask && !a.mask[e]) return;
   double y[NS], Qref, Vdcref, Vgrid, Sinsol;
   init_env<M>(cfg, y, Qref, Vdcref, Vgrid, Sinsol);
@@ -664,10 +721,17 @@ static int launch_step(const pvder_env_config* cfg, double* sd, int32_t* si, int
   } while (0)
   if (cfg->phases == 1) PVDER_LAUNCH1(Model1ph, false);
   else if (cfg->balanced3 == PVDER_3PH_BALANCED) PVDER_LAUNCH1(Model3phBal, false);
-  else if (cfg->balanced3 == PVDER_3PH_AUTO) PVDER_LAUNCH1(Model3ph, true);
-  else if (cfg->balanced3 == PVDER_3PH_SPLIT) {
+  else if (cfg->balanced3 == PVDER_3PH_AUTO) {
+    // balanced sets on phase a; whatever that kernel hands over (redo list in si) goes to the three-lane kernel, a
+    // small fixed grid that finds the list empty in normal operation
+    PVDER_LAUNCH1(Model3phBal, true);
+    CK(cudaGetLastError());
+    unsigned grid3 = (unsigned)((n_envs + SPLIT_ENVS_PER_BLOCK - 1) / SPLIT_ENVS_PER_BLOCK);
+    if (grid3 > 2u * 148u) grid3 = 2u * 148u;
+    step_kernel_split3<true><<<grid3, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Split3>(cfg->par, hinv), a);
+  } else if (cfg->balanced3 == PVDER_3PH_SPLIT) {
     const unsigned grid3 = (unsigned)((n_envs + SPLIT_ENVS_PER_BLOCK - 1) / SPLIT_ENVS_PER_BLOCK);
-    step_kernel_split3<<<grid3, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Split3>(cfg->par, hinv), a);
+    step_kernel_split3<false><<<grid3, BLOCK, 0, st>>>(*cfg, make_rodas_tab<Split3>(cfg->par, hinv), a);
   }
   else PVDER_LAUNCH1(Model3ph, false);
 #undef PVDER_LAUNCH1
@@ -818,20 +882,10 @@ struct pvder_env {
   double ms_total;
   int64_t launches;
   int fresh;   // no reset_host() yet: the first one starts episode 0
+  int tab_rows;   // rows of the event tables allocated at creation (PVDER_EVENTS_TABLE)
 };
 
-int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_offset, pvder_env** out) {
-  int rc = check_cfg(cfg);
-  if (rc) return rc;
-  if (!out || n_envs < 1) return PVDER_ERR_INVALID;
-  pvder_env* h = new (std::nothrow) pvder_env();
-  if (!h) return PVDER_ERR_NOMEM;
-  std::memset(h, 0, sizeof(*h));
-  h->cfg = *cfg;
-  h->n = n_envs;
-  h->off = env_offset;
-  h->ld = (n_envs + 31) / 32 * 32;
-  h->ns = 6 * cfg->phases + 5;
+static int env_create_impl(pvder_env* h, const pvder_env_config* cfg) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
@@ -851,9 +905,9 @@ int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_of
     else if (cfg->balanced3 == PVDER_3PH_BALANCED)
       CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<Model3phBal>, BLOCK, 0));
     else if (cfg->balanced3 == PVDER_3PH_AUTO)
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<Model3ph, true>, BLOCK, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<Model3phBal, true>, BLOCK, 0));
     else if (cfg->balanced3 == PVDER_3PH_SPLIT) {
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_split3, BLOCK, 0));
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel_split3<false>, BLOCK, 0));
       envs_per_cta = SPLIT_ENVS_PER_BLOCK;
     } else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<Model3ph>, BLOCK, 0));
     if (per_sm < 1) per_sm = 1;
@@ -872,30 +926,73 @@ int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_of
   CK(cudaMalloc(&h->d_reward, sizeof(double) * h->n));
   CK(cudaMalloc(&h->d_done, h->n));
   if (cfg->event_mode == PVDER_EVENTS_TABLE && cfg->ev_count > 0) {
+    h->tab_rows = cfg->ev_count;
     CK(cudaMalloc(&h->d_vtab, sizeof(double) * cfg->ev_count * h->ld));
     CK(cudaMalloc(&h->d_stab, sizeof(double) * cfg->ev_count * h->ld));
   }
-  rc = launch_reset(&h->cfg, h->sd, h->si, h->ld, nullptr, h->d_vtab, h->d_stab, 1, nullptr, nullptr, h->n, h->off, h->stream);
+  int rc = launch_reset(&h->cfg, h->sd, h->si, h->ld, nullptr, h->d_vtab, h->d_stab, 1, nullptr, nullptr, h->n, h->off, h->stream);
   if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
   h->fresh = 1;
+  return PVDER_OK;
+}
+
+int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_offset, pvder_env** out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!out || n_envs < 1) return PVDER_ERR_INVALID;
+  pvder_env* h = new (std::nothrow) pvder_env();
+  if (!h) return PVDER_ERR_NOMEM;
+  std::memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  h->n = n_envs;
+  h->off = env_offset;
+  h->ld = (n_envs + 31) / 32 * 32;
+  h->ns = 6 * cfg->phases + 5;
+  rc = env_create_impl(h, cfg);
+  if (rc) {                      // one cleanup path: whatever was created so far is released (null members are skipped)
+    const cudaError_t keep = g_last_cuda;
+    pvder_env_destroy(h);
+    g_last_cuda = keep;
+    return rc;
+  }
   *out = h;
+  return PVDER_OK;
+}
+
+// Swap the configuration of an existing handle (new seed, goal, reward terms, event ranges ...) without releasing its
+// streams, events and device buffers: what the single-env facade does at every reset() instead of destroying and
+// re-creating the handle.  The model (phases, three-phase mode) and the shape of the event tables must not change.
+int pvder_env_reconfigure(pvder_env* h, const pvder_env_config* cfg) {
+  if (!h) return PVDER_ERR_INVALID;
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (cfg->phases != h->cfg.phases || cfg->balanced3 != h->cfg.balanced3) return PVDER_ERR_INVALID;
+  const int rows = (cfg->event_mode == PVDER_EVENTS_TABLE && cfg->ev_count > 0) ? cfg->ev_count : 0;
+  if (rows > h->tab_rows) return PVDER_ERR_INVALID;
+  CK(cudaStreamSynchronize(h->stream));
+  h->cfg = *cfg;
+  h->fresh = 1;                  // the next reset_host() starts episode 0 of the new configuration
   return PVDER_OK;
 }
 
 int pvder_env_destroy(pvder_env* h) {
   if (!h) return PVDER_ERR_INVALID;
-  cudaStreamSynchronize(h->stream);
+  // work may be in flight on any of the four streams (null handles of a half-built env are skipped)
+  for (cudaStream_t st : {h->stream, h->stream2, h->copy_stream, h->h2d_stream})
+    if (st) cudaStreamSynchronize(st);
   cudaFree(h->sd); cudaFree(h->si); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_obs64);
   cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_vtab); cudaFree(h->d_stab);
-  cudaEventDestroy(h->e0); cudaEventDestroy(h->e1);
-  for (int c = 0; c < PVDER_MAX_CHUNKS; ++c) cudaEventDestroy(h->chunk_done[c]);
-  for (int c = 0; c < PVDER_MAX_CHUNKS; ++c) cudaEventDestroy(h->act_ready[c]);
-  cudaEventDestroy(h->cp0); cudaEventDestroy(h->cp1);
-  cudaStreamDestroy(h->h2d_stream);
-  cudaStreamDestroy(h->stream2);
-  cudaStreamDestroy(h->copy_stream);
-  cudaStreamDestroy(h->stream);
+  if (h->e0) cudaEventDestroy(h->e0);
+  if (h->e1) cudaEventDestroy(h->e1);
+  for (int c = 0; c < PVDER_MAX_CHUNKS; ++c)
+    if (h->chunk_done[c]) cudaEventDestroy(h->chunk_done[c]);
+  for (int c = 0; c < PVDER_MAX_CHUNKS; ++c)
+    if (h->act_ready[c]) cudaEventDestroy(h->act_ready[c]);
+  if (h->cp0) cudaEventDestroy(h->cp0);
+  if (h->cp1) cudaEventDestroy(h->cp1);
+  for (cudaStream_t st : {h->h2d_stream, h->stream2, h->copy_stream, h->stream})
+    if (st) cudaStreamDestroy(st);
   delete h;
   return PVDER_OK;
 }

@@ -55,6 +55,7 @@ struct LanesT {
   }
   PVDER_DEV bool any3(bool b) const { return ((__ballot_sync(m(), b) >> base) & 7u) != 0u; }
   PVDER_DEV bool any_warp(bool b) const { return __ballot_sync(m(), b) != 0u; }
+  PVDER_DEV int min_warp(int v) const { return __reduce_min_sync(m(), v); }
   PVDER_DEV double from_a(double v) const { return __shfl_sync(m(), v, base); }
   PVDER_DEV int from_a(int v) const { return __shfl_sync(m(), v, base); }
   PVDER_DEV double pc(double a, double b, double c) const { return p == 0 ? a : (p == 1 ? b : c); }
@@ -131,6 +132,7 @@ struct LanesT {
   bool any3(const B3& b) const { return b.v[0] || b.v[1] || b.v[2]; }
   bool any3(bool b) const { return b; }
   bool any_warp(bool b) const { return b; }
+  int min_warp(int v) const { return v; }
   double from_a(const V3& v) const { return v.v[0]; }
   double from_a(double v) const { return v; }
   int from_a(int v) const { return v; }
@@ -634,7 +636,7 @@ struct SplitStepResult {
   int exact;
   int clamped;
 };
-PVDER_NOINLINE SplitStepResult ros_slow_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
+PVDER_SLOW_LINKAGE SplitStepResult ros_slow_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
                                               Split3::In in, Split3::Consts k, const RodasTab* tab,
                                               Split3::Gains g, Aux base, int level) {
   SplitStepResult r;
@@ -767,52 +769,92 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
     Inputs in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);   // changes only when an event fires
     S::In in = S::inputs(ln, kc, in_s);
     aux_exact_sv(par, in_s, r.y.s[4], r.y.s[0], base);
-    // same loop as advance_env (few loop-carried integers; the clamp mode is sampled before every sub-step).  The
-    // fine-step level is warp-uniform only in lock-step batches, so the choice between the hot step and the out-of-line
-    // path is made per group under a ballot mask.
+    // Same segment structure as advance_env: [A] a sub-step that is refined (fine-step level > 0) or left the range of
+    // the incremental side-inputs goes through the slow path, per group under a ballot mask; [B] the plain sub-steps
+    // that follow run in the hot loop, which contains no call and keeps the WARP converged (its shuffles use the
+    // compile-time full mask): it runs the number of sub-steps every live group of the warp can take (all of them in
+    // lock-step batches); a group that is already at its end only keeps the warp converged (discard).
     const int k0 = r.k, k_end = r.k + cfg.n_sub_per_step;
+    constexpr int NO_EVENT = 1 << 30;
     int ev_left;
     {
       const int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
-      ev_left = (j_next < cfg.ev_count) ? cfg.ev_start_k + j_next * cfg.ev_step_k - r.k : 0;
+      ev_left = (j_next < cfg.ev_count) ? cfg.ev_start_k + j_next * cfg.ev_step_k - r.k : NO_EVENT;
     }
     const bool ev_here = r.k >= cfg.ev_start_k && (r.k - cfg.ev_start_k) % cfg.ev_step_k == 0 &&
                          (r.k - cfg.ev_start_k) / cfg.ev_step_k < cfg.ev_count;
     int lvl_in = ((cfg.refine_on_action && act != 0 && run) || ev_here) ? cfg.refine_input_level : 0;
-    do {
-      const int lvl_st = (r.k < cfg.startup_substeps) ? cfg.startup_level : cfg.base_level;
-      const int lvl = lvl_in > lvl_st ? lvl_in : lvl_st;
-      bool m_over;
-      const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
-      bool clamped = g.any;
-      // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
-      // come from the constant bank (fewer live registers, no spills in the common case).  A warp in which every
-      // group is refined skips the hot step; a refined group in a mixed warp only keeps it converged (discard).
-      bool ok = false;
-      if (ln.any_warp(lvl == 0))
-        ok = ln.any_warp(g.any) ? ros_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base, lvl != 0)
-                                : ros_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base, lvl != 0);
-      const LanesT<true> lx = ln.sub(!ok);
-      if (!ok) {
-        const SplitStepResult res = ros_slow_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base, lvl);
-        r.y = res.y;
-        base = res.base;
-        r.exact += res.exact;
-        clamped |= res.clamped != 0;
+    bool redo = false;
+    auto event_due = [&]() {
+      if (ev_left != 0) return;
+      const int j = (r.k - cfg.ev_start_k) / cfg.ev_step_k;
+      apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j, r.Vgrid, r.Sinsol);
+      in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
+      in = S::inputs(ln, kc, in_s);
+      ev_left = (j + 1 < cfg.ev_count) ? cfg.ev_step_k : NO_EVENT;
+      lvl_in = cfg.refine_input_level;
+    };
+    while (ln.any_warp(r.k != k_end)) {
+      // [A]
+      {
+        const bool live = r.k != k_end;
+        const int lvl_st = (r.k < cfg.startup_substeps) ? cfg.startup_level : cfg.base_level;
+        const int lvl = lvl_in > lvl_st ? lvl_in : lvl_st;
+        const bool need = live && (lvl != 0 || redo);
+        if (ln.any_warp(need)) {
+          bool m_over;
+          const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);    // sums: whole warp
+          const LanesT<true> lx = ln.sub(need);
+          if (need) {
+            lvl_in = 0;
+            redo = false;
+            const SplitStepResult res = ros_slow_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base, lvl);
+            r.y = res.y;
+            base = res.base;
+            r.exact += res.exact;
+            if (g.any || res.clamped != 0) r.windup += 1;
+            if (traj && run) record_substep_split(ln, traj, traj_ld, r.k - k0, r.y, r.Vgrid, r.Sinsol);
+            r.k += 1;
+            ev_left -= 1;
+            event_due();
+          }
+        }
       }
-      if (clamped) r.windup += 1;
-      lvl_in = 0;
-      if (traj && run) record_substep_split(ln, traj, traj_ld, r.k - k0, r.y, r.Vgrid, r.Sinsol);   // not the keep-converged dummy work
-      r.k += 1;
-      if (--ev_left == 0) {
-        const int j = (r.k - cfg.ev_start_k) / cfg.ev_step_k;
-        apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j, r.Vgrid, r.Sinsol);
-        in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
-        in = S::inputs(ln, kc, in_s);
-        ev_left = (j + 1 < cfg.ev_count) ? cfg.ev_step_k : 0;
-        lvl_in = cfg.refine_input_level;
+      // [B]
+      const bool live = r.k != k_end;
+      int seg = k_end - r.k;
+      if (ev_left < seg) seg = ev_left;
+      if (r.k < cfg.startup_substeps) {
+        if (cfg.startup_level != 0) seg = 0;
+        else if (cfg.startup_substeps - r.k < seg) seg = cfg.startup_substeps - r.k;   // base_level starts there
+      } else if (cfg.base_level != 0) seg = 0;
+      if (lvl_in != 0) seg = 0;
+      const int seg_w = ln.min_warp(live ? seg : NO_EVENT);
+      if (seg_w > 0 && seg_w != NO_EVENT) {
+        int left = seg_w, took = 0, wind = 0;
+        bool fail = false;
+        do {
+          bool m_over;
+          const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
+          // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
+          // come from the constant bank (fewer live registers, no spills in the common case)
+          const bool ok = ln.any_warp(g.any) ? ros_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base, !live)
+                                             : ros_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base, !live);
+          fail = live && !ok;
+          if (live && ok) {
+            wind += g.any ? 1 : 0;
+            if (traj && run) record_substep_split(ln, traj, traj_ld, r.k + took - k0, r.y, r.Vgrid, r.Sinsol);
+            took += 1;
+          }
+          if (ln.any_warp(fail)) break;     // a group left the incremental range: it is redone in [A]
+        } while (--left != 0);
+        redo = fail;
+        r.k += took;
+        ev_left -= took;
+        r.windup += wind;
+        if (took) event_due();
       }
-    } while (r.k != k_end);
+    }
     auto bad = vnonfinite(r.y.p[0]);
 #pragma unroll
     for (int i = 1; i < 6; ++i) bad = vor(bad, vnonfinite(r.y.p[i]));

@@ -41,7 +41,7 @@ class PVDER(Utilities):
                        **cfgmod.REWARD_SPEC}
     env_action_spec = {"action_list": {"default": ["Q_control"], "valid": ["Q_control", "Vdc_control"]},
                        **cfgmod.ACTION_SPEC}
-    env_goal_spec = cfgmod.GOAL_SPEC
+    env_goal_spec = cfgmod.GOAL_SPEC   # class-level default; every instance works on its own copy
     default_goal = cfgmod.DEFAULT_GOAL
 
     def __init__(self, goals_list=None, n_sim_time_steps_per_env_step=None, max_sim_time=None, DISCRETE_REWARD=None,
@@ -61,6 +61,10 @@ class PVDER(Utilities):
         self.DISCRETE_REWARD = DISCRETE_REWARD
         self._seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)  # reference RNG is unseeded
         self._handle = None
+        self._handle_key = None
+        # per instance (the reference mutates a class-level dict); my_spec = required (PVDER_env.py:445-452)
+        self.env_goal_spec = copy.deepcopy(cfgmod.GOAL_SPEC)
+        self.update_env_goal(None, None)
         self._obs = np.zeros((1, _cabi.OBS_DIM), dtype=np.float32)
         self._obs64 = np.zeros((1, _cabi.OBS_DIM), dtype=np.float64)
         self._rew = np.zeros(1, dtype=np.float64)
@@ -125,19 +129,27 @@ class PVDER(Utilities):
             self._handle = None
 
     def setup_PVDER_simulation(self, model_type=None):
-        """PVDER_env.py:366-398: a fresh simulator at t = 0 with new random events."""
+        """PVDER_env.py:366-398: a fresh simulator at t = 0 with new random events.  The device handle (streams,
+        buffers) is created once per model and re-configured afterwards -- new seed, goal, reward list, event ranges --
+        instead of being destroyed and re-created at every reset."""
         lib = _cabi.load()
-        self._destroy()
         self.max_sim_time = self.max_sim_time_user
         self._episode_seed = (self._seed + 0x9E3779B97F4A7C15 * (self._episodes + 1)) & 0xFFFFFFFFFFFFFFFF
+        goal = self.goals_list[0]
         self.config = EnvConfig(model_type=model_type or self.model_type,
                                 n_sim_time_steps_per_env_step=self.n_sim_time_steps_per_env_step,
                                 max_sim_time=self.max_sim_time, DISCRETE_REWARD=self.DISCRETE_REWARD,
-                                goals_list=self.goals_list, events_spec=self.env_events_spec, event_mode="philox",
+                                goals_list=self.goals_list, reward_list=self.env_goal_spec[goal]["reward"]["my_spec"],
+                                events_spec=self.env_events_spec, event_mode="philox",
                                 seed=self._episode_seed, max_episode_steps=self.spec.max_episode_steps)
-        h = C.c_void_p()
-        _cabi.check(lib.pvder_env_create(C.byref(self.config.c), 1, 0, C.byref(h)))
-        self._handle = h
+        key = (self.config.phases, self.config.c.balanced3)
+        if self._handle is not None and self._handle_key == key:
+            _cabi.check(lib.pvder_env_reconfigure(self._handle, C.byref(self.config.c)))
+        else:
+            self._destroy()
+            h = C.c_void_p()
+            _cabi.check(lib.pvder_env_create(C.byref(self.config.c), 1, 0, C.byref(h)))
+            self._handle, self._handle_key = h, key
         ex = self.config.extras
         self.sim = types.SimpleNamespace(
             name="DER_sim_b200", tInc=cfgmod.SIM_TIME_STEP, tStart=0.0, tStop=0.0, Sbase=ex["Sbase"], Vbase=ex["Vbase"],
@@ -179,7 +191,9 @@ class PVDER(Utilities):
         status = _cabi.STATUS_OK
         if self._done_buf[0] and self._rew[0] == -100.0:
             status = int(self._state_i32()[_cabi.SI_STATUS])
-        self.CONVERGENCE_FAILURE = status == _cabi.STATUS_NONFINITE
+        # NONFINITE: the integrator failed.  UNBALANCED cannot occur here (the facade runs the three-phase model in
+        # 'auto' mode, which hands such an env to the general model), but is surfaced the same way if it ever does.
+        self.CONVERGENCE_FAILURE = status in (_cabi.STATUS_NONFINITE, _cabi.STATUS_UNBALANCED)
         assert not self.CONVERGENCE_FAILURE, "Convergence flag should be true to calculate reward!"   # :177
         self._reward = int(self._rew[0]) if self.DISCRETE_REWARD else float(self._rew[0])
         self.sim.tStart = self.sim.tStop
@@ -240,9 +254,41 @@ class PVDER(Utilities):
         self.env_events_spec.clear()
         self.env_events_spec.update(current)
 
-    def calc_returns(self, n_episodes=2, action_specs=("random", "inc", "dec", "no_change")):
+    def update_env_goal(self, goal_type=None, goal_spec=None):
+        """PVDER_env.py:445-456.  (None, None): every goal's `my_spec` = its required reward/action terms, as in the
+        reference.  Otherwise ``goal_spec = {"reward": [...]}`` sets the reward list of ``goal_type`` to its required
+        term plus the chosen optional ones (env_goal_spec, :78-93) -- the branch the reference left "under
+        construction"; it takes effect at the next reset(), when the simulator is rebuilt."""
+        if goal_type is None and goal_spec is None:
+            for g in self.env_goal_spec:
+                self.env_goal_spec[g]["reward"]["my_spec"] = list(self.env_goal_spec[g]["reward"]["required"])
+                self.env_goal_spec[g]["action"]["my_spec"] = list(self.env_goal_spec[g]["action"]["required"])
+            return
+        if goal_type not in self.env_goal_spec:
+            raise ValueError("{} is not a valid goal!".format(goal_type))
+        extra = set(goal_spec or {}) - {"reward"}
+        if extra:
+            raise ValueError("{} is not a valid goal spec entry!".format(sorted(extra)))
+        self.env_goal_spec[goal_type]["reward"]["my_spec"] = cfgmod.validate_reward_list(goal_type,
+                                                                                          (goal_spec or {}).get("reward"))
+
+    def calc_returns(self, n_episodes=2, action_specs=("random", "inc", "dec", "no_change"), batched=True):
         """Average return of fixed policies for every goal (reference PVDER_env.py:458-497, same
-        action mapping: 'inc' -> action 0, 'dec' -> 1, 'no_change' -> 2)."""
+        action mapping: 'inc' -> action 0, 'dec' -> 1, 'no_change' -> 2).  batched (default): the whole sweep runs as
+        vector rollouts on the device (PVDERVecEnv.calc_returns: one launch per env step for all policies and episodes
+        of a goal); batched=False: the reference's serial loop through this env's own reset()/step()."""
+        if batched:
+            from .vec_env import PVDERVecEnv
+
+            venv = PVDERVecEnv(1, seed=self._seed, model_type=self.model_type,
+                               n_sim_time_steps_per_env_step=self.n_sim_time_steps_per_env_step,
+                               max_sim_time=self.max_sim_time_user, DISCRETE_REWARD=self.DISCRETE_REWARD,
+                               goals_list=self.goals_list, events_spec=self.env_events_spec,
+                               max_episode_steps=self.spec.max_episode_steps)
+            venv._goal_rewards = {g: list(self.env_goal_spec[g]["reward"]["my_spec"]) for g in self.env_goal_spec}
+            self.env_average_return = venv.calc_returns(n_episodes=n_episodes, action_specs=action_specs)
+            self.pp.pprint(self.env_average_return)
+            return self.env_average_return
         self.env_average_return = {}
         saved = self.goals_list
         for goal in self.env_goal_spec:

@@ -18,7 +18,10 @@ class EnvSpec:
     def make(self, **kwargs):
         kw = copy.deepcopy(self.kwargs)
         kw.update(kwargs)
-        env = self.entry_point(spec=self, **kw)
+        env = self.entry_point(**kw)           # like gym.make: the entry point only sees its kwargs ...
+        env.spec = self                        # ... and gym attaches the spec afterwards
+        if hasattr(env, "max_sim_time_user"):  # its clamp depends on spec.max_episode_steps (PVDER_env.py:565-573)
+            env.max_sim_time = env.max_sim_time_user
         if self.max_episode_steps is not None:
             env = TimeLimit(env, self.max_episode_steps)
         return env
@@ -76,14 +79,19 @@ registry: dict[str, EnvSpec] = {}
 
 def register(id, entry_point, kwargs=None, max_episode_steps=None):
     registry[id] = EnvSpec(id, entry_point, kwargs, max_episode_steps)
-    try:  # also expose the id through a real gym, when there is one
-        import gym  # type: ignore
+    # also expose the id through a real gym / gymnasium, when one is importable (neither is in this image)
+    for modname in ("gym", "gymnasium"):
+        try:
+            mod = __import__(modname)
+            known = getattr(mod.envs.registry, "env_specs", mod.envs.registry)
+            if id not in known:
+                mod.register(id=id, entry_point=entry_point, kwargs=dict(kwargs or {}), max_episode_steps=max_episode_steps)
+        except ImportError:
+            continue
+        except Exception as exc:      # a registry API this shim does not know: say so instead of hiding it
+            import warnings
 
-        if id not in getattr(gym.envs.registry, "env_specs", gym.envs.registry):
-            gym.register(id=id + "-b200" if False else id, entry_point=entry_point, kwargs=kwargs,
-                         max_episode_steps=max_episode_steps)
-    except Exception:
-        pass
+            warnings.warn(f"could not register {id} with {modname}: {exc}")
     return registry[id]
 
 

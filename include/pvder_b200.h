@@ -45,7 +45,9 @@ extern "C" {
 #define PVDER_SI_HIST 5           /* 5 rows: action histogram (env_utilities.py:25-30) */
 #define PVDER_SI_WINDUP 10        /* sub-steps taken with an anti-windup clamp active */
 #define PVDER_SI_EXACT 11         /* sub-steps redone with library sin/cos/exp (outside the incremental range) */
-#define PVDER_SI_FIELDS 12
+#define PVDER_SI_REDO_LIST 12     /* PVDER_3PH_AUTO scratch: local indices of the envs the balanced kernel handed to the three-lane one */
+#define PVDER_SI_REDO_CTRL 13     /* PVDER_3PH_AUTO scratch: [0] number of list entries, [1] ticket of the consuming kernel (both 0 between steps) */
+#define PVDER_SI_FIELDS 14
 
 enum { PVDER_GOAL_VOLTAGE = 0, PVDER_GOAL_Q = 1, PVDER_GOAL_POWER = 2 };      /* PVDER_env.py:78-93 */
 /* reward terms (PVDER_env.py:67-71 reward_list 'valid'; evaluated at :251-299) */
@@ -53,11 +55,14 @@ enum { PVDER_TERM_VOLTAGE = 0, PVDER_TERM_Q = 1, PVDER_TERM_POWER = 2, PVDER_TER
 #define PVDER_MAX_REWARD_TERMS 4
 enum { PVDER_EVENTS_NONE = 0, PVDER_EVENTS_PHILOX = 1, PVDER_EVENTS_TABLE = 2 };
 enum { PVDER_STATUS_OK = 0, PVDER_STATUS_BAD_ACTION = 1, PVDER_STATUS_NONFINITE = 2,
-       PVDER_STATUS_UNBALANCED = 3 /* balanced3 mode met a per-phase duty-cycle clamp */ };
+       PVDER_STATUS_UNBALANCED = 3 /* PVDER_3PH_BALANCED only: the per-phase duty-cycle clamp (A.3) engaged, which the
+                                      phase-a reduction cannot represent: reward -100, done (PVDER_3PH_AUTO hands such an
+                                      env to the general model instead) */ };
 /* three-phase integration mode (pvder_env_config.balanced3) */
 enum { PVDER_3PH_GENERAL = 0,   /* 23 states, one thread per env */
        PVDER_3PH_BALANCED = 1,  /* balanced set carried by phase a (11 states) */
-       PVDER_3PH_AUTO = 2,      /* per env: balanced reduction when the stored state is balanced, else general */
+       PVDER_3PH_AUTO = 2,      /* per env: balanced reduction while the stored state is a balanced set and no per-phase
+                                   duty-cycle clamp engages; any other env is stepped by the three-lane kernel */
        PVDER_3PH_SPLIT = 3 };   /* 23 states, three lanes per env (one per phase, warp-shuffle reductions) */
 enum { PVDER_OK = 0, PVDER_ERR_INVALID = -1, PVDER_ERR_CUDA = -2, PVDER_ERR_NOMEM = -3 };
 
@@ -198,6 +203,10 @@ int pvder_fp64_peak(int iters, double* tflops, double* ms);
 typedef struct pvder_env pvder_env;
 int pvder_env_create(const pvder_env_config* cfg, int64_t n_envs, int64_t env_offset, pvder_env** out);
 int pvder_env_destroy(pvder_env* env);
+/* Swap the configuration of a handle (seed, goal, reward terms, event ranges, n_sim ...) keeping its streams and device
+   buffers: what PVDER.reset() -- which builds a new simulator per episode, PVDER_env.py:316-334, :366-398 -- does here
+   instead of re-creating the handle.  phases / three-phase mode / event-table shape must not change. */
+int pvder_env_reconfigure(pvder_env* env, const pvder_env_config* cfg);
 int pvder_env_set_event_tables(pvder_env* env, const double* vgrid_tab, const double* sinsol_tab);
 int pvder_env_reset_host(pvder_env* env, float* obs_out, double* obs64_out);
 /* Copies action host->device, launches pvder_step, copies obs/reward/done device->host, waits. */

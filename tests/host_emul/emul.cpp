@@ -15,6 +15,12 @@ using namespace pvder;
 
 static double* g_traj = nullptr;   // optional trajectory buffer [n_sub][NS_STORE + 2][n] of the next emul_step call
 
+static void step_one_split(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+                           const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
+                           uint8_t* done, int64_t n, int64_t off, int64_t e);
+
+// AUTO3 (M = Model3phBal): like the CUDA launch pair of PVDER_3PH_AUTO -- a balanced stored state is stepped on phase
+// a; an env that is not balanced, or whose duty-cycle clamp engages during the step, is redone by the lane-split model.
 template <class M, bool AUTO3 = false>
 static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
                      const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
@@ -23,6 +29,14 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
   const RodasTab tab = make_rodas_tab<M>(cfg.par, cfg.substeps_per_sec);
   for (int64_t e = 0; e < n; ++e) {
     EnvRegs<M> r;
+    if constexpr (AUTO3) {
+      double z[23];
+      for (int i = 0; i < 23; ++i) z[i] = sd[(int64_t)i * ld + e];
+      if (!is_balanced(z)) {
+        step_one_split(cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off, e);
+        continue;
+      }
+    }
     load_state<M>(sd, ld, e, r.y);
     r.Qref = sd[(int64_t)PVDER_SD_QREF(NS) * ld + e];
     r.Vdcref = sd[(int64_t)PVDER_SD_VDCREF(NS) * ld + e];
@@ -40,13 +54,15 @@ static void step_all(const pvder_env_config& cfg, double* sd, int32_t* si, int64
     Outputs o;
     int done_out, hist_inc;
     bool hist_clear;
-    bool run;
-    if constexpr (AUTO3)
-      run = advance_env_auto3(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out, hist_inc,
-                              hist_clear, g_traj ? g_traj + e : nullptr, n);
-    else
-      run = advance_env<M>(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out, hist_inc,
-                           hist_clear, g_traj ? g_traj + e : nullptr, n);
+    const int status_in = r.status;
+    const bool run = advance_env<M>(cfg, tab, r, action[e], true, vtab, stab, ld, e, (uint32_t)(off + e), o, done_out,
+                                    hist_inc, hist_clear, g_traj ? g_traj + e : nullptr, n);
+    if constexpr (AUTO3) {
+      if (run && status_in != PVDER_STATUS_UNBALANCED && r.status == PVDER_STATUS_UNBALANCED) {
+        step_one_split(cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off, e);
+        continue;
+      }
+    }
     if (reward) reward[e] = o.reward;
     if (reward_i) reward_i[e] = o.reward_i;
     if (done) done[e] = (uint8_t)done_out;
@@ -160,13 +176,13 @@ static void store_split(double* sd, int64_t ld, int64_t e, const Split3::Vec& y)
   for (int i = 0; i < 5; ++i) sd[(int64_t)(18 + i) * ld + e] = y.s[i];
 }
 
-static void step_all_split(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+static void step_one_split(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
                            const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
-                           uint8_t* done, int64_t n, int64_t off) {
+                           uint8_t* done, int64_t n, int64_t off, int64_t e) {
   constexpr int NS = 23;
   const RodasTab tab = make_rodas_tab<Split3>(cfg.par, cfg.substeps_per_sec);
   const Lanes3 ln;
-  for (int64_t e = 0; e < n; ++e) {
+  {
     EnvRegsSplit r;
     load_split(sd, ld, e, r.y);
     r.Qref = sd[(int64_t)PVDER_SD_QREF(NS) * ld + e];
@@ -213,6 +229,12 @@ static void step_all_split(const pvder_env_config& cfg, double* sd, int32_t* si,
     if (obs64)
       for (int j = 0; j < PVDER_OBS_DIM; ++j) obs64[e * PVDER_OBS_DIM + j] = o.obs[j];
   }
+}
+
+static void step_all_split(const pvder_env_config& cfg, double* sd, int32_t* si, int64_t ld, const int32_t* action,
+                           const double* vtab, const double* stab, double* obs64, double* reward, int32_t* reward_i,
+                           uint8_t* done, int64_t n, int64_t off) {
+  for (int64_t e = 0; e < n; ++e) step_one_split(cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off, e);
 }
 
 // rhs (mode 0) or W^-1 b (mode 1) of the lane-split model at a 23-state point; frz = freeze mask bits
@@ -301,7 +323,7 @@ int emul_step(const pvder_env_config* cfg, double* sd, int32_t* si, int64_t ld, 
   else if (cfg->balanced3 == PVDER_3PH_BALANCED)
     step_all<Model3phBal>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   else if (cfg->balanced3 == PVDER_3PH_AUTO)
-    step_all<Model3ph, true>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
+    step_all<Model3phBal, true>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   else if (cfg->balanced3 == PVDER_3PH_SPLIT)
     step_all_split(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);
   else step_all<Model3ph>(*cfg, sd, si, ld, action, vtab, stab, obs64, reward, reward_i, done, n, off);

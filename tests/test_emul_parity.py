@@ -3,6 +3,7 @@ outputs) compiled as plain C++ (tests/host_emul) and checked against the oracle 
 twins.  This is what makes the CUDA path debuggable without a GPU; the GPU tier then asserts that
 the nvcc build of the same source agrees with this build to ~1e-11 (test_gpu_parity.py)."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -316,24 +317,29 @@ def test_balanced_reduction_equals_general_three_phase():
 
 
 def test_three_phase_auto_mode_dispatch():
-    """auto: balanced envs take the phase-a reduction, an unbalanced env the general 23-state model."""
+    """auto: balanced envs take the phase-a reduction, an unbalanced env the general 23-state model in its three-lane
+    form (the one-thread general kernel is only a cross-check)."""
     kw = dict(model_type="model_2", events_spec=H.SAG_SPEC, seed=4, DISCRETE_REWARD=False)
     auto = E.EmulVecEnv(4, balanced_three_phase="auto", **kw)
     gen = E.EmulVecEnv(4, balanced_three_phase=False, **kw)
+    spl = E.EmulVecEnv(4, balanced_three_phase="split", **kw)
     bal = E.EmulVecEnv(4, balanced_three_phase=True, **kw)
-    assert (auto.cfg.c.balanced3, gen.cfg.c.balanced3, bal.cfg.c.balanced3) == (2, 0, 1)
-    for env in (auto, gen, bal):
+    assert (auto.cfg.c.balanced3, gen.cfg.c.balanced3, bal.cfg.c.balanced3, spl.cfg.c.balanced3) == (2, 0, 1, 3)
+    for env in (auto, gen, bal, spl):
         env.reset()
     # knock env 2 off the balanced manifold (phase b current +1 %)
-    for env in (auto, gen):
+    for env in (auto, gen, spl):
         env.sd[6, 2] *= 1.01
     for s in range(5):
         a = twin.sample_actions_twin(4, s, 4, 0)
         oa, _, _, _ = auto.step(a)
         og, _, _, _ = gen.step(a)
         ob, _, _, _ = bal.step(a)
-    # unbalanced env: identical to the general path bit for bit
-    np.testing.assert_array_equal(auto.sd[:, 2], gen.sd[:, 2])
+        spl.step(a)
+    # unbalanced env: identical to the three-lane path bit for bit, to the one-thread general path to rounding
+    np.testing.assert_array_equal(auto.sd[:, 2], spl.sd[:, 2])
+    np.testing.assert_array_equal(auto.si[:12, 2], spl.si[:12, 2])
+    np.testing.assert_allclose(auto.sd[:, 2], gen.sd[:, 2], rtol=1e-9, atol=1e-11)
     assert not np.array_equal(auto.sd[:, 2], bal.sd[:, 2])
     # balanced envs: identical to the balanced path bit for bit, and equal to the general path to rounding
     for e in (0, 1, 3):
@@ -630,3 +636,102 @@ def test_trajectory_recording_matches_oracle_substeps(model_type, mode):
             t_in_force = (step * 120 + 2 * j + 1) / 120.0
             assert em.traj[2 * j + 1, ns, 0] == ev.vgrid(t_in_force)
             assert em.traj[2 * j + 1, ns + 1, 0] == ev.sinsol(t_in_force)
+
+
+def test_auto_mode_hands_a_duty_cycle_clamp_to_the_general_model():
+    """a balanced env whose per-phase duty-cycle clamp engages (|m| > 10 m_limit, A.3) must keep
+    integrating -- the reference does -- instead of ending the episode: 'auto' redoes that env step with the general
+    model (three-lane form), explicit 'balanced' mode reports UNBALANCED with reward -100 + done (documented)."""
+    kw = dict(model_type="model_2", events_spec={"voltage": {"ENABLE": False}}, DISCRETE_REWARD=False)
+    envs = {m: E.EmulVecEnv(2, balanced_three_phase=m, **kw) for m in ("auto", "split", "balanced")}
+    for env in envs.values():
+        env.reset()
+        # env 1: push the duty cycle over the limit symmetrically in the three phases (x <- 11 x keeps the set balanced)
+        for ph in range(3):
+            env.sd[6 * ph + 2, 1] *= 11.0
+            env.sd[6 * ph + 3, 1] *= 11.0
+    for s in range(3):
+        out = {m: env.step([0, 0]) for m, env in envs.items()}
+    auto, spl, bal = envs["auto"], envs["split"], envs["balanced"]
+    assert int(auto.si[3, 1]) == _cabi.STATUS_OK and not out["auto"][2][1] and out["auto"][1][1] != -100.0
+    np.testing.assert_array_equal(auto.sd[:, 1], spl.sd[:, 1])            # same model, same bits
+    np.testing.assert_array_equal(out["auto"][0][1], out["split"][0][1])
+    assert int(auto.si[10, 1]) == int(spl.si[10, 1]) > 0                   # clamped sub-steps were counted
+    np.testing.assert_allclose(auto.sd[:, 0], spl.sd[:, 0], rtol=1e-9, atol=1e-11)   # the untouched env: balanced path
+    assert int(bal.si[3, 1]) == _cabi.STATUS_UNBALANCED and out["balanced"][2][1] and out["balanced"][1][1] == -100.0
+
+
+@pytest.mark.parametrize("goal,terms", [("voltage_regulation", ["voltage_error", "Q_error"]),
+                                        ("power_regulation", ["power_error", "Vdc_error"]),
+                                        ("Q_regulation", ["Q_error"])])
+@pytest.mark.parametrize("discrete", [True, False])
+def test_reward_term_lists(goal, terms, discrete):
+    """env_goal_spec[goal]['reward']['my_spec'] with optional terms (PVDER_env.py:78-93, :249-299): the reward is the
+    sum of the listed terms, kernel source == numpy twin bit for bit == the oracle's restatement of reward_calc."""
+    em = E.EmulVecEnv(4, model_type="model_1", events_spec=H.SAG_SPEC, seed=9, DISCRETE_REWARD=discrete,
+                      goals_list=[goal], reward_list=terms)
+    assert em.cfg.reward_list == terms
+    em.reset()
+    ids = [_cabi.REWARD_TERMS[t] for t in terms]
+    from oracle.env_oracle import reward_from_outputs
+    from oracle.pvder_model import Inputs, PVDERModel, load_der_params
+    model = PVDERModel(load_der_params("10"))
+    for s in range(6):
+        a = twin.sample_actions_twin(9, s, 4, 0)
+        obs, rew, done, _ = em.step(a)
+        ns = em.ns
+        _, r_tw, _ = twin.outputs_twin(em.cfg.par, 1, em.sd[:ns], em.sd[ns], em.sd[ns + 1], em.sd[ns + 2], em.sd[ns + 3],
+                                       em.si[0], em.cfg.max_sim_time, _cabi.GOALS[goal], discrete, reward_terms=ids)
+        np.testing.assert_array_equal(np.asarray(rew, dtype=np.float64), r_tw)
+        for i in range(4):
+            y = em.sd[:ns, i].copy()
+            out = model.outputs(y, Inputs(Vgrid=em.sd[ns + 2, i], Sinsol=em.sd[ns + 3, i]))
+            r_or = reward_from_outputs(out, goal, discrete, em.sd[ns, i], model.p, terms, em.sd[ns + 1, i])
+            assert rew[i] == pytest.approx(r_or, rel=1e-12, abs=1e-15)
+    with pytest.raises(ValueError):
+        G.EnvConfig(goals_list=["voltage_regulation"], reward_list=["voltage_error", "Vdc_error"])   # reference: NameError
+    with pytest.raises(ValueError):
+        G.EnvConfig(goals_list=["Q_regulation"], reward_list=["voltage_error"])                      # required term missing
+
+
+def test_reference_format_der_config(tmp_path):
+    """EnvConfig(config_file=...) accepts the REFERENCE's parameter-file layout (config_der.json: nested sections,
+    parent_config inheritance, :23-26) and reproduces the same per-unit parameters and SURVEY Appendix B known answers
+    as this project's flat table."""
+    import json
+    ref_layout = {
+        "50": {"parent_config": "", "basic_specs": {"model_type": "SolarPVDERThreePhase"}, "basic_options": {"Sinsol": 100.0},
+               "module_parameters": {"Np": 11, "Ns": 735, "Vdcmpp0": 550.0},
+               "inverter_ratings": {"Srated": 50e3, "Vdcrated": 550.0, "Ioverload": 1.3, "Vrmsrated": 177.0},
+               "circuit_parameters": {"Rf_actual": 0.002, "Lf_actual": 25.0e-6, "C_actual": 300.0e-6, "R1_actual": 0.0019,
+                                      "X1_actual": 0.0561},
+               "controller_gains": {"Kp_GCC": 6000.0, "Ki_GCC": 2000.0, "Kp_DC": -2.0, "Ki_DC": -10.0, "Kp_Q": 0.2, "Ki_Q": 10.0,
+                                    "wp": 20e4},
+               "steadystate_values": {"maR0": 0.89, "maI0": 0.0, "iaR0": 1.0, "iaI0": 0.001},
+               "initial_states": {"xPLL": 0.0, "wte": 6.28}},
+        "50_type1": {"parent_config": "50", "inverter_ratings": {"Ioverload": 1.1}},
+        "50_type2": {"parent_config": "50_type1", "controller_gains": {"Kp_Q": 0.3}},
+        "loop_a": {"parent_config": "loop_b"}, "loop_b": {"parent_config": "loop_a"},
+    }
+    f = tmp_path / "config_der.json"
+    f.write_text(json.dumps(ref_layout))
+    flat, nested = G.EnvConfig(model_type="model_2"), G.EnvConfig(model_type="model_2", config_file=str(f))
+    for name, _ in _cabi.Params._fields_:
+        assert getattr(flat.par, name) == getattr(nested.par, name), name
+    assert flat.y0 == nested.y0
+    assert nested.ma0 == pytest.approx(0.91126 + 0.02940j, abs=2e-5)           # SURVEY A.6 known answer, derId 50
+    child = G.EnvConfig(model_type="model_2", config_file=str(f), der_id="50_type1")
+    assert child.par.iref_limit == pytest.approx(flat.par.iref_limit * 1.1 / 1.3) and child.par.Kp_Q == 0.2
+    grandchild = G.EnvConfig(model_type="model_2", config_file=str(f), der_id="50_type2")
+    assert grandchild.par.Kp_Q == 0.3 and grandchild.par.iref_limit == child.par.iref_limit
+    with pytest.raises(ValueError, match="cycle"):
+        G.EnvConfig(model_type="model_2", config_file=str(f), der_id="loop_a")
+    with pytest.raises(ValueError):
+        G.EnvConfig(model_type="model_1", config_file=str(f), der_id="50")      # three-phase DER for the single-phase model
+    ref = "/root/reference/config_der.json"                                     # the reference's own file, where present
+    if os.path.exists(ref):
+        for model_type in ("model_1", "model_2"):
+            a, b = G.EnvConfig(model_type=model_type), G.EnvConfig(model_type=model_type, config_file=ref)
+            for name, _ in _cabi.Params._fields_:
+                assert getattr(a.par, name) == getattr(b.par, name), (model_type, name)
+        assert G.EnvConfig(model_type="model_2", config_file=ref, der_id="50_type1").par.iref_limit == child.par.iref_limit

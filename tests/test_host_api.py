@@ -221,3 +221,33 @@ def test_host_buffer_chunk_plan_invariants():
     m = lib.pvder_plan_chunks(110, 0.66, sizes)                                  # 1 Mi single-phase envs on a B200
     s = [sizes[i] for i in range(m)]
     assert m >= 9 and all(abs(s[i + 1] / s[i] - 0.66) < 0.2 for i in range(1, 6)), s
+
+
+def test_registers_with_a_real_gym_when_one_is_importable(monkeypatch):
+    """the id is also registered with gym / gymnasium when importable (neither is in this image: a stand-in
+    module records the call).  The entry point receives only its kwargs -- no `spec=` -- like under a real gym.make."""
+    import sys
+    import types
+
+    from gym_pvder_b200 import registration
+
+    calls = []
+    fake = types.ModuleType("gymnasium")
+    fake.envs = types.SimpleNamespace(registry={})
+    fake.register = lambda **kw: calls.append(kw)
+    monkeypatch.setitem(sys.modules, "gymnasium", fake)
+    monkeypatch.setitem(sys.modules, "gym", None)          # "import gym" raises ImportError
+    seen = {}
+
+    class Probe:
+        max_sim_time_user = None
+
+        def __init__(self, **kw):
+            seen.update(kw)
+
+    registration.register(id="PVDER-probe-v0", entry_point=Probe, kwargs={"x": 1}, max_episode_steps=7)
+    assert calls == [{"id": "PVDER-probe-v0", "entry_point": Probe, "kwargs": {"x": 1}, "max_episode_steps": 7}]
+    env = registration.make("PVDER-probe-v0", y=2)
+    assert seen == {"x": 1, "y": 2}                        # no spec= kwarg
+    assert env.env.spec.id == "PVDER-probe-v0" and env._max_episode_steps == 7
+    del registration.registry["PVDER-probe-v0"]
