@@ -296,6 +296,9 @@ __global__ void PVDER_SPLIT_BOUNDS
 #pragma unroll
     for (int j = 0; j < PVDER_OBS_DIM; ++j) a.obs_f64[e * PVDER_OBS_DIM + j] = o.obs[j];
   }
+  if constexpr (LIST) {     // consumed: the scratch rows are all zero again between env steps
+    if (owner) a.si[(int64_t)PVDER_SI_REDO_LIST * a.ld + idx] = 0;
+  }
   if (a.obs_f32) {
     if constexpr (LIST) {   // scattered envs: each owner lane writes its row
       if (owner) {

@@ -65,9 +65,15 @@ def random_events(seed, partial=SAG_SPEC):
 
 
 def assert_episode_step_close(y, obs, y_ref, obs_ref, phases, in_windup, what="", atol=ATOL):
-    """One env step of a full-episode fixture: the normal tolerances, or -- from the first env step on at which the oracle
-    reports anti-windup sub-steps (chattering hybrid mode, DESIGN.md "Tolerances") -- 2e-4 relative on the electrical and
-    controller states and observations, 2e-3 rad/s / 2e-5 rad on the PLL states."""
+    """One env step of a full-episode fixture against the oracle tier that samples the anti-windup clamp like the kernel
+    (once per half-cycle): the normal tolerances, or -- from the first env step on at which the oracle reports anti-windup
+    sub-steps -- 2e-4 relative / 1e-6 absolute on the electrical and controller states and observations, 2e-3 rad/s /
+    2e-5 rad on the PLL states.  Why looser there: near the limit the clamp decision |i_ref| > iref_limit is knife-edge,
+    so a 1e-7 difference between two integrators can flip it for one half-cycle, which moves the frozen integrator by up to
+    Ki * error * h.  MEASURED (kernel source vs this tier, 8 full random-policy episodes with a +Q bias, 673 clamped env
+    steps, identical windup counts in all of them): worst error 13.9x the normal tolerance (1.4e-4 relative), median
+    episode 0.07x; on the committed fixtures 0.064x.  The bound is that measurement with a 1.4x margin; the gap to the
+    CONTINUOUS clamp semantics is a separate, larger number (CONTINUOUS_CLAMP_ATOL below)."""
     if not in_windup:
         assert_state_close(y, y_ref, phases, atol=atol, what=what)
         np.testing.assert_allclose(obs, obs_ref, rtol=RTOL, atol=atol, err_msg=f"{what} obs")
@@ -97,3 +103,31 @@ def assert_reward_mismatches_sit_on_a_threshold(cfg, sd_cols, mismatch, budget=1
     if len(idx):
         margin = voltage_error_margin(cfg, sd_cols[:, idx])
         assert (margin < tol).all(), f"discrete reward differs {margin} away from a threshold"
+
+
+# Anti-windup regime against the CONTINUOUS-clamp oracle (oracle/env_oracle.py solver="tight_continuous", fixtures
+# tests/golden/golden_continuous_clamp_model_1.npz).  The kernel -- like the "tight" oracle tier -- decides the clamp once
+# per half-cycle; pvder decides it inside every right-hand-side call.  MEASURED gap between the two
+# semantics (tight-oracle tier against tight-oracle tier, tests/golden/make_golden_continuous.py), worst |state error|:
+#   +Q cycle of config 2 (limit reached at env step 103, 57 clamped env steps)            9.5e-4 pu  (xQ, at the onset)
+#   +Q-biased random policy with sags (clamp releases for a few half-cycles at step 128)  7.6e-3 pu  (xQ: the integrator
+#       runs at Ki_Q dQ ~ 10 pu/s while released, so the instant of re-engagement -- resolved to 1/120 s -- matters)
+# and 0.016 x the normal tolerance before the limit is reached.  The kernel reproduces the sampled tier (0.06x .. 14x the
+# normal tolerance, windup counts identical), so the bounds below are the gap itself with a 1.3x..2x margin, not a
+# statement about the integrator.  The reference's own LSODA call (O2) FAILS at the release of the second trajectory.
+CONTINUOUS_CLAMP_ATOL = {0: 2e-3, 1: 1e-2}
+
+
+def assert_vs_continuous_clamp(y, obs, gold, traj, s, what=""):
+    """One env step against the continuous-clamp fixture: normal tolerances until the oracle first reports an active clamp
+    (in either clamp semantics), the measured-gap bound afterwards."""
+    clamped = gold["windup"][traj, s] > 0 or gold["windup_sampled"][traj, s] > 0
+    yr, orf = gold["state"][traj, s], gold["obs"][traj, s]
+    if not clamped:
+        assert_state_close(y, yr, 1, what=what)
+        np.testing.assert_allclose(obs, orf, rtol=RTOL, atol=ATOL, err_msg=f"{what} obs")
+    else:
+        atol = CONTINUOUS_CLAMP_ATOL[traj]
+        np.testing.assert_allclose(y[:9], yr[:9], rtol=0, atol=atol, err_msg=f"{what} states (continuous clamp)")
+        assert abs(y[10] - yr[10]) <= atol and abs(y[9] - yr[9]) <= 100 * atol, f"{what} PLL states (continuous clamp)"
+        np.testing.assert_allclose(obs, orf, rtol=0, atol=atol, err_msg=f"{what} obs (continuous clamp)")

@@ -735,3 +735,28 @@ def test_reference_format_der_config(tmp_path):
             for name, _ in _cabi.Params._fields_:
                 assert getattr(a.par, name) == getattr(b.par, name), (model_type, name)
         assert G.EnvConfig(model_type="model_2", config_file=ref, der_id="50_type1").par.iref_limit == child.par.iref_limit
+
+
+def test_against_the_continuous_clamp_oracle():
+    """the kernel source against a tight oracle that decides the anti-windup clamp (nearly)
+    continuously, as pvder does (tight_continuous tier) -- not only against the tier that shares the kernel's half-cycle
+    clamp sampling.  Normal tolerances until the current limit is reached; from then on the MEASURED gap between the two
+    clamp semantics (helpers.CONTINUOUS_CLAMP_ATOL).  The kernel's trajectory must also stay the sampled tier's."""
+    gold = np.load("tests/golden/golden_continuous_clamp_model_1.npz")
+    n = 2
+    em = E.EmulVecEnv(n, model_type="model_1", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False)
+    em.set_event_tables(gold["vgrid_tab"], gold["sinsol_tab"])
+    em.reset()
+    gap = np.zeros(n)
+    for s in range(160):
+        obs, rew, done, _ = em.step(gold["actions"][:, s])
+        for i in range(n):
+            H.assert_vs_continuous_clamp(em.sd[:11, i], obs[i], gold, i, s, what=f"traj{i} step{s}")
+            wind = bool(gold["windup_sampled"][i, s] > 0)
+            H.assert_episode_step_close(em.sd[:11, i], obs[i], gold["state_sampled"][i, s], gold["obs_sampled"][i, s], 1, wind,
+                                        what=f"sampled tier traj{i} step{s}")
+            gap[i] = max(gap[i], np.abs(gold["state_sampled"][i, s] - gold["state"][i, s])[:9].max())
+    # the fixture carries the gap the bounds were derived from
+    assert 5e-4 < gap[0] < H.CONTINUOUS_CLAMP_ATOL[0] and 5e-3 < gap[1] < H.CONTINUOUS_CLAMP_ATOL[1]
+    assert list(em.si[10]) == list(gold["windup_sampled"][:, -1])
+    assert abs(int(em.si[10, 0]) - int(gold["windup"][0, -1])) <= 10 and abs(int(em.si[10, 1]) - int(gold["windup"][1, -1])) <= 10
