@@ -428,6 +428,26 @@ def main():
     e2e_checksum = float(h_rew.sum())
     pchunks, pratio = C.c_int32(), C.c_double()
     _cabi.check(lib.pvder_env_pipeline_info(h, C.byref(pchunks), C.byref(pratio)))
+    # the same leg with the opt-in compact result formats (half obs, f32 reward, done bits: 26.1 instead of 53 B/env)
+    h_obs16 = torch.empty((n, 11), dtype=torch.float16).pin_memory()
+    h_rew32 = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_bits = torch.empty((n + 31) // 32, dtype=torch.int32).pin_memory()
+
+    def host_step_compact(s):
+        _cabi.check(lib.pvder_env_step_host_compact(h, C.c_void_p(h_act[s % n_act].data_ptr()), C.c_void_p(h_obs16.data_ptr()),
+                                                    C.c_void_p(h_rew32.data_ptr()), C.c_void_p(h_bits.data_ptr())))
+
+    for s in range(We):
+        host_step_compact(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        host_step_compact(We + s)
+    barrier()
+    tw2 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw2, op=dist.ReduceOp.MAX)
+    e2e_compact = world * n * Ke / float(tw2.item())
     _cabi.check(lib.pvder_env_destroy(h))
 
     # ---- host-copy ceiling: all ranks copy one step's results (53 B/env) device -> pinned host at the same time -------
@@ -612,6 +632,8 @@ def main():
                     "chunks": pchunks.value, "copy_to_kernel_time_ratio": pratio.value,
                     "host_copy_ceiling_gbs": copy_gbs, "host_copy_ceiling_env_steps_per_s": copy_ceiling,
                     "frac_of_min_device_rate_and_copy_ceiling": e2e_value / min(device_rate, copy_ceiling),
+                    "compact": {"value": e2e_compact, "unit": unit, "d2h_bytes_per_step": 22 * n + 4 * n + 4 * ((n + 31) // 32),
+                                "formats": "obs IEEE half, reward f32, done bit-packed (pvder_env_step_host_compact, opt-in)"},
                     "note": "host_copy_ceiling: all ranks copying one step's outputs (53 B/env) device -> pinned host at the "
                             "same time, nothing else running"},
             "gpu_launches": K * launches_per_step, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,

@@ -89,6 +89,7 @@ SIGNATURES = {
     "pvder_env_set_event_tables": (C.c_int, [_vp, _vp, _vp]),
     "pvder_env_reset_host": (C.c_int, [_vp, _vp, _vp]),
     "pvder_env_step_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "pvder_env_step_host_compact": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "pvder_env_state_host": (C.c_int, [_vp, _vp, _vp]),
     "pvder_env_set_refs_host": (C.c_int, [_vp, _vp]),
     "pvder_env_device_ptrs": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),

@@ -781,6 +781,8 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
   if (run && (unsigned)act >= (unsigned)PVDER_N_ACTIONS) {   // PVDER_env.py:201
     r.status = PVDER_STATUS_BAD_ACTION;
     run = false;
+  } else if (run && r.status == PVDER_STATUS_BAD_ACTION) {
+    r.status = PVDER_STATUS_OK;      // the rejected action changed nothing: the next valid step clears the flag
   }
   if (run) {
     hist_inc = act;                                          // env_utilities.py:25-30

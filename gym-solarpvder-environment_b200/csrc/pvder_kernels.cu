@@ -14,6 +14,8 @@
 //   observation    <- PVDER.state           :531-542
 //   done           <- :183-191
 // reset kernel     <- PVDER.reset / setup_PVDER_simulation :316-334, :366-398
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -526,6 +528,26 @@ __global__ void __launch_bounds__(BLOCK) qnet_policy_kernel(const float* __restr
   }
 }
 
+// Compact output formats of the host-buffer call (opt-in, pvder_env_step_host_compact): obs f32 -> IEEE half (22 B per
+// env), reward f64 -> f32, done u8 -> one bit per env (32 envs per word, env 32 w + b in bit b of word w).  53 -> 26.1
+// bytes per env step over PCIe; one streaming pass over data that is still in L2.
+__global__ void __launch_bounds__(256) compact_outputs_kernel(const float* __restrict__ obs, const double* __restrict__ reward,
+                                                              const uint8_t* __restrict__ done, __half* __restrict__ obs_h,
+                                                              float* __restrict__ reward_f, uint32_t* __restrict__ done_bits,
+                                                              int64_t n) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = e < n;
+  if (obs_h) {
+    const int64_t total = n * PVDER_OBS_DIM;
+    for (int64_t i = e; i < total; i += (int64_t)gridDim.x * blockDim.x) obs_h[i] = __float2half_rn(obs[i]);
+  }
+  if (reward_f && in) reward_f[e] = (float)reward[e];
+  if (done_bits) {
+    const unsigned bits = __ballot_sync(0xffffffffu, in && done[e] != 0);
+    if ((threadIdx.x & 31) == 0 && in) done_bits[e >> 5] = bits;
+  }
+}
+
 __global__ void stats_kernel(const double* sd, const int32_t* si, int64_t ld, int ns, int64_t n, double* out) {
   double acc[12];
 #pragma unroll
@@ -868,6 +890,9 @@ struct pvder_env {
   double* d_obs64;
   double* d_reward;
   uint8_t* d_done;
+  __half* d_obs_h;            // compact outputs (allocated on first use)
+  float* d_reward_f;
+  uint32_t* d_done_bits;
   double* d_vtab;
   double* d_stab;
   cudaStream_t stream;        // compute (even chunks)
@@ -986,6 +1011,7 @@ int pvder_env_destroy(pvder_env* h) {
     if (st) cudaStreamSynchronize(st);
   cudaFree(h->sd); cudaFree(h->si); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_obs64);
   cudaFree(h->d_reward); cudaFree(h->d_done); cudaFree(h->d_vtab); cudaFree(h->d_stab);
+  cudaFree(h->d_obs_h); cudaFree(h->d_reward_f); cudaFree(h->d_done_bits);
   if (h->e0) cudaEventDestroy(h->e0);
   if (h->e1) cudaEventDestroy(h->e1);
   for (int c = 0; c < PVDER_MAX_CHUNKS; ++c)
@@ -1033,8 +1059,16 @@ int pvder_plan_chunks(int64_t units, double q, int64_t* sizes) {
     return 1;
   }
   if (!(q >= 0.3)) q = 0.3;
-  if (q > 0.9) q = 0.9;
   const int64_t R = units - 4;                     // what follows the first chunk
+  if (q > 0.9) {
+    // copy-bound (the copy of a chunk takes at least as long as its kernel: several ranks sharing one host memory
+    // system): the copy engine is the critical resource, so all it needs is an early start and no gaps -- a one-wave
+    // first chunk, then equal chunks
+    const int m = (R >= 7 * 4) ? 7 : (int)(R / 4 > 1 ? R / 4 : 1);
+    sizes[0] = 4;
+    for (int c = 0; c < m; ++c) sizes[1 + c] = R / m + (c < R % m ? 1 : 0);
+    return 1 + m;
+  }
   for (int m = PVDER_MAX_CHUNKS - 1; m >= 2; --m) {
     const double s1 = (double)R * (1.0 - q) / (1.0 - std::pow(q, m));
     if (s1 * std::pow(q, m - 1) < 1.0) continue;   // smallest chunk below one unit: fewer chunks
@@ -1055,9 +1089,21 @@ int pvder_plan_chunks(int64_t units, double q, int64_t* sizes) {
   return 2;
 }
 
-int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
-                        uint8_t* done_out) {
+struct CompactOut {
+  uint16_t* obs_h;       // host, [n][11] IEEE half
+  float* reward_f;       // host, [n]
+  uint32_t* done_bits;   // host, [(n + 31) / 32]
+};
+
+static int env_step_host_impl(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
+                              uint8_t* done_out, const CompactOut* co) {
   if (!h || !action) return PVDER_ERR_INVALID;
+  if (co) {
+    if (co->obs_h && !h->d_obs_h) CK(cudaMalloc(&h->d_obs_h, sizeof(__half) * PVDER_OBS_DIM * h->n));
+    if (co->reward_f && !h->d_reward_f) CK(cudaMalloc(&h->d_reward_f, sizeof(float) * h->n));
+    if (co->done_bits && !h->d_done_bits) CK(cudaMalloc(&h->d_done_bits, sizeof(uint32_t) * ((h->n + 31) / 32)));
+  }
+  const bool need_obs32 = obs_out || (co && co->obs_h);
   // Large batches are cut into up to 12 chunks (units of a quarter wave of resident CTAs) that run alternately
   // on two compute streams -- they touch disjoint envs, so the head of chunk c+1 fills the SMs the draining
   // tail of chunk c leaves idle -- while the action H2D copies (h2d stream) run ahead of the kernels and the
@@ -1069,7 +1115,7 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
   // on n_sim and on how many ranks share the host's memory system -- and is kept within [0.3, 0.9].
   int64_t start[PVDER_MAX_CHUNKS + 1];
   int64_t size[PVDER_MAX_CHUNKS];
-  const int64_t unit = h->wave_envs / 4;
+  const int64_t unit = h->wave_envs / 4 / 32 * 32;   // chunk starts are multiples of 32 envs (coalescing, done-bit words)
   const int chunks = pvder_plan_chunks(h->n < (1 << 16) ? 0 : h->n / unit, h->copy_ratio, size);
   start[0] = 0;
   for (int c = 0; c < chunks; ++c) start[c + 1] = start[c] + size[c] * unit;
@@ -1090,13 +1136,31 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
     if (c == 1) CK(cudaStreamWaitEvent(h->stream2, h->e0, 0));      // keep launch order: chunk 1 after the start mark
     CK(cudaStreamWaitEvent(cs, h->act_ready[c], 0));
     int rc = pvder_step(&h->cfg, h->sd + lo, h->si + lo, h->ld, h->d_action + lo, h->d_vtab ? h->d_vtab + lo : nullptr,
-                        h->d_stab ? h->d_stab + lo : nullptr, obs_out ? h->d_obs + lo * PVDER_OBS_DIM : nullptr,
+                        h->d_stab ? h->d_stab + lo : nullptr, need_obs32 ? h->d_obs + lo * PVDER_OBS_DIM : nullptr,
                         obs64_out ? h->d_obs64 + lo * PVDER_OBS_DIM : nullptr, h->d_reward + lo, nullptr, h->d_done + lo,
                         cnt, h->off + lo, cs);
     if (rc) return rc;
+    if (co) {
+      const unsigned cgrid = (unsigned)((cnt + 255) / 256);
+      compact_outputs_kernel<<<cgrid, 256, 0, cs>>>(h->d_obs + lo * PVDER_OBS_DIM, h->d_reward + lo, h->d_done + lo,
+                                                    co->obs_h ? h->d_obs_h + lo * PVDER_OBS_DIM : nullptr,
+                                                    co->reward_f ? h->d_reward_f + lo : nullptr,
+                                                    co->done_bits ? h->d_done_bits + lo / 32 : nullptr, cnt);
+      CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(h->chunk_done[c], cs));
     CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
     if (c == 1) CK(cudaEventRecord(h->cp0, h->copy_stream));
+    if (co) {
+      if (co->obs_h)
+        CK(cudaMemcpyAsync(co->obs_h + lo * PVDER_OBS_DIM, h->d_obs_h + lo * PVDER_OBS_DIM, sizeof(__half) * PVDER_OBS_DIM * cnt,
+                           cudaMemcpyDeviceToHost, h->copy_stream));
+      if (co->reward_f)
+        CK(cudaMemcpyAsync(co->reward_f + lo, h->d_reward_f + lo, sizeof(float) * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (co->done_bits)
+        CK(cudaMemcpyAsync(co->done_bits + lo / 32, h->d_done_bits + lo / 32, sizeof(uint32_t) * ((cnt + 31) / 32),
+                           cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     if (obs_out)
       CK(cudaMemcpyAsync(obs_out + lo * PVDER_OBS_DIM, h->d_obs + lo * PVDER_OBS_DIM, sizeof(float) * PVDER_OBS_DIM * cnt,
                          cudaMemcpyDeviceToHost, h->copy_stream));
@@ -1128,10 +1192,21 @@ int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, dou
     const double r = 1.15 * ((double)cms / (double)(start[2] - start[1])) / ((double)ms / (double)h->n);
     if (r > 0.0 && r < 100.0) {
       double q = 0.5 * h->copy_ratio + 0.5 * r;
-      h->copy_ratio = q < 0.3 ? 0.3 : (q > 0.9 ? 0.9 : q);
+      h->copy_ratio = q < 0.3 ? 0.3 : (q > 4.0 ? 4.0 : q);      // > 0.9: pvder_plan_chunks switches to the copy-bound plan
     }
   }
   return PVDER_OK;
+}
+
+int pvder_env_step_host(pvder_env* h, const int32_t* action, float* obs_out, double* obs64_out, double* reward_out,
+                        uint8_t* done_out) {
+  return env_step_host_impl(h, action, obs_out, obs64_out, reward_out, done_out, nullptr);
+}
+
+int pvder_env_step_host_compact(pvder_env* h, const int32_t* action, uint16_t* obs_f16_out, float* reward_f32_out,
+                                uint32_t* done_bits_out) {
+  const CompactOut co{obs_f16_out, reward_f32_out, done_bits_out};
+  return env_step_host_impl(h, action, nullptr, nullptr, nullptr, nullptr, &co);
 }
 
 int pvder_env_state_host(pvder_env* h, double* sd_out, int32_t* si_out) {

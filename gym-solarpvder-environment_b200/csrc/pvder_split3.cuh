@@ -55,7 +55,6 @@ struct LanesT {
   }
   PVDER_DEV bool any3(bool b) const { return ((__ballot_sync(m(), b) >> base) & 7u) != 0u; }
   PVDER_DEV bool any_warp(bool b) const { return __ballot_sync(m(), b) != 0u; }
-  PVDER_DEV int min_warp(int v) const { return __reduce_min_sync(m(), v); }
   PVDER_DEV double from_a(double v) const { return __shfl_sync(m(), v, base); }
   PVDER_DEV int from_a(int v) const { return __shfl_sync(m(), v, base); }
   PVDER_DEV double pc(double a, double b, double c) const { return p == 0 ? a : (p == 1 ? b : c); }
@@ -81,6 +80,7 @@ PVDER_DEV Lanes3 make_lanes(int lane) {
 }
 PVDER_DEV double vfma(double a, double b, double c) { return fma(a, b, c); }
 PVDER_DEV double vsel(bool c, double a, double b) { return c ? a : b; }
+PVDER_DEV double vsel_group(bool c, double a, double b) { return c ? a : b; }   // c: one decision for the three lanes of a group
 PVDER_DEV double vrcp(double a) { return pvder_rcp(a); }
 PVDER_DEV bool vgt(double a, double b) { return a > b; }
 PVDER_DEV bool vor(bool a, bool b) { return a || b; }
@@ -117,6 +117,7 @@ inline V3 vrcp(const V3& a) { return V3(1.0 / a.v[0], 1.0 / a.v[1], 1.0 / a.v[2]
 inline V3 vsel(const B3& c, const V3& a, const V3& b) {
   return V3(c.v[0] ? a.v[0] : b.v[0], c.v[1] ? a.v[1] : b.v[1], c.v[2] ? a.v[2] : b.v[2]);
 }
+inline V3 vsel_group(bool c, const V3& a, const V3& b) { return c ? a : b; }
 inline B3 vgt(const V3& a, const V3& b) { return B3{{a.v[0] > b.v[0], a.v[1] > b.v[1], a.v[2] > b.v[2]}}; }
 inline B3 vand(const B3& a, bool b) { return B3{{a.v[0] && b, a.v[1] && b, a.v[2] && b}}; }
 inline B3 vor(const B3& a, const B3& b) { return B3{{a.v[0] || b.v[0], a.v[1] || b.v[1], a.v[2] || b.v[2]}}; }
@@ -132,7 +133,6 @@ struct LanesT {
   bool any3(const B3& b) const { return b.v[0] || b.v[1] || b.v[2]; }
   bool any3(bool b) const { return b; }
   bool any_warp(bool b) const { return b; }
-  int min_warp(int v) const { return v; }
   double from_a(const V3& v) const { return v.v[0]; }
   double from_a(double v) const { return v; }
   int from_a(int v) const { return v; }
@@ -265,7 +265,9 @@ struct Split3 {
 
   // Autonomous right-hand side (A.3) from the point record.
   // FREE: no clamp active in this warp -> the gains are the parameters (constant bank), g is not read.
-  template <bool FREE>
+  // ACC: F arrives pre-loaded (the stage's sum of c_ij/h K_j) and the right-hand side is accumulated onto it -- the addend
+  //      rides on each row's last multiply, so no separate adds sit between the right-hand side and the solve.
+  template <bool FREE, bool ACC = false>
   static PVDER_DEV void rhs(const Params& par, const Consts& k, const Aux& ax, const Gains& g, const double* luc,
                             const Vec& Y, const Pt& q, Vec& F) {
     // x, xDC, xQ, xPLL rows: gains pre-scaled by h*gamma (unit-pivot rows)
@@ -274,18 +276,34 @@ struct Split3 {
     const double g4 = FREE ? luc[LC_G4H] : g.g4, g5 = FREE ? luc[LC_G5H] : g.g5;
     const double hV = 0.5 * Y.s[0];
     const V iR = Y.p[0], iI = Y.p[1];
-    F.p[0] = vfma(q.wr, iI, par.inv_Lf * vfma(q.mR, hV, vfma(-par.Rf, iR, -q.vR)));
-    F.p[1] = vfma(-q.wr, iR, par.inv_Lf * vfma(q.mI, hV, vfma(-par.Rf, iI, -q.vI)));
-    F.p[2] = g0 * Y.p[4];
-    F.p[3] = g1 * Y.p[5];
+    const V eR = vfma(q.mR, hV, vfma(-par.Rf, iR, -q.vR)), eI = vfma(q.mI, hV, vfma(-par.Rf, iI, -q.vI));
     const V rfR = vfma(k.rr, q.irefR, -(k.ri * q.irefI)), rfI = vfma(k.ri, q.irefR, k.rr * q.irefI);
-    F.p[4] = g2 * ((rfR - Y.p[4]) - iR);
-    F.p[5] = g3 * ((rfI - Y.p[5]) - iI);
-    F.s[0] = par.inv_C * fma(-0.25, q.Ps, ax.PoV);      // (Ppv - Vdc Ps / 4) / (C Vdc) = (Ppv / Vdc - Ps / 4) / C
-    F.s[1] = g4 * q.dV;
-    F.s[2] = -(g5 * q.dQ);
-    F.s[3] = luc[LC_KIPLL_H] * q.vd;
-    F.s[4] = q.wex + par.dw;
+    const V dR = (rfR - Y.p[4]) - iR, dI = (rfI - Y.p[5]) - iI;
+    if (ACC) {
+      F.p[0] = vfma(q.wr, iI, vfma(V(par.inv_Lf), eR, F.p[0]));
+      F.p[1] = vfma(-q.wr, iR, vfma(V(par.inv_Lf), eI, F.p[1]));
+      F.p[2] = vfma(g0, Y.p[4], F.p[2]);
+      F.p[3] = vfma(g1, Y.p[5], F.p[3]);
+      F.p[4] = vfma(g2, dR, F.p[4]);
+      F.p[5] = vfma(g3, dI, F.p[5]);
+      F.s[0] = fma(par.inv_C, fma(-0.25, q.Ps, ax.PoV), F.s[0]);
+      F.s[1] = fma(g4, q.dV, F.s[1]);
+      F.s[2] = fma(-g5, q.dQ, F.s[2]);
+      F.s[3] = fma(luc[LC_KIPLL_H], q.vd, F.s[3]);
+      F.s[4] = (q.wex + par.dw) + F.s[4];
+    } else {
+      F.p[0] = vfma(q.wr, iI, par.inv_Lf * eR);
+      F.p[1] = vfma(-q.wr, iR, par.inv_Lf * eI);
+      F.p[2] = g0 * Y.p[4];
+      F.p[3] = g1 * Y.p[5];
+      F.p[4] = g2 * dR;
+      F.p[5] = g3 * dI;
+      F.s[0] = par.inv_C * fma(-0.25, q.Ps, ax.PoV);      // (Ppv - Vdc Ps / 4) / (C Vdc) = (Ppv / Vdc - Ps / 4) / C
+      F.s[1] = g4 * q.dV;
+      F.s[2] = -(g5 * q.dQ);
+      F.s[3] = luc[LC_KIPLL_H] * q.vd;
+      F.s[4] = q.wex + par.dw;
+    }
   }
 
   // Factors of W = I/(h g) - J(y) in block-arrow form (see the file header).
@@ -518,10 +536,11 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K2);
-#define ST(m) K2.m[i] = vfma(CC(m, 21), K1.m[i], K2.m[i]);
+  // the stage's sum of c_ij/h K_j is pre-loaded and the right-hand side accumulated onto it (rhs<.., true>)
+#define ST(m) K2.m[i] = CC(m, 21) * K1.m[i];
   PVDER_EACH(ST)
 #undef ST
+  S::template rhs<FREE, true>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K2);
   S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K2);
   // stage 3: K1, K2 are folded into Y3, the pre-loaded sums of stages 3 (-> K3) and 4 (-> K4) and the new state
   // (-> K1) as soon as K2 exists
@@ -536,10 +555,8 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
   PVDER_EACH(ST)
 #undef ST
   aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K2);   // K2 = f(Y3)
-#define ST(m)                          \
-  K3.m[i] = K3.m[i] + K2.m[i];         \
-  K4.m[i] = K4.m[i] + K3.m[i];
+  S::template rhs<FREE, true>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K3);   // K3 = b_3
+#define ST(m) K4.m[i] = K4.m[i] + K3.m[i];
   PVDER_EACH(ST)
 #undef ST
   S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K3);
@@ -620,31 +637,45 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
 #undef PVDER_EACH
 #undef CC
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  if (!EXACT && ln.any3(oor)) return false;   // group-wide: the three lanes must agree on the redo
-  y = Y;
-  base = ax;
-  return true;
+  // Commit by selects, not by an early return: a per-group branch here would set the lanes of a failing env apart from the
+  // rest of the warp right in front of the next shuffles (see advance_env_split).  Group-wide decision: the three lanes
+  // must agree (EXACT: oor only carries `discard`).
+  const bool bad = ln.any3(oor);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y.p[i] = vsel_group(bad, y.p[i], Y.p[i]);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) y.s[i] = bad ? y.s[i] : Y.s[i];
+  base.sn = bad ? base.sn : ax.sn;
+  base.cs = bad ? base.cs : ax.cs;
+  base.E = bad ? base.E : ax.E;
+  base.PoV = bad ? base.PoV : ax.PoV;
+  base.dPoV = bad ? base.dPoV : ax.dPoV;
+  return !bad;
 }
 
 // Out-of-line slow path (see ros_slow in pvder_env_step.cuh): level 0 = the half-cycle step redone with library
 // transcendentals at every stage; level > 0 = the sub-step as 2^level steps of h / 2^level with tab->fine[level - 1], the
-// clamp mode re-sampled before every fine step.  Everything travels by value so that nothing in the caller's hot loop
-// has its address taken (that would pin it to local memory).  Entered by the lanes in ln.mask (whole groups).
+// clamp mode re-sampled before every fine step.  Every fine step uses library transcendentals too: the function stays
+// straight-line code inside one loop whose trip count is the same for all lanes that enter it.
+//
+// CONVERGENCE CONTRACT (learned the hard way on B200: a version that let groups with different needs share one call --
+// different loop lengths, a retry only for some -- hung the kernel or died with "illegal instruction" inside
+// __shfl_sync as soon as one env of a warp left the beaten path).  The caller enters with the ballot mask of the groups
+// that need exactly THIS level, so all lanes of `ln.mask` execute the same instructions in the same order; every shuffle
+// and vote in here names exactly those lanes.  Everything travels by value so that nothing in the caller's hot loop has
+// its address taken (that would pin it to local memory).
 struct SplitStepResult {
   Split3::Vec y;
   Aux base;
-  int exact;
   int clamped;
 };
-PVDER_SLOW_LINKAGE SplitStepResult ros_slow_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
+PVDER_NOINLINE SplitStepResult ros_slow_split(LanesT<true> ln, Split3::Vec y, const pvder_env_config* cfg, Inputs in_s,
                                               Split3::In in, Split3::Consts k, const RodasTab* tab,
                                               Split3::Gains g, Aux base, int level) {
   SplitStepResult r;
-  r.exact = 0;
   r.clamped = 0;
-  if (level <= 0) {
+  if (level <= 0) {      // (level is the same in every lane of the mask)
     ros_core_split<true, false>(ln, y, *cfg, in_s, in, k, static_cast<const RodasCoef&>(*tab), g, base);
-    r.exact = 1;
   } else {
     const RodasCoef& ft = tab->fine[level - 1];
     const int nf = 1 << level;
@@ -654,10 +685,7 @@ PVDER_SLOW_LINKAGE SplitStepResult ros_slow_split(LanesT<true> ln, Split3::Vec y
       bool m_over;
       g = Split3::gains(ln, cfg->par, k, in, y, ft.luc, m_over);
       r.clamped |= g.any ? 1 : 0;
-      if (!ros_core_split<false, false>(ln, y, *cfg, in_s, in, k, ft, g, base)) {
-        ros_core_split<true, false>(ln, y, *cfg, in_s, in, k, ft, g, base);
-        r.exact += 1;
-      }
+      ros_core_split<true, false>(ln, y, *cfg, in_s, in, k, ft, g, base);
     }
   }
   r.y = y;
@@ -749,18 +777,20 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
   const S::Consts kc = S::consts(ln);
   hist_inc = -1;
   hist_clear = false;
-  bool run = active && !r.done;                     // PVDER_env.py:145-154: step after done is a no-op
-  if (run && (unsigned)act >= (unsigned)PVDER_N_ACTIONS) {   // PVDER_env.py:201
-    r.status = PVDER_STATUS_BAD_ACTION;
-    run = false;
-  }
-  if (run) {
-    hist_inc = act;                                          // env_utilities.py:25-30
-    r.steps += 1;                                            // PVDER_env.py:156
+  // (selects throughout: see the note on group-divergent branches at the sub-step loop)
+  const bool stepping = active && !r.done;          // PVDER_env.py:145-154: step after done is a no-op
+  const bool bad_action = stepping && (unsigned)act >= (unsigned)PVDER_N_ACTIONS;   // PVDER_env.py:201
+  const bool run = stepping && !bad_action;
+  // a rejected action changes nothing; the next valid step clears the flag
+  r.status = bad_action ? PVDER_STATUS_BAD_ACTION : ((run && r.status == PVDER_STATUS_BAD_ACTION) ? PVDER_STATUS_OK : r.status);
+  hist_inc = run ? act : -1;                        // env_utilities.py:25-30
+  r.steps += run ? 1 : 0;                           // PVDER_env.py:156
+  {
     const double dQ = (act == 1) ? cfg.delQ_pu : ((act == 2) ? -cfg.delQ_pu : 0.0);
     const double dV = (act == 3) ? cfg.delVdc_pu : ((act == 4) ? -cfg.delVdc_pu : 0.0);
-    r.Qref = __dadd_rn(r.Qref, dQ);                          // PVDER_env.py:225
-    r.Vdcref = __dadd_rn(r.Vdcref, dV);                      // PVDER_env.py:229
+    const double q = __dadd_rn(r.Qref, dQ), v = __dadd_rn(r.Vdcref, dV);
+    r.Qref = run ? q : r.Qref;                      // PVDER_env.py:225
+    r.Vdcref = run ? v : r.Vdcref;                  // PVDER_env.py:229
   }
   const bool any_run = ln.any_warp(run);                     // warp-uniform
   if (any_run) {
@@ -769,90 +799,82 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
     Inputs in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);   // changes only when an event fires
     S::In in = S::inputs(ln, kc, in_s);
     aux_exact_sv(par, in_s, r.y.s[4], r.y.s[0], base);
-    // Same segment structure as advance_env: [A] a sub-step that is refined (fine-step level > 0) or left the range of
-    // the incremental side-inputs goes through the slow path, per group under a ballot mask; [B] the plain sub-steps
-    // that follow run in the hot loop, which contains no call and keeps the WARP converged (its shuffles use the
-    // compile-time full mask): it runs the number of sub-steps every live group of the warp can take (all of them in
-    // lock-step batches); a group that is already at its end only keeps the warp converged (discard).
-    const int k0 = r.k, k_end = r.k + cfg.n_sub_per_step;
-    constexpr int NO_EVENT = 1 << 30;
-    int ev_left;
-    {
-      const int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
-      ev_left = (j_next < cfg.ev_count) ? cfg.ev_start_k + j_next * cfg.ev_step_k - r.k : NO_EVENT;
-    }
+    // One loop over the half-cycle sub-steps, the warp converged through its hot step (whose shuffles use the compile-time
+    // full mask).  A group whose sub-step is refined (fine-step level > 0: the inputs changed at its start, the PLL pull-in
+    // after reset, base_level) or left the range of the incremental side-inputs takes the out-of-line path under the
+    // ballot mask of the groups at the same level (ros_slow_split: convergence contract there); in the hot step such a
+    // group only keeps the warp company (discard).  This is the loop shape of round 1, which is the one that has been
+    // run through every failure mode on the device; the call-free segment loop of the one-thread kernels (advance_env)
+    // measured 8 % faster here but could not be made to survive an env that blows up (see ros_slow_split).
+    const int k0 = r.k;
+    int j_next = (r.k < cfg.ev_start_k) ? 0 : (r.k - cfg.ev_start_k) / cfg.ev_step_k + 1;
+    int next_k = cfg.ev_start_k + j_next * cfg.ev_step_k;
     const bool ev_here = r.k >= cfg.ev_start_k && (r.k - cfg.ev_start_k) % cfg.ev_step_k == 0 &&
                          (r.k - cfg.ev_start_k) / cfg.ev_step_k < cfg.ev_count;
     int lvl_in = ((cfg.refine_on_action && act != 0 && run) || ev_here) ? cfg.refine_input_level : 0;
-    bool redo = false;
-    auto event_due = [&]() {
-      if (ev_left != 0) return;
-      const int j = (r.k - cfg.ev_start_k) / cfg.ev_step_k;
-      apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j, r.Vgrid, r.Sinsol);
-      in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
-      in = S::inputs(ln, kc, in_s);
-      ev_left = (j + 1 < cfg.ev_count) ? cfg.ev_step_k : NO_EVENT;
-      lvl_in = cfg.refine_input_level;
-    };
-    while (ln.any_warp(r.k != k_end)) {
-      // [A]
-      {
-        const bool live = r.k != k_end;
-        const int lvl_st = (r.k < cfg.startup_substeps) ? cfg.startup_level : cfg.base_level;
-        const int lvl = lvl_in > lvl_st ? lvl_in : lvl_st;
-        const bool need = live && (lvl != 0 || redo);
-        if (ln.any_warp(need)) {
-          bool m_over;
-          const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);    // sums: whole warp
-          const LanesT<true> lx = ln.sub(need);
-          if (need) {
-            lvl_in = 0;
-            redo = false;
-            const SplitStepResult res = ros_slow_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base, lvl);
+    bool dead = false;   // the state went non-finite or absurd: the env is finished (status NONFINITE below) and parked on
+                         // the finite reset state, so that its lanes execute what healthy lanes execute from then on
+    for (int s = 0; s < cfg.n_sub_per_step; ++s) {
+      const int lvl_st = (r.k < cfg.startup_substeps) ? cfg.startup_level : cfg.base_level;
+      const int lvl = dead ? 0 : (lvl_in > lvl_st ? lvl_in : lvl_st);
+      lvl_in = 0;
+      bool m_over;
+      const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
+      bool clamped = g.any;
+      // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
+      // come from the constant bank (fewer live registers, no spills in the common case)
+      const bool skip = lvl != 0 || dead;
+      const bool ok = ln.any_warp(g.any) ? ros_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base, skip)
+                                         : ros_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base, skip);
+      const bool slow = !ok && !dead;
+      if (ln.any_warp(slow)) {
+#pragma unroll 1
+        for (int L = 0; L <= PVDER_FINE_LEVELS; ++L) {
+          const bool mine = slow && lvl == L;
+          const LanesT<true> lx = ln.sub(mine);
+          if (mine) {
+            const SplitStepResult res = ros_slow_split(lx, r.y, &cfg, in_s, in, kc, &tab, g, base, L);
             r.y = res.y;
             base = res.base;
-            r.exact += res.exact;
-            if (g.any || res.clamped != 0) r.windup += 1;
-            if (traj && run) record_substep_split(ln, traj, traj_ld, r.k - k0, r.y, r.Vgrid, r.Sinsol);
-            r.k += 1;
-            ev_left -= 1;
-            event_due();
+            r.exact += 1 << L;
+            clamped |= res.clamped != 0;
           }
         }
+        // QUARANTINE (group-wide decision, after a slow sub-step: that is where a runaway state shows up first).  A
+        // state that is non-finite or absurd (|Vdc| > 1e3 pu, |delta| > 1e8 rad) cannot recover.
+        auto nf = vnonfinite(r.y.p[0]);
+#pragma unroll
+        for (int i = 1; i < 6; ++i) nf = vor(nf, vnonfinite(r.y.p[i]));
+        bool nfs = !(fabs(r.y.s[0]) < 1e3) || !(fabs(r.y.s[4]) < 1e8);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) nfs |= !(bool)isfinite(r.y.s[i]);
+        const bool failed_now = slow && (ln.any3(nf) || ln.any3(nfs));
+        if (ln.any_warp(failed_now)) {
+          S::Vec y0;
+          double q0, q1, q2, q3;
+          init_env_split(ln, cfg, y0, q0, q1, q2, q3);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) r.y.p[i] = vsel_group(failed_now, y0.p[i], r.y.p[i]);
+#pragma unroll
+          for (int i = 0; i < 5; ++i) r.y.s[i] = failed_now ? y0.s[i] : r.y.s[i];
+          Aux b0;
+          aux_exact_sv(par, in_s, r.y.s[4], r.y.s[0], b0);      // every lane, at its own (sane) state
+          base.sn = failed_now ? b0.sn : base.sn;
+          base.cs = failed_now ? b0.cs : base.cs;
+          base.E = failed_now ? b0.E : base.E;
+          dead = dead || failed_now;
+        }
       }
-      // [B]
-      const bool live = r.k != k_end;
-      int seg = k_end - r.k;
-      if (ev_left < seg) seg = ev_left;
-      if (r.k < cfg.startup_substeps) {
-        if (cfg.startup_level != 0) seg = 0;
-        else if (cfg.startup_substeps - r.k < seg) seg = cfg.startup_substeps - r.k;   // base_level starts there
-      } else if (cfg.base_level != 0) seg = 0;
-      if (lvl_in != 0) seg = 0;
-      const int seg_w = ln.min_warp(live ? seg : NO_EVENT);
-      if (seg_w > 0 && seg_w != NO_EVENT) {
-        int left = seg_w, took = 0, wind = 0;
-        bool fail = false;
-        do {
-          bool m_over;
-          const S::Gains g = S::gains(ln, par, kc, in, r.y, tab.luc, m_over);
-          // warp-uniform choice: with no clamp active anywhere in the warp the gain-dependent coefficients
-          // come from the constant bank (fewer live registers, no spills in the common case)
-          const bool ok = ln.any_warp(g.any) ? ros_core_split<false, false>(ln, r.y, cfg, in_s, in, kc, tab, g, base, !live)
-                                             : ros_core_split<false, true>(ln, r.y, cfg, in_s, in, kc, tab, g, base, !live);
-          fail = live && !ok;
-          if (live && ok) {
-            wind += g.any ? 1 : 0;
-            if (traj && run) record_substep_split(ln, traj, traj_ld, r.k + took - k0, r.y, r.Vgrid, r.Sinsol);
-            took += 1;
-          }
-          if (ln.any_warp(fail)) break;     // a group left the incremental range: it is redone in [A]
-        } while (--left != 0);
-        redo = fail;
-        r.k += took;
-        ev_left -= took;
-        r.windup += wind;
-        if (took) event_due();
+      if (clamped && !dead) r.windup += 1;
+      if (traj && run) record_substep_split(ln, traj, traj_ld, r.k - k0, r.y, r.Vgrid, r.Sinsol);   // not the keep-converged dummy work
+      r.k += 1;
+      if (r.k == next_k && j_next < cfg.ev_count) {
+        apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, j_next, r.Vgrid, r.Sinsol);
+        in_s = make_inputs(cfg, r.Vgrid, r.Qref, r.Vdcref, r.Sinsol);
+        in = S::inputs(ln, kc, in_s);
+        j_next += 1;
+        next_k += cfg.ev_step_k;
+        lvl_in = cfg.refine_input_level;
       }
     }
     auto bad = vnonfinite(r.y.p[0]);
@@ -861,50 +883,61 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
     bool nonfinite = false;
 #pragma unroll
     for (int i = 0; i < 5; ++i) nonfinite |= !(bool)isfinite(r.y.s[i]);
-    nonfinite = ln.any3(bad) || ln.any3(nonfinite);
-    if (nonfinite) r.status = PVDER_STATUS_NONFINITE;
-    if (!run) {            // this env was only keeping the warp converged: undo
-      restore(r);
-      r.status = status_in;
+    nonfinite = ln.any3(bad) || ln.any3(nonfinite) || dead;
+    r.status = nonfinite ? PVDER_STATUS_NONFINITE : r.status;
+    if (ln.any_warp(!run)) {   // an env that was only keeping the warp company: undo (every lane reloads, the others discard)
+      EnvRegsSplit q = r;
+      restore(q);
+      q.status = status_in;
+      const bool back = !run;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) r.y.p[i] = vsel_group(back, q.y.p[i], r.y.p[i]);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) r.y.s[i] = back ? q.y.s[i] : r.y.s[i];
+      r.Qref = back ? q.Qref : r.Qref; r.Vdcref = back ? q.Vdcref : r.Vdcref;
+      r.Vgrid = back ? q.Vgrid : r.Vgrid; r.Sinsol = back ? q.Sinsol : r.Sinsol;
+      r.ret = back ? q.ret : r.ret; r.last_reward = back ? q.last_reward : r.last_reward;
+      r.k = back ? q.k : r.k; r.steps = back ? q.steps : r.steps; r.episode = back ? q.episode : r.episode;
+      r.status = back ? q.status : r.status; r.done = back ? q.done : r.done;
+      r.windup = back ? q.windup : r.windup; r.exact = back ? q.exact : r.exact;
     }
   }
 
   compute_outputs_split(ln, cfg, kc, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o);
-  done_out = r.done;
-  if (run) {
-    if (r.status == PVDER_STATUS_NONFINITE) {   // PVDER_env.py:170-172: -100, episode ends
-      o.reward = -100.0;
-      o.reward_i = -100;
-      done_out = 1;
-    }
-    if (r.k >= cfg.done_substep) done_out = 1;  // PVDER_env.py:183
-    r.last_reward = o.reward;
-    r.ret += o.reward;                          // env_utilities.py:32-38
-    r.done = done_out;
-  } else {
-    o.reward = r.last_reward;                   // cached tuple, PVDER_env.py:196
-    o.reward_i = (int)r.last_reward;
-  }
+  // (selects, not branches: the lanes of a warp stay converged up to the vote below whatever their envs did)
+  const bool failed = run && r.status == PVDER_STATUS_NONFINITE;   // PVDER_env.py:170-172: -100, episode ends
+  o.reward = failed ? -100.0 : (run ? o.reward : r.last_reward);   // not run: cached tuple, PVDER_env.py:196
+  o.reward_i = failed ? -100 : (run ? o.reward_i : (int)r.last_reward);
+  done_out = (failed || (run && r.k >= cfg.done_substep)) ? 1 : r.done;   // PVDER_env.py:183
+  r.last_reward = run ? o.reward : r.last_reward;
+  r.ret += run ? o.reward : 0.0;                // env_utilities.py:32-38
+  r.done = run ? done_out : r.done;
+  // Auto-reset (vector-env convention: the observation is the first of the new episode, reward/done are the final
+  // ones).  The output sums need the whole warp, so everything happens under a warp-wide vote and is selected per env.
   const bool reset_now = run && done_out && cfg.auto_reset;
-  if (reset_now) {
-    init_env_split(ln, cfg, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol);
-    r.episode += 1;
-    r.k = 0; r.steps = 0; r.done = 0; r.ret = 0.0; r.status = PVDER_STATUS_OK; r.windup = 0; r.exact = 0;
-    if (cfg.ev_start_k == 0 && cfg.ev_count > 0)
-      apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)r.episode, 0, r.Vgrid, r.Sinsol);
-    hist_inc = -1;
-    hist_clear = true;
-  }
-  // Vector-env convention: after an auto-reset the observation is the first of the new episode, the
-  // reward/done are the final ones.  The output sums need the whole warp, so they are recomputed
-  // under a warp-uniform condition and selected per env.
   if (ln.any_warp(reset_now)) {
+    S::Vec y0;
+    double Q0, V0, G0, S0;
+    init_env_split(ln, cfg, y0, Q0, V0, G0, S0);
+    const int ep = r.episode + 1;
+    if (cfg.ev_start_k == 0 && cfg.ev_count > 0)
+      apply_event(cfg, vtab, stab, ld, e, env_glob, (uint32_t)ep, 0, G0, S0);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) r.y.p[i] = vsel_group(reset_now, y0.p[i], r.y.p[i]);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) r.y.s[i] = reset_now ? y0.s[i] : r.y.s[i];
+    r.Qref = reset_now ? Q0 : r.Qref; r.Vdcref = reset_now ? V0 : r.Vdcref;
+    r.Vgrid = reset_now ? G0 : r.Vgrid; r.Sinsol = reset_now ? S0 : r.Sinsol;
+    r.episode = reset_now ? ep : r.episode;
+    r.k = reset_now ? 0 : r.k; r.steps = reset_now ? 0 : r.steps; r.done = reset_now ? 0 : r.done;
+    r.ret = reset_now ? 0.0 : r.ret; r.status = reset_now ? PVDER_STATUS_OK : r.status;
+    r.windup = reset_now ? 0 : r.windup; r.exact = reset_now ? 0 : r.exact;
+    hist_inc = reset_now ? -1 : hist_inc;
+    hist_clear = reset_now;
     Outputs o2;
     compute_outputs_split(ln, cfg, kc, r.y, r.Qref, r.Vdcref, r.Vgrid, r.Sinsol, r.k, o2);
-    if (reset_now) {
 #pragma unroll
-      for (int j = 0; j < PVDER_OBS_DIM; ++j) o.obs[j] = o2.obs[j];
-    }
+    for (int j = 0; j < PVDER_OBS_DIM; ++j) o.obs[j] = reset_now ? o2.obs[j] : o.obs[j];
   }
   return run;
 }

@@ -29,7 +29,7 @@ class PVDERVecEnv:
                  n_sim_time_steps_per_env_step=15, max_sim_time=40.0, DISCRETE_REWARD=True,
                  goals_list=("voltage_regulation",), events_spec=None, event_mode="philox", auto_reset=False,
                  obs_f64=False, micro=1, balanced_three_phase="auto", grid_unbalance_ratio=(1.0, 1.0),
-                 config=None, **config_kwargs):
+                 config=None, validate_actions=False, **config_kwargs):
         """config_kwargs: further EnvConfig fields (reward_list, der_id, config_file, refine_input_level,
         refine_on_action, startup_substeps, startup_level, max_episode_steps)."""
         import torch
@@ -44,6 +44,10 @@ class PVDERVecEnv:
         if self.device.index is None:      # 'cuda' != 'cuda:0' for torch: compare like with like in step()
             self.device = torch.device("cuda", torch.cuda.current_device())
         self._obs_f64 = bool(obs_f64)
+        # True: step() checks every action against Discrete(5) and raises like the reference's assertion (PVDER_env.py:201)
+        # -- one device reduction + sync per step, for debugging; False: a bad action sets PVDER_STATUS_BAD_ACTION for that
+        # env (step skipped, cached reward returned) until its next valid step; poll with check_status()
+        self.validate_actions = bool(validate_actions)
         self.cfg = config or EnvConfig(model_type=model_type,
                                        n_sim_time_steps_per_env_step=n_sim_time_steps_per_env_step,
                                        max_sim_time=max_sim_time, DISCRETE_REWARD=DISCRETE_REWARD,
@@ -112,6 +116,8 @@ class PVDERVecEnv:
         if actions.dtype != t.int32 or actions.device != self.device or not actions.is_contiguous():
             self._actions.copy_(actions.to(self.device).reshape(self.num_envs))
             actions = self._actions
+        if self.validate_actions and bool(((actions < 0) | (actions >= _cabi.N_ACTIONS)).any()):
+            raise AssertionError("an action is not available in the environment action space!")      # PVDER_env.py:201
         with t.cuda.device(self.device):
             if self.traj is None:
                 _cabi.check(self.lib.pvder_step(self._cfgp(), _ptr(self.sd), _ptr(self.si), self.ld, _ptr(actions),

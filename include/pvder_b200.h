@@ -212,6 +212,11 @@ int pvder_env_reset_host(pvder_env* env, float* obs_out, double* obs64_out);
 /* Copies action host->device, launches pvder_step, copies obs/reward/done device->host, waits. */
 int pvder_env_step_host(pvder_env* env, const int32_t* action, float* obs_out, double* obs64_out,
                         double* reward_out, uint8_t* done_out);
+/* Same step with COMPACT result formats (opt-in, for consumers bound by the host's copy bandwidth: several ranks per box):
+ * observations as IEEE half [n][11] (the Box is [-10, 10]: 1e-3 relative), reward as float32, done as one bit per env
+ * (env 32 w + b in bit b of done_bits[w]).  Each output is nullable ("obs on demand").  53 -> 26.1 bytes per env step. */
+int pvder_env_step_host_compact(pvder_env* env, const int32_t* action, uint16_t* obs_f16_out, float* reward_f32_out,
+                                uint32_t* done_bits_out);
 int pvder_env_state_host(pvder_env* env, double* sd_out, int32_t* si_out);
 int pvder_env_set_refs_host(pvder_env* env, const double* sd_in);
 /* Device pointers of the handle's state (for zero-copy interop). */

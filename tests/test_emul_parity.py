@@ -544,7 +544,11 @@ def test_split_stepping_equals_one_thread_general_model(ratio):
         np.testing.assert_allclose(spl.sd, gen.sd, rtol=1e-11, atol=1e-12)
         np.testing.assert_allclose(os_, og, rtol=1e-11, atol=1e-12)
         np.testing.assert_array_equal(rs, rg)
-        np.testing.assert_array_equal(spl.si, gen.si)
+        # all counters but one: the three-lane kernel takes every fine step with library transcendentals (its slow path is
+        # straight-line code by contract), the one-thread kernel only those that leave the incremental range
+        rows = [i for i in range(_cabi.SI_FIELDS) if i != _cabi.SI_EXACT]
+        np.testing.assert_array_equal(spl.si[rows], gen.si[rows])
+        assert (spl.si[_cabi.SI_EXACT] >= gen.si[_cabi.SI_EXACT]).all()
         np.testing.assert_array_equal(ds, dg)
     assert gen.si[_cabi.SI_EPISODE].min() >= 1
 
@@ -640,25 +644,52 @@ def test_trajectory_recording_matches_oracle_substeps(model_type, mode):
 
 def test_auto_mode_hands_a_duty_cycle_clamp_to_the_general_model():
     """a balanced env whose per-phase duty-cycle clamp engages (|m| > 10 m_limit, A.3) must keep
-    integrating -- the reference does -- instead of ending the episode: 'auto' redoes that env step with the general
-    model (three-lane form), explicit 'balanced' mode reports UNBALANCED with reward -100 + done (documented)."""
+    integrating -- the reference does -- instead of ending the episode at once: 'auto' redoes such an env step with the
+    general model (three-lane form); explicit 'balanced' mode reports UNBALANCED with reward -100 + done (documented).
+    The clamp is made reachable by lowering the limit to just above the operating point (10 m_limit = 0.912 vs
+    |m| = 0.9117: a +Q action pushes env 1 over it).  In this model an engaged duty-cycle clamp destabilises the current
+    loop -- the DER survives two env steps (59 clamped sub-steps), then runs away and is quarantined (next test)."""
     kw = dict(model_type="model_2", events_spec={"voltage": {"ENABLE": False}}, DISCRETE_REWARD=False)
     envs = {m: E.EmulVecEnv(2, balanced_three_phase=m, **kw) for m in ("auto", "split", "balanced")}
     for env in envs.values():
+        env.cfg.c.par.m_limit10 = 0.912
         env.reset()
-        # env 1: push the duty cycle over the limit symmetrically in the three phases (x <- 11 x keeps the set balanced)
-        for ph in range(3):
-            env.sd[6 * ph + 2, 1] *= 11.0
-            env.sd[6 * ph + 3, 1] *= 11.0
     for s in range(3):
-        out = {m: env.step([0, 0]) for m, env in envs.items()}
+        out = {m: env.step([0, 1]) for m, env in envs.items()}
     auto, spl, bal = envs["auto"], envs["split"], envs["balanced"]
-    assert int(auto.si[3, 1]) == _cabi.STATUS_OK and not out["auto"][2][1] and out["auto"][1][1] != -100.0
-    np.testing.assert_array_equal(auto.sd[:, 1], spl.sd[:, 1])            # same model, same bits
+    assert (auto.si[3] == _cabi.STATUS_OK).all() and not out["auto"][2].any() and (out["auto"][1] != -100.0).all()
+    np.testing.assert_array_equal(auto.sd[:, 1], spl.sd[:, 1])             # same model, same bits
     np.testing.assert_array_equal(out["auto"][0][1], out["split"][0][1])
-    assert int(auto.si[10, 1]) == int(spl.si[10, 1]) > 0                   # clamped sub-steps were counted
-    np.testing.assert_allclose(auto.sd[:, 0], spl.sd[:, 0], rtol=1e-9, atol=1e-11)   # the untouched env: balanced path
+    assert int(auto.si[10, 1]) == int(spl.si[10, 1]) > 50 and int(auto.si[10, 0]) == 0   # clamped sub-steps were counted
+    np.testing.assert_allclose(auto.sd[:, 0], spl.sd[:, 0], rtol=1e-9, atol=1e-11)       # env 0: balanced path
     assert int(bal.si[3, 1]) == _cabi.STATUS_UNBALANCED and out["balanced"][2][1] and out["balanced"][1][1] == -100.0
+    assert int(bal.si[3, 0]) == _cabi.STATUS_OK
+
+
+@pytest.mark.parametrize("mode", ["split", "auto"])
+def test_an_env_that_blows_up_is_quarantined(mode):
+    """Failure detection: an env whose state runs away (here: duty-cycle integrators scaled by 11, the DC link
+    collapses within a few half-cycles) ends with status NONFINITE, reward -100 and done -- the reference's intended
+    failure path, PVDER_env.py:170-172 -- without disturbing the other envs of its warp; its stored state is the reset
+    state (finite), so nothing downstream ever sees Inf/NaN."""
+    kw = dict(model_type="model_2", events_spec=H.SAG_SPEC, seed=21, DISCRETE_REWARD=False, balanced_three_phase=mode)
+    em, ref = E.EmulVecEnv(12, **kw), E.EmulVecEnv(12, **kw)
+    em.reset()
+    ref.reset()
+    for ph in range(3):
+        em.sd[6 * ph + 2, 5] *= 11.0
+        em.sd[6 * ph + 3, 5] *= 11.0
+    for s in range(3):
+        a = twin.sample_actions_twin(21, s, 12, 0)
+        obs, rew, done, _ = em.step(a)
+        ref.step(a)
+        if s == 0:
+            assert done[5] and rew[5] == -100.0 and int(em.si[3, 5]) == _cabi.STATUS_NONFINITE
+    others = [i for i in range(12) if i != 5]
+    np.testing.assert_array_equal(em.sd[:, others], ref.sd[:, others])
+    np.testing.assert_array_equal(em.si[:12, others], ref.si[:12, others])
+    assert np.isfinite(em.sd).all() and np.isfinite(obs).all()
+    assert int(em.si[1, 5]) == 1 and done[5]                     # one step was taken, then step-after-done no-ops
 
 
 @pytest.mark.parametrize("goal,terms", [("voltage_regulation", ["voltage_error", "Q_error"]),
@@ -760,3 +791,34 @@ def test_against_the_continuous_clamp_oracle():
     assert 5e-4 < gap[0] < H.CONTINUOUS_CLAMP_ATOL[0] and 5e-3 < gap[1] < H.CONTINUOUS_CLAMP_ATOL[1]
     assert list(em.si[10]) == list(gold["windup_sampled"][:, -1])
     assert abs(int(em.si[10, 0]) - int(gold["windup"][0, -1])) <= 10 and abs(int(em.si[10, 1]) - int(gold["windup"][1, -1])) <= 10
+
+
+def test_unbalanced_grid_vs_pvders_abc_dq0_pll_input():
+    """SURVEY A.4 / VERDICT r1 item 7: on an unbalanced grid pvder feeds its PLL the abc->dq0 transform of the time-domain
+    voltages, which carries a 2w ripple; the kernel integrates its cycle average (the positive-sequence projection, the
+    only thing a half-cycle grid can represent).  MEASURED on a (1, 0.95, 1.03) grid, 16 env steps with sags, insolation
+    steps and random actions, three-lane kernel source against the tight oracle in pvder's abc_dq0 mode: all 11
+    observations and the 21 electrical/controller states stay inside the NORMAL tolerances (worst |obs error| 1.2e-7);
+    only the two unobserved PLL states carry the ripple, sampled at a fixed phase: xPLL 1.4e-3 rad/s, delta 8.1e-4 rad."""
+    import random
+    ratio = (0.95, 1.03)
+    ev = H.random_events(3)
+    orc = OraclePVDEREnv(model_type="model_2", solver="tight", events=ev, DISCRETE_REWARD=False, vg_ratio=(1.0,) + ratio,
+                         pll_mode="abc_dq0")
+    orc.reset()
+    em = E.EmulVecEnv(1, model_type="model_2", events_spec=H.SAG_SPEC, event_mode="table", DISCRETE_REWARD=False,
+                      balanced_three_phase="split", grid_unbalance_ratio=ratio)
+    em.set_event_tables(*H.oracle_tables(ev, em.cfg.c))
+    em.reset()
+    rng = random.Random(1)
+    ripple = np.zeros(2)
+    for s in range(6):
+        a = rng.randrange(5)
+        oo, orw, od, _ = orc.step(a)
+        obs, rew, done, _ = em.step([a])
+        y, yr = em.sd[:23, 0], H.oracle_delta_state(orc)
+        np.testing.assert_allclose(obs[0], oo, rtol=H.RTOL, atol=2 * H.ATOL, err_msg=f"step {s} obs")
+        np.testing.assert_allclose(y[:21], yr[:21], rtol=H.RTOL, atol=H.ATOL, err_msg=f"step {s} states")
+        assert rew[0] == pytest.approx(orw, rel=1e-5, abs=1e-10)
+        ripple = np.maximum(ripple, np.abs(y[21:] - yr[21:]))
+    assert 5e-4 < ripple[0] < 2e-3 and 2e-4 < ripple[1] < 1.2e-3      # the 2w ripple of the unobserved PLL states
