@@ -40,6 +40,12 @@ struct LanesT {
   int p;              // phase of this lane
   int n1, n2;         // lanes holding the next two phases (cyclic)
 
+  // The member mask of every shuffle/vote: the compile-time full warp on the hot path (ptxas then issues each collective as
+  // a plain SHFL/VOTE with a "branch if divergent" to an out-of-line WARPSYNC.COLLECTIVE stub), the ballot mask of the
+  // region in the out-of-line path.  RULE for every user: a collective must be executed by ALL lanes of its mask -- never
+  // inside a per-group branch, and never as the right operand of && / || (short-circuit evaluation is such a branch: the
+  // two bugs that hung this kernel on B200, or killed it with "illegal instruction" inside __shfl_sync, were a retry that
+  // only some groups of a shared mask took and `any3(a) || any3(b)`).
   PVDER_DEV unsigned m() const { return DYN ? mask : 0xffffffffu; }
   // Sum over the three phases, two shuffles: own + next + next-next.  Lane a gets (a + b) + c; the other
   // lanes get the same sum in a rotated order (last-bit differences), so every DECISION derived from a
@@ -637,20 +643,12 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
 #undef PVDER_EACH
 #undef CC
   aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
-  // Commit by selects, not by an early return: a per-group branch here would set the lanes of a failing env apart from the
-  // rest of the warp right in front of the next shuffles (see advance_env_split).  Group-wide decision: the three lanes
-  // must agree (EXACT: oor only carries `discard`).
-  const bool bad = ln.any3(oor);
-#pragma unroll
-  for (int i = 0; i < 6; ++i) y.p[i] = vsel_group(bad, y.p[i], Y.p[i]);
-#pragma unroll
-  for (int i = 0; i < 5; ++i) y.s[i] = bad ? y.s[i] : Y.s[i];
-  base.sn = bad ? base.sn : ax.sn;
-  base.cs = bad ? base.cs : ax.cs;
-  base.E = bad ? base.E : ax.E;
-  base.PoV = bad ? base.PoV : ax.PoV;
-  base.dPoV = bad ? base.dPoV : ax.dPoV;
-  return !bad;
+  // group-wide decision (the three lanes must agree on the redo); a group that only keeps the warp company commits nothing
+  if (!EXACT && ln.any3(oor)) return false;
+  if (EXACT && discard) return false;
+  y = Y;
+  base = ax;
+  return true;
 }
 
 // Out-of-line slow path (see ros_slow in pvder_env_step.cuh): level 0 = the half-cycle step redone with library
@@ -840,6 +838,7 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
             clamped |= res.clamped != 0;
           }
         }
+#ifndef PVDER_SPLIT_NO_QUARANTINE
         // QUARANTINE (group-wide decision, after a slow sub-step: that is where a runaway state shows up first).  A
         // state that is non-finite or absurd (|Vdc| > 1e3 pu, |delta| > 1e8 rad) cannot recover.
         auto nf = vnonfinite(r.y.p[0]);
@@ -848,7 +847,10 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
         bool nfs = !(fabs(r.y.s[0]) < 1e3) || !(fabs(r.y.s[4]) < 1e8);
 #pragma unroll
         for (int i = 1; i < 4; ++i) nfs |= !(bool)isfinite(r.y.s[i]);
-        const bool failed_now = slow && (ln.any3(nf) || ln.any3(nfs));
+        // (both votes by every lane: `a || b` would skip the second one in the groups where the first is true -- a vote
+        // that only some lanes of its mask execute is exactly what hung this kernel on B200)
+        const bool nf_any = ln.any3(nf), nfs_any = ln.any3(nfs);
+        const bool failed_now = slow && (nf_any || nfs_any);
         if (ln.any_warp(failed_now)) {
           S::Vec y0;
           double q0, q1, q2, q3;
@@ -864,6 +866,7 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
           base.E = failed_now ? b0.E : base.E;
           dead = dead || failed_now;
         }
+#endif
       }
       if (clamped && !dead) r.windup += 1;
       if (traj && run) record_substep_split(ln, traj, traj_ld, r.k - k0, r.y, r.Vgrid, r.Sinsol);   // not the keep-converged dummy work
@@ -883,7 +886,10 @@ PVDER_DEV bool advance_env_split(const Lanes3& ln, const pvder_env_config& cfg, 
     bool nonfinite = false;
 #pragma unroll
     for (int i = 0; i < 5; ++i) nonfinite |= !(bool)isfinite(r.y.s[i]);
-    nonfinite = ln.any3(bad) || ln.any3(nonfinite) || dead;
+    {
+      const bool bad_any = ln.any3(bad), nf_any = ln.any3(nonfinite);   // both votes by every lane (no short-circuit)
+      nonfinite = bad_any || nf_any || dead;
+    }
     r.status = nonfinite ? PVDER_STATUS_NONFINITE : r.status;
     if (ln.any_warp(!run)) {   // an env that was only keeping the warp company: undo (every lane reloads, the others discard)
       EnvRegsSplit q = r;

@@ -1,5 +1,5 @@
 #!/bin/bash
-O=gpurun_out/r2x
+O=gpurun_out/r2y
 mkdir -p $O
 timeout 60 python tools/r2_debug_mild.py >> $O/debug.log 2>&1; echo "mild rc=$?" | tee -a $O/summary.txt
 for args in "split clamp 64" "auto oddclamp 1000" "split oddclamp 1000"; do
