@@ -8,7 +8,7 @@ flops / DRAM traffic only when the library it loads carries the same hash.
              model_1=profiles/r2f_flops_1ph.csv,profiles/r2f_step_kernel_1ph_ncu_full.csv
 
 flops.csv: `ncu --metrics smsp__sass_thread_inst_executed_op_{dfma,dadd,dmul,fp64}_pred_on.sum ... --csv` of ONE launch of
-1,048,576 envs x 30 sub-steps;  full.csv: `ncu -i x.ncu-rep --page raw --csv` of a --set full capture of one launch."""
+1,048,576 envs x 30 sub-steps;  full.csv: `ncu -i x.ncu-rep --page raw --csv` of a --set full capture of one launch, or its tools/ncu_compact.py form."""
 import csv
 import json
 import os
@@ -27,6 +27,15 @@ def metric_rows(path):
     if "Metric Name" in hdr:                       # long format (--metrics ... --csv)
         i, j = hdr.index("Metric Name"), hdr.index("Metric Value")
         return {r[i]: float(r[j].replace(",", "")) for r in rows[1:] if len(r) > j}
+    if hdr[:3] == ["metric", "unit", "value"]:     # compact format (tools/ncu_compact.py)
+        out, units = {}, {}
+        for k, u, v in rows[1:]:
+            units[k] = u
+            try:
+                out[k] = float(v.replace(",", ""))
+            except ValueError:
+                pass
+        return out, units
     vals = rows[2]                                 # wide format (--page raw --csv): header, units, values
     out = {}
     for k, v in zip(hdr, vals):
