@@ -28,6 +28,9 @@ namespace pvder {
 #ifndef PVDER_FOLD
 #define PVDER_FOLD 1   // Rodas4: fold K1..K4 into the stage-5/6 sums early: same FMAs, 2 fewer live vectors (B200: 3.11 -> 3.04 ms)
 #endif
+#ifndef PVDER_STAGE4_DELTA
+#define PVDER_STAGE4_DELTA 1   // ROS4-L: the fourth solve yields K_4 - K_3 (b_3 is not re-added: 11 FP64 instructions fewer per step)
+#endif
 #ifndef PVDER_FREE_PATH
 #define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the stepper core, chosen per warp (experiment)
 #endif
@@ -51,6 +54,7 @@ struct RodasCoefT {   // a_ij and c_ij/h, read by DFMA straight from the constan
   // b_4 = b_3 + d41 K1 + d42 K2 + c43/h K3); ds4j = the same times h*gamma for the unit-pivot rows
   double m1, m2, m3, m4;
   double d41, d42, ds41, ds42;
+  double m34;       // m3 + m4 (PVDER_STAGE4_DELTA: the fourth solve yields K_4 - K_3)
 };
 using RodasCoef = RodasCoefT<0>;
 // The kernels' coefficient table (a __grid_constant__ launch parameter): the set for the half-cycle step h that the hot
@@ -73,6 +77,7 @@ PVDER_HD void fill_rodas(T& t, const Params& par, double hinv) {
   t.c41 = c41 * hinv; t.c42 = c42 * hinv; t.c43 = -0.6949742501781779e+00 * hinv;
   t.d41 = (c41 - c31) * hinv; t.d42 = (c42 - c32) * hinv;
   t.m1 = 0.2255570073418735e+01; t.m2 = 0.2870493262186792e+00; t.m3 = 0.4353179431840180e+00; t.m4 = 0.1093502252409163e+01;
+  t.m34 = t.m3 + t.m4;
 #else
   t.a21 = 0.1544000000000000e+01;
   t.a31 = 0.9466785280815826e+00; t.a32 = 0.2557011698983284e+00;
@@ -257,6 +262,16 @@ PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in,
   aux_advance<M, EXACT, false>(par, in, base, dl0, V0, Y, ax, oor);
   PVDER_WITH_GAINS(M::rhs_acc(Y, par, in, ax, PVDER_GN, K3))
   // stage 4 re-uses f(Y3): b_4 = b_3 + sum_j (c_4j - c_3j)/h K_j + c_43/h K_3
+#if PVDER_STAGE4_DELTA
+  // W K_3 = b_3, so W (K_4 - K_3) = sum_j (c_4j - c_3j)/h K_j + c_43/h K_3: the fourth solve yields K_4 - K_3 and b_3 is
+  // never added (11 DADD fewer, and b_3 need not survive the third solve);  y+ = yn + (m_3 + m_4) K_3 + m_4 (K_4 - K_3)
+  M::solve(lu, tab.luc, K3);
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    K4[i] = fma(PVDER_C(43), K3[i], K4[i]);
+    yn[i] = fma(tab.m34, K3[i], yn[i]);
+  }
+#else
 #pragma unroll
   for (int i = 0; i < NS; ++i) K4[i] += K3[i];
   M::solve(lu, tab.luc, K3);
@@ -265,6 +280,7 @@ PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in,
     K4[i] = fma(PVDER_C(43), K3[i], K4[i]);
     yn[i] = fma(tab.m3, K3[i], yn[i]);
   }
+#endif
 #undef PVDER_C
 #undef PVDER_D
   M::solve(lu, tab.luc, K4);
@@ -856,6 +872,10 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
       if (seg > 0) {
         // hot loop: a countdown and the clamped-sub-step counter are all the integers it carries
         int left = seg, wind = 0;
+#if defined(PVDER_HOT_UNROLL) && defined(__CUDACC__)
+        constexpr int kHotUnroll = PVDER_HOT_UNROLL;
+#pragma unroll kHotUnroll
+#endif
         do {
           bool m_over;
           const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);

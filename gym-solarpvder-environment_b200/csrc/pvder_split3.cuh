@@ -562,6 +562,15 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
 #undef ST
   aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE, true>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K3);   // K3 = b_3
+#if PVDER_STAGE4_DELTA
+  // the fourth solve yields K_4 - K_3 (see ros_core): b_3 is not re-added
+  S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K3);
+#define ST(m)                                   \
+  K4.m[i] = vfma(CC(m, 43), K3.m[i], K4.m[i]);  \
+  K1.m[i] = vfma(tab.m34, K3.m[i], K1.m[i]);
+  PVDER_EACH(ST)
+#undef ST
+#else
 #define ST(m) K4.m[i] = K4.m[i] + K3.m[i];
   PVDER_EACH(ST)
 #undef ST
@@ -571,6 +580,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
   K1.m[i] = vfma(tab.m3, K3.m[i], K1.m[i]);
   PVDER_EACH(ST)
 #undef ST
+#endif
   S::template solve<FREE>(ln, par, k, g, fac, y, tab.luc, K4);
 #define ST(m) Y.m[i] = vfma(tab.m4, K4.m[i], K1.m[i]);
   PVDER_EACH(ST)

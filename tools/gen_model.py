@@ -33,7 +33,14 @@ CORE_INVERSE = os.environ.get("PVDER_GEN_CORE_INVERSE", "0") != "0"   # "1": the
 CORE_N = int(os.environ.get("PVDER_GEN_CORE_INVERSE", "0"))
 CONST_PIVOTS = os.environ.get("PVDER_GEN_CONST_PIVOTS", "off")   # off | reg | bank (measured slower)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
+OUT = os.environ.get("PVDER_GEN_OUT") or os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
+# study switch: tier of the PLL angle in the elimination order (2 = with the currents and Vdc, the committed order;
+# 1.5 = before them: its pivot no longer waits for the two current pivots -- one reciprocal level less on the critical path)
+DL_TIER = float(os.environ.get("PVDER_GEN_DL_TIER", "2"))
+# study switch: store the U rows of the computed-pivot rows pre-multiplied by the reciprocal pivot (b_k = d_k b_k - sum (d_k u_kc) b_c:
+# the pivot multiply leaves the back-substitution chain; costs one multiply per such U entry in the factorisation)
+SCALED_U = os.environ.get("PVDER_GEN_SCALED_U", "0") != "0"
+VDC_TIER = float(os.environ.get("PVDER_GEN_VDC_TIER", "2"))   # same for Vdc (1.4 with DL_TIER 1.5: Vdc, dl, then the currents)
 
 PAR = ["Rf", "Rt", "Xt", "inv_Lf", "inv_wb", "Kp_GCC", "Ki_GCC", "Kp_DC", "Ki_DC", "Kp_Q", "Ki_Q",
        "wp", "Kp_PLL", "Ki_PLL", "inv_C", "w0", "dw"]
@@ -304,8 +311,8 @@ def elimination_order(n, pattern, P):
         tier[o + 4] = tier[o + 5] = 1
         tier[o] = tier[o + 1] = 2
     tier[base + 1] = tier[base + 2] = tier[base + 3] = 0
-    tier[base] = 2
-    tier[base + 4] = 2
+    tier[base] = VDC_TIER
+    tier[base + 4] = DL_TIER
     pat = set(pattern)
     remaining = set(range(n))
     order = []
@@ -559,9 +566,14 @@ def generate(P, mult=1):
                     li = "1.0" if j == c else f"li_{j}_{c}"
                     terms.append(f"ui_{r}_{j}" if li == "1.0" else f"ui_{r}_{j} * {li}")
                 A(f"    lu.ci_{r}_{c} = " + " + ".join(terms) + ";")
+    def scaled_u(r, c):
+        return SCALED_U and r not in unit and not (CONST_PIVOTS == "bank" and r in const_piv) and pos[c] > pos[r] and r not in coreset
     for (r, c) in members:
         if r != c and not (r in coreset and c in coreset):
-            A(f"    lu.{wname(r, c)} = {wname(r, c)};")
+            if scaled_u(r, c):
+                A(f"    lu.{wname(r, c)} = {wname(r, c)} * d_{r};")
+            else:
+                A(f"    lu.{wname(r, c)} = {wname(r, c)};")
     for k in range(n):
         if not (CONST_PIVOTS == "bank" and k in const_piv) and k not in coreset and k not in unit:
             A(f"    lu.d_{k} = d_{k};")
@@ -590,6 +602,14 @@ def generate(P, mult=1):
             A(f"    b[{r}] = cx_{r};")
     for k in reversed(order):
         if k in coreset:
+            continue
+        if SCALED_U and k not in unit and not (CONST_PIVOTS == "bank" and k in const_piv):
+            A(f"    b[{k}] *= lu.d_{k};")
+            nflop_s += 1
+            # most recently solved unknown last: everything else is off the chain
+            for c in sorted((c for c in range(n) if pos[c] > pos[k] and (k, c) in pat), key=lambda c: -pos[c]):
+                A(f"    b[{k}] = fma(-lu.{wname(k, c)}, b[{c}], b[{k}]);")
+                nflop_s += 2
             continue
         for c in sorted(c for c in range(n) if pos[c] > pos[k] and (k, c) in pat):
             A(f"    b[{k}] = fma(-lu.{wname(k, c)}, b[{c}], b[{k}]);")
