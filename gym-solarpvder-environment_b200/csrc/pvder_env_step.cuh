@@ -31,6 +31,9 @@ namespace pvder {
 #ifndef PVDER_STAGE4_DELTA
 #define PVDER_STAGE4_DELTA 1   // ROS4-L: the fourth solve yields K_4 - K_3 (b_3 is not re-added: 11 FP64 instructions fewer per step)
 #endif
+#ifndef PVDER_AUX_SHORT
+#define PVDER_AUX_SHORT 0   // one-thread kernels: incremental side-inputs with the shorter dependency chains (aux_advance_sv).
+#endif                      // B200: 1.410 -> 1.424 ms single-phase (off), 8.18 -> 8.11 ms three-lane (always on there)
 #ifndef PVDER_FREE_PATH
 #define PVDER_FREE_PATH 0   // 1: separate clamp-free instantiation of the stepper core, chosen per warp (experiment)
 #endif
@@ -139,7 +142,7 @@ PVDER_DEV void aux_exact(const Params& par, const Inputs& in, const double (&y)[
 // FULL = false (inner stages): sin, cos, E and the array current Ppv/Vdc the right-hand side reads.  FULL = true (the
 // state the step ends in, base point of the next step's Jacobian): sin, cos, E; the PV part is evaluated from E at
 // the start of the next step, with the inputs in force then (ros_core).
-template <bool EXACT, bool FULL = true>
+template <bool EXACT, bool FULL = true, bool SHORT = (PVDER_AUX_SHORT != 0)>
 PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b, double dl0, double V0, double dl,
                               double V, Aux& a, bool& out_of_range) {
   if (EXACT) {
@@ -151,7 +154,24 @@ PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b,
   const double x = par.kappa * dv;
   // outside the polynomial range the caller discards this step and redoes it with EXACT = true
   out_of_range |= !(fabs(d) < 0.0625 && fabs(x) < 0.0625);
-  {
+  if (SHORT) {
+    // the same polynomials with shorter dependency chains (the side-inputs sit on the critical path of every stage:
+    // sin/cos 6 -> 5 levels, exp 7 -> 5 by Estrin's scheme; one multiply more)
+    const double d2 = d * d;
+    const double d3 = d2 * d;
+    const double ps = fma(d2, 1.0 / 120.0, -1.0 / 6.0);
+    const double sd = fma(ps, d3, d);                          // sin d  = d - d^3/6 + d^5/120
+    const double pc = fma(d2, 1.0 / 24.0, -0.5);
+    const double cdm1 = pc * d2;                               // cos d - 1 = -d^2/2 + d^4/24
+    a.sn = fma(b.cs, sd, fma(b.sn, cdm1, b.sn));
+    a.cs = fma(-b.sn, sd, fma(b.cs, cdm1, b.cs));
+    const double x2 = x * x;
+    const double pu = fma(x, 0.5, 1.0);
+    const double pv = fma(x, 1.0 / 24.0, 1.0 / 6.0);
+    const double pw = fma(x2, 1.0 / 120.0, pv);
+    const double pe = fma(x2, pw, pu);                         // 1 + x/2 + x^2/6 + x^3/24 + x^4/120
+    a.E = fma(b.E * x, pe, b.E);                               // E0 * exp(x), exp to x^5/120
+  } else {
     const double d2 = d * d;
     const double ps = fma(d2, 1.0 / 120.0, -1.0 / 6.0);
     const double sd = fma(ps * d2, d, d);                      // sin d  = d - d^3/6 + d^5/120
@@ -164,9 +184,9 @@ PVDER_DEV void aux_advance_sv(const Params& par, const Inputs& in, const Aux& b,
     pe = fma(pe, x, 0.5);
     pe = fma(pe, x, 1.0);
     a.E = fma(b.E * pe, x, b.E);                               // E0 * exp(x), exp to x^5/120
-    if (FULL) a.PoV = a.dPoV = 0.0;
-    else a.PoV = ppv_over_v_from_exp(par, in, a.E);
   }
+  if (FULL) a.PoV = a.dPoV = 0.0;
+  else a.PoV = ppv_over_v_from_exp(par, in, a.E);
 }
 
 template <class M, bool EXACT, bool FULL = true>
@@ -199,7 +219,7 @@ PVDER_DEV void make_gains(const Params& par, const TAB& tab, unsigned frz, doubl
 }
 
 #ifndef PVDER_LAZY_GAINS
-#define PVDER_LAZY_GAINS 1   // 1: re-derive the effective gains from the clamp bits at every stage (selects on the idle ALU pipe)
+#define PVDER_LAZY_GAINS 0   // 1: re-derive the effective gains from the clamp bits at every stage (selects on the idle ALU pipe)
 #endif                       //    instead of holding 9 doubles across the whole step: no spills left with ROS4-L (1.481 -> 1.468 ms)
 PVDER_DEV unsigned opaque_bits(unsigned v) {
 #ifdef __CUDACC__

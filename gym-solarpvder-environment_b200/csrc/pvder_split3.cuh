@@ -541,7 +541,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
 #define ST(m) Y.m[i] = vfma(tab.a21, K1.m[i], y.m[i]);
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false, true>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   // the stage's sum of c_ij/h K_j is pre-loaded and the right-hand side accumulated onto it (rhs<.., true>)
 #define ST(m) K2.m[i] = CC(m, 21) * K1.m[i];
   PVDER_EACH(ST)
@@ -560,7 +560,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
   }
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false, true>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE, true>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K3);   // K3 = b_3
 #if PVDER_STAGE4_DELTA
   // the fourth solve yields K_4 - K_3 (see ros_core): b_3 is not re-added
@@ -591,7 +591,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
 #define ST(m) Y.m[i] = vfma(tab.a21, K1.m[i], y.m[i]);
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false, true>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K2);
 #define ST(m) K2.m[i] = vfma(CC(m, 21), K1.m[i], K2.m[i]);
   PVDER_EACH(ST)
@@ -601,7 +601,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
 #define ST(m) Y.m[i] = vfma(tab.a32, K2.m[i], vfma(tab.a31, K1.m[i], y.m[i]));
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false, true>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K3);
 #define ST(m) K3.m[i] = vfma(CC(m, 32), K2.m[i], vfma(CC(m, 31), K1.m[i], K3.m[i]));
   PVDER_EACH(ST)
@@ -611,7 +611,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
 #define ST(m) Y.m[i] = vfma(tab.a43, K3.m[i], vfma(tab.a42, K2.m[i], vfma(tab.a41, K1.m[i], y.m[i])));
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false, true>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K4.m[i] = vfma(CC(m, 43), K3.m[i], vfma(CC(m, 42), K2.m[i], vfma(CC(m, 41), K1.m[i], K4.m[i])));
   PVDER_EACH(ST)
@@ -628,7 +628,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
   PVDER_EACH(ST)
 #undef ST
   // stage 5
-  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false, true>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K2.m[i] = K2.m[i] + K4.m[i];
   PVDER_EACH(ST)
@@ -640,7 +640,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
   K3.m[i] = vfma(CC(m, 65), K2.m[i], K3.m[i]);
   PVDER_EACH(ST)
 #undef ST
-  aux_advance_sv<EXACT, false>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, false, true>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   S::template rhs<FREE>(par, k, ax, g, tab.luc, Y, S::point(ln, par, k, in, ax, Y), K4);
 #define ST(m) K3.m[i] = K3.m[i] + K4.m[i];
   PVDER_EACH(ST)
@@ -652,7 +652,7 @@ PVDER_DEV bool ros_core_split(const LN& ln, Split3::Vec& y, const pvder_env_conf
 #endif
 #undef PVDER_EACH
 #undef CC
-  aux_advance_sv<EXACT>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
+  aux_advance_sv<EXACT, true, true>(par, in_s, base, dl0, V0, Y.s[4], Y.s[0], ax, oor);
   // group-wide decision (the three lanes must agree on the redo); a group that only keeps the warp company commits nothing
   if (!EXACT && ln.any3(oor)) return false;
   if (EXACT && discard) return false;

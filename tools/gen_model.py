@@ -26,21 +26,26 @@ import sys
 
 import sympy as sp
 
-# explicit inverse of the dense core (currents, Vdc, delta) instead of its LU: same flops per solve,
-# but a 4x4 mat-vec has a 3-deep dependency chain where the triangular solves have ~16.  Measured
-# on B200: 4 % SLOWER (register pressure), hence off by default.  Only for cores of <= 4 unknowns.
+# Elimination order and the treatment of the stiff core (measured on B200, profiles/r2b_*_sweep.txt):
+#   * tiers: Vdc (1.4) and the PLL angle (1.5) are pivoted BEFORE the current pair -- their two pivots are independent
+#     of each other, so their reciprocals run in parallel (the round-1 order Vdc, iaR, iaI, dl had four sequential
+#     reciprocal levels: 1.433 -> 1.409 ms per 1 Mi-env step);
+# Study switches kept for the record (none of them is faster): CORE_INVERSE = 2 with CRAMER2 (the last 2x2 pivot block -- the
+# current pair -- inverted by Cramer's rule: one reciprocal of the determinant instead of two sequential pivots, the block's
+# four solve operations a 2x2 mat-vec of depth 2: 1.411 vs 1.419 ms in the 20-step window, 1.470 vs 1.461 over a full
+# episode -- inside the box-to-box noise, so the plain LU stays), CORE_INVERSE = 1 | 3 (explicit inverse of the whole 4x4
+# core / its last 3 pivots through the LU: more flops than the shorter chains buy back), CONST_PIVOTS = reg | bank,
+# SCALED_U (U rows pre-multiplied by the reciprocal pivot: 1.430 vs 1.409 ms, the +9 multiplies cost more than the shorter
+# back-substitution gains).
 CORE_INVERSE = os.environ.get("PVDER_GEN_CORE_INVERSE", "0") != "0"   # "1": the whole core (<= 4 unknowns); "2"/"3": its last 2/3 pivots
 CORE_N = int(os.environ.get("PVDER_GEN_CORE_INVERSE", "0"))
-CONST_PIVOTS = os.environ.get("PVDER_GEN_CONST_PIVOTS", "off")   # off | reg | bank (measured slower)
+CRAMER2 = os.environ.get("PVDER_GEN_CRAMER2", "1") != "0" and CORE_N == 2
+CONST_PIVOTS = os.environ.get("PVDER_GEN_CONST_PIVOTS", "off")   # off | reg | bank
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.environ.get("PVDER_GEN_OUT") or os.path.join(ROOT, "gym-solarpvder-environment_b200", "csrc")
-# study switch: tier of the PLL angle in the elimination order (2 = with the currents and Vdc, the committed order;
-# 1.5 = before them: its pivot no longer waits for the two current pivots -- one reciprocal level less on the critical path)
-DL_TIER = float(os.environ.get("PVDER_GEN_DL_TIER", "2"))
-# study switch: store the U rows of the computed-pivot rows pre-multiplied by the reciprocal pivot (b_k = d_k b_k - sum (d_k u_kc) b_c:
-# the pivot multiply leaves the back-substitution chain; costs one multiply per such U entry in the factorisation)
+DL_TIER = float(os.environ.get("PVDER_GEN_DL_TIER", "1.5"))     # 2 = with the currents (round-1 order)
+VDC_TIER = float(os.environ.get("PVDER_GEN_VDC_TIER", "1.4"))   # 2 = with the currents (round-1 order)
 SCALED_U = os.environ.get("PVDER_GEN_SCALED_U", "0") != "0"
-VDC_TIER = float(os.environ.get("PVDER_GEN_VDC_TIER", "2"))   # same for Vdc (1.4 with DL_TIER 1.5: Vdc, dl, then the currents)
 
 PAR = ["Rf", "Rt", "Xt", "inv_Lf", "inv_wb", "Kp_GCC", "Ki_GCC", "Kp_DC", "Ki_DC", "Kp_Q", "Ki_Q",
        "wp", "Kp_PLL", "Ki_PLL", "inv_C", "w0", "dw"]
@@ -483,7 +488,8 @@ def generate(P, mult=1):
         for c in core:
             A(f"    double ci_{r}_{c};   // explicit inverse of the dense core")
     A("  };")
-    nflop_f = sum(2 if o[0] in ("fma",) else 1 for o in ops)
+    in_block = lambda o: CRAMER2 and bool(core) and all(i in coreset for i in o[1:])
+    nflop_f = sum(2 if o[0] in ("fma",) else 1 for o in ops if not in_block(o)) + (7 if CRAMER2 and core else 0)
     A(f"  static constexpr int LU_ENTRIES = {len(members)};   // incl. {len(members) - len(pattern)} fill-ins")
     A("")
     A("  static PVDER_DEV void factor(const double (&y)[NS], const Params& par, const Inputs& in, const Aux& aux,")
@@ -512,6 +518,8 @@ def generate(P, mult=1):
         if r != c:
             A(f"    double {wname(r, c)} = -j_{r}_{c};")
     for op in ops:
+        if CRAMER2 and core and all(i in coreset for i in op[1:]):
+            continue                      # the last 2x2 block is inverted below, not factored
         if op[0] == "inv":
             k = op[1]
             if k in unit:
@@ -532,7 +540,14 @@ def generate(P, mult=1):
         else:
             _, r, c, k = op
             A(f"    double {wname(r, c)} = -{wname(r, k)} * {wname(k, c)};")
-    if core:
+    if core and CRAMER2:
+        a, b = core
+        A(f"    const double rdet = pvder_rcp(fma({wname(a, a)}, {wname(b, b)}, -({wname(a, b)} * {wname(b, a)})));")
+        A(f"    lu.ci_{a}_{a} = {wname(b, b)} * rdet;")
+        A(f"    lu.ci_{a}_{b} = -({wname(a, b)} * rdet);")
+        A(f"    lu.ci_{b}_{a} = -({wname(b, a)} * rdet);")
+        A(f"    lu.ci_{b}_{b} = {wname(a, a)} * rdet;")
+    elif core:
         # inverse of the core from its LU (unit-lower multipliers w_r_k, upper w_k_c, d_k = 1/u_kk)
         cpos = {k: i for i, k in enumerate(core)}
         has = lambda r, c: (r, c) in pat

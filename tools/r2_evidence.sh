@@ -13,12 +13,12 @@ python bench.py --model model_2 --three-phase-mode split --steps 40 --warmup 5 -
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extra-configs --e2e-steps 1 > $O/launches_bench.log 2>&1
 M=smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_fp64_pred_on.sum,smsp__thread_inst_executed.sum,gpu__time_duration.sum
 B="--steps 12 --warmup 3 --no-cpu-baseline --no-extra-configs --e2e-steps 1"
-ncu --metrics $M --clock-control none -k regex:step_kernel -s 10 -c 1 --csv --log-file $O/flops_1ph.csv python bench.py $B > $O/f1.log 2>&1
+ncu --metrics $M --clock-control none -k "regex:^step_kernel$" -s 10 -c 1 --csv --log-file $O/flops_1ph.csv python bench.py $B > $O/f1.log 2>&1
 ncu --metrics $M --clock-control none -k regex:step_kernel_split3 -s 10 -c 1 --csv --log-file $O/flops_split.csv python bench.py --model model_2 --three-phase-mode split $B > $O/f3.log 2>&1
-ncu --metrics $M --clock-control none -k regex:step_kernelIN -s 10 -c 1 --csv --log-file $O/flops_m2auto.csv python bench.py --model model_2 $B > $O/f2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 10 -c 1 -o $O/step_1ph python bench.py $B > $O/ncu1.log 2>&1
+ncu --metrics $M --clock-control none -k "regex:^step_kernel$" -s 10 -c 1 --csv --log-file $O/flops_m2auto.csv python bench.py --model model_2 $B > $O/f2.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:^step_kernel$" -s 10 -c 1 -o $O/step_1ph python bench.py $B > $O/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:step_kernel_split3 -s 10 -c 1 -o $O/step_split3 python bench.py --model model_2 --three-phase-mode split $B > $O/ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:step_kernelIN -s 10 -c 1 -o $O/step_m2auto python bench.py --model model_2 $B > $O/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:^step_kernel$" -s 10 -c 1 -o $O/step_m2auto python bench.py --model model_2 $B > $O/ncu2.log 2>&1
 python tools/step_trace.py model_1 > $O/step_trace_1ph.txt 2>&1
 python tools/single_env_latency.py > $O/single_env_latency.json 2> $O/single.err
 for tool in memcheck synccheck racecheck; do
