@@ -915,7 +915,13 @@ struct pvder_env {
 
 static int env_create_impl(pvder_env* h, const pvder_env_config* cfg) {
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  {
+    // highest priority: the compaction kernel of the compact-output call runs on this stream, and its few CTAs must be
+    // scheduled ahead of the thousands of pending step-kernel CTAs of the next chunk, not behind them
+    int pr_least = 0, pr_greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+    CK(cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, pr_greatest));
+  }
   CK(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
   for (int c = 0; c < PVDER_MAX_CHUNKS; ++c) CK(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
@@ -1140,16 +1146,19 @@ static int env_step_host_impl(pvder_env* h, const int32_t* action, float* obs_ou
                         obs64_out ? h->d_obs64 + lo * PVDER_OBS_DIM : nullptr, h->d_reward + lo, nullptr, h->d_done + lo,
                         cnt, h->off + lo, cs);
     if (rc) return rc;
-    if (co) {
-      const unsigned cgrid = (unsigned)((cnt + 255) / 256);
-      compact_outputs_kernel<<<cgrid, 256, 0, cs>>>(h->d_obs + lo * PVDER_OBS_DIM, h->d_reward + lo, h->d_done + lo,
-                                                    co->obs_h ? h->d_obs_h + lo * PVDER_OBS_DIM : nullptr,
-                                                    co->reward_f ? h->d_reward_f + lo : nullptr,
-                                                    co->done_bits ? h->d_done_bits + lo / 32 : nullptr, cnt);
-      CK(cudaGetLastError());
-    }
     CK(cudaEventRecord(h->chunk_done[c], cs));
     CK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+    if (co) {
+      // on the (high-priority) copy stream, in order before this chunk's copies: launched on the compute stream it
+      // would queue behind the next chunk's step kernel and delay every copy by one chunk (measured: 5.8e8 vs 7.0e8
+      // env-steps/s for the full formats at N = 1)
+      const unsigned cgrid = (unsigned)((cnt + 255) / 256);
+      compact_outputs_kernel<<<cgrid, 256, 0, h->copy_stream>>>(h->d_obs + lo * PVDER_OBS_DIM, h->d_reward + lo, h->d_done + lo,
+                                                                co->obs_h ? h->d_obs_h + lo * PVDER_OBS_DIM : nullptr,
+                                                                co->reward_f ? h->d_reward_f + lo : nullptr,
+                                                                co->done_bits ? h->d_done_bits + lo / 32 : nullptr, cnt);
+      CK(cudaGetLastError());
+    }
     if (c == 1) CK(cudaEventRecord(h->cp0, h->copy_stream));
     if (co) {
       if (co->obs_h)
