@@ -216,7 +216,12 @@ __global__ void PVDER_SPLIT_BOUNDS
   constexpr int NS = 23;
   __shared__ float stage[SPLIT_ENVS_PER_BLOCK * PVDER_OBS_DIM];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if PVDER_SPLIT_SMEM_SUMS
+  __shared__ double xbuf[BLOCK / 32][PVDER_SPLIT_SUMS_MAX * 32];   // per-warp exchange buffer of the phase sums (sum3n)
+  const Lanes3 ln = make_lanes(lane, xbuf[warp]);
+#else
   const Lanes3 ln = make_lanes(lane);
+#endif
   const int g = ln.base / 3, p = ln.p;
   const int slot = warp * SPLIT_ENVS_PER_WARP + g;
   int32_t* ctrl = a.si + (int64_t)PVDER_SI_REDO_CTRL * a.ld;

@@ -27,6 +27,10 @@ namespace pvder {
 // ---------------------------------------------------------------------------------------------
 // Lane abstraction
 // ---------------------------------------------------------------------------------------------
+#ifndef PVDER_SPLIT_SMEM_SUMS
+#define PVDER_SPLIT_SMEM_SUMS 1
+#endif
+#define PVDER_SPLIT_SUMS_MAX 13
 #ifdef __CUDACC__
 // DYN = false: the whole warp is converged (hot path; the member mask is the compile-time constant
 // 0xffffffff, which lets ptxas drop the destination initialisation of every SHFL).  DYN = true: a
@@ -36,6 +40,8 @@ struct LanesT {
   using V = double;   // per-phase value: this lane's phase
   using B = bool;
   unsigned mask;      // lanes executing the current region (DYN only)
+  double* sm;         // this warp's exchange buffer [PVDER_SPLIT_SUMS_MAX][32] in shared memory (sum3n)
+  int self;           // this lane's own index (lanes 30, 31 shadow 27, 28 but keep their own buffer slot)
   int base;           // first lane of the group (phase a)
   int p;              // phase of this lane
   int n1, n2;         // lanes holding the next two phases (cyclic)
@@ -54,6 +60,30 @@ struct LanesT {
     const double b = __shfl_sync(m(), v, n1), c = __shfl_sync(m(), v, n2);
     return __dadd_rn(__dadd_rn(v, b), c);
   }
+  // N phase sums at once (same order as sum3: own + next + next-next).  Through shared memory when PVDER_SPLIT_SMEM_SUMS:
+  // N STS.64, a warp barrier, 2 N LDS.64 into aligned register pairs and a closing barrier instead of 4 N SHFL plus
+  // about as many register moves (SHFL results do not land in aligned pairs under a 255-register allocation) -- the
+  // three-lane kernel issues more non-FP64 instructions per FP64 instruction than the pipe takes for free.
+  // Lanes only ever read the slots of their own group, and the lanes of a group always execute together, so the barriers
+  // order exactly what they have to (and they name the same member mask as every other collective: rule at m()).
+  template <int N>
+  PVDER_DEV void sum3n(const double (&v)[N], double (&out)[N]) const {
+#if PVDER_SPLIT_SMEM_SUMS
+    static_assert(N <= PVDER_SPLIT_SUMS_MAX, "exchange buffer too small");
+#pragma unroll
+    for (int k = 0; k < N; ++k) sm[32 * k + self] = v[k];
+    __syncwarp(m());
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double b = sm[32 * k + n1], c = sm[32 * k + n2];
+      out[k] = __dadd_rn(__dadd_rn(v[k], b), c);
+    }
+    __syncwarp(m());
+#else
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = sum3(v[k]);
+#endif
+  }
   // fixed order (a + b) + c in all three lanes (outputs: bit-identical to the one-thread kernel)
   PVDER_DEV double sum3_ordered(double v) const {
     const double a = __shfl_sync(m(), v, base), b = __shfl_sync(m(), v, base + 1), c = __shfl_sync(m(), v, base + 2);
@@ -68,14 +98,17 @@ struct LanesT {
   PVDER_DEV LanesT<true> sub(bool pred) const {
     LanesT<true> l;
     l.mask = __ballot_sync(m(), pred);
+    l.sm = sm; l.self = self;
     l.base = base; l.p = p; l.n1 = n1; l.n2 = n2;
     return l;
   }
 };
 using Lanes3 = LanesT<false>;
-PVDER_DEV Lanes3 make_lanes(int lane) {
+PVDER_DEV Lanes3 make_lanes(int lane, double* warp_buf = nullptr) {
   // lanes 3g..3g+2 = phases a, b, c of group g; lanes 30, 31 shadow lanes 27, 28
   Lanes3 l;
+  l.sm = warp_buf;
+  l.self = lane;
   const int g = lane < 30 ? lane / 3 : 9;
   l.p = lane < 30 ? lane - 3 * g : lane - 30;
   l.base = 3 * g;
@@ -136,6 +169,10 @@ struct LanesT {
   using B = B3;
   double sum3(const V3& v) const { return (v.v[0] + v.v[1]) + v.v[2]; }
   double sum3_ordered(const V3& v) const { return (v.v[0] + v.v[1]) + v.v[2]; }
+  template <int N>
+  void sum3n(const V3 (&v)[N], double (&out)[N]) const {
+    for (int k = 0; k < N; ++k) out[k] = sum3(v[k]);
+  }
   bool any3(const B3& b) const { return b.v[0] || b.v[1] || b.v[2]; }
   bool any3(bool b) const { return b; }
   bool any_warp(bool b) const { return b; }
@@ -257,9 +294,12 @@ struct Split3 {
     q.ck = vfma(ax.cs, k.ca, ax.sn * k.sa);        // cos(delta - alpha_p)
     q.sk = vfma(ax.sn, k.ca, -(ax.cs * k.sa));     // sin(delta - alpha_p)
     const V vdk = vfma(q.vR, q.ck, q.vI * q.sk);
-    q.Qp = 0.5 * ln.sum3(qs);
-    q.Ps = ln.sum3(ps);
-    q.vd = (1.0 / 3.0) * ln.sum3(vdk);             // positive-sequence d-axis voltage (A.4)
+    const V pin[3] = {qs, ps, vdk};
+    double psum[3];
+    ln.sum3n(pin, psum);
+    q.Qp = 0.5 * psum[0];
+    q.Ps = psum[1];
+    q.vd = (1.0 / 3.0) * psum[2];                  // positive-sequence d-axis voltage (A.4)
     q.wex = fma(par.Kp_PLL, q.vd, Y.s[3]);
     q.wr = fma(q.wex, par.inv_wb, par.w0 * par.inv_wb);
     q.dV = in.Vdcref - Y.s[0];
@@ -375,14 +415,17 @@ struct Split3 {
     const V e4R = -(f.epR * k.ri), e4I = f.epI * k.rr;                                            // d irefI
     const V c4R = vfma(f.n11, e4R, f.n12 * e4I), c4I = vfma(-f.n12, e4R, f.n22 * e4I);
     const V uR = iR * tkR, uI = iI * tkI;    // direct part of d Ps / d iref through Ku
-    const double RQ1 = ln.sum3(vfma(f.qR, c1R, f.qI * c1I)), RQ2 = ln.sum3(vfma(f.qR, c2R, f.qI * c2I));
-    const double RQ3 = ln.sum3(vfma(f.qR, c3R, f.qI * c3I)), RQ4 = ln.sum3(vfma(f.qR, c4R, f.qI * c4I));
-    const double Rv1 = ln.sum3(vfma(f.dR, c1R, f.dI * c1I)), Rv2 = ln.sum3(vfma(f.dR, c2R, f.dI * c2I));
-    const double Rv3 = ln.sum3(vfma(f.dR, c3R, f.dI * c3I)), Rv4 = ln.sum3(vfma(f.dR, c4R, f.dI * c4I));
-    const double RP1 = ln.sum3(vfma(f.pR, c1R, f.pI * c1I)), RP2 = ln.sum3(vfma(f.pR, c2R, f.pI * c2I));
-    const double RP3 = ln.sum3(vfma(f.pR, c3R, vfma(f.pI, c3I, vfma(uR, k.rr, uI * k.ri))));
-    const double RP4 = ln.sum3(vfma(f.pR, c4R, vfma(f.pI, c4I, vfma(uI, k.rr, -(uR * k.ri)))));
-    f.vdd = (1.0 / 3.0) * ln.sum3(vfma(q.vI, q.ck, -(q.vR * q.sk)));
+    const V fin[13] = {vfma(f.qR, c1R, f.qI * c1I), vfma(f.qR, c2R, f.qI * c2I), vfma(f.qR, c3R, f.qI * c3I),
+                       vfma(f.qR, c4R, f.qI * c4I), vfma(f.dR, c1R, f.dI * c1I), vfma(f.dR, c2R, f.dI * c2I),
+                       vfma(f.dR, c3R, f.dI * c3I), vfma(f.dR, c4R, f.dI * c4I), vfma(f.pR, c1R, f.pI * c1I),
+                       vfma(f.pR, c2R, f.pI * c2I), vfma(f.pR, c3R, vfma(f.pI, c3I, vfma(uR, k.rr, uI * k.ri))),
+                       vfma(f.pR, c4R, vfma(f.pI, c4I, vfma(uI, k.rr, -(uR * k.ri)))), vfma(q.vI, q.ck, -(q.vR * q.sk))};
+    double fs[13];
+    ln.sum3n(fin, fs);
+    const double RQ1 = fs[0], RQ2 = fs[1], RQ3 = fs[2], RQ4 = fs[3];
+    const double Rv1 = fs[4], Rv2 = fs[5], Rv3 = fs[6], Rv4 = fs[7];
+    const double RP1 = fs[8], RP2 = fs[9], RP3 = fs[10], RP4 = fs[11];
+    f.vdd = (1.0 / 3.0) * fs[12];
     f.RQ[0] = RQ1; f.RQ[1] = RQ3; f.RQ[2] = RQ4;
     f.Rv[0] = Rv1; f.Rv[1] = Rv3; f.Rv[2] = Rv4;
     f.RP[0] = RP1; f.RP[1] = RP3; f.RP[2] = RP4;
@@ -431,9 +474,10 @@ struct Split3 {
     const V mmR = vfma(thR, buR, hxR), mmI = vfma(thI, buI, hxI);
     const V rR = vfma(f.e, mmR, b.p[0]), rI = vfma(f.e, mmI, b.p[1]);
     const V tR = vfma(f.n11, rR, f.n12 * rI), tI = vfma(f.n22, rI, -(f.n12 * rR));
-    const double sQ = ln.sum3(vfma(f.qR, tR, f.qI * tI));
-    const double sv = ln.sum3(vfma(f.dR, tR, f.dI * tI));
-    const double sP = ln.sum3(vfma(f.pR, tR, vfma(f.pI, tI, vfma(iR, mmR, iI * mmI))));
+    const V sin3[3] = {vfma(f.qR, tR, f.qI * tI), vfma(f.dR, tR, f.dI * tI), vfma(f.pR, tR, vfma(f.pI, tI, vfma(iR, mmR, iI * mmI)))};
+    double ss[3];
+    ln.sum3n(sin3, ss);
+    const double sQ = ss[0], sv = ss[1], sP = ss[2];
     const double b3 = b.s[1], b4 = b.s[2], hp = b.s[3];
     const double b1 = par.inv_wb * hp;
     const double kd0 = (b.s[4] + hp) * inv_gh;

@@ -251,3 +251,21 @@ def test_registers_with_a_real_gym_when_one_is_importable(monkeypatch):
     assert seen == {"x": 1, "y": 2}                        # no spec= kwarg
     assert env.env.spec.id == "PVDER-probe-v0" and env._max_episode_steps == 7
     del registration.registry["PVDER-probe-v0"]
+
+
+def test_generated_model_headers_are_reproducible(tmp_path):
+    """The committed csrc/pvder_model_*.cuh are exactly what tools/gen_model.py emits with its default switches (pivot
+    order Vdc, delta before the current pair; plain LU) -- nobody edits generated code by hand, and the study switches
+    (PVDER_GEN_*) default to the committed configuration."""
+    import subprocess
+    import sys
+
+    env = {k: v for k, v in os.environ.items() if not k.startswith("PVDER_GEN_")}
+    env["PVDER_GEN_OUT"] = str(tmp_path)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "tools", "gen_model.py")], check=True, env=env, capture_output=True,
+                   timeout=900)
+    csrc = os.path.join(root, "gym-solarpvder-environment_b200", "csrc")
+    for name in ("pvder_model_1ph.cuh", "pvder_model_3ph.cuh", "pvder_model_3ph_bal.cuh"):
+        with open(os.path.join(csrc, name)) as fa, open(os.path.join(str(tmp_path), name)) as fb:
+            assert fa.read() == fb.read(), f"{name} differs from the generator's output"
