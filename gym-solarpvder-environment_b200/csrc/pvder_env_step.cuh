@@ -506,6 +506,28 @@ PVDER_DEV bool same_sign(double a, double b) {
   return sa == sb;
 }
 
+// The same test on the bit patterns (integer pipe only, no FP64 compare): equal iff both are zero (+-0), or neither is and
+// the sign bits agree.  Identical to same_sign for every non-NaN argument (a NaN -- an env that is about to be reported
+// NONFINITE -- counts as a signed non-zero here, as a zero there).
+PVDER_DEV bool same_sign_bits(double a, double b) {
+#ifdef __CUDACC__
+  const int ha = __double2hiint(a), hb = __double2hiint(b);
+  const unsigned la = (unsigned)__double2loint(a), lb = (unsigned)__double2loint(b);
+#else
+  unsigned long long ua, ub;
+  std::memcpy(&ua, &a, 8);
+  std::memcpy(&ub, &b, 8);
+  const int ha = (int)(ua >> 32), hb = (int)(ub >> 32);
+  const unsigned la = (unsigned)ua, lb = (unsigned)ub;
+#endif
+  const bool za = ((((unsigned)ha) << 1) | la) == 0u, zb = ((((unsigned)hb) << 1) | lb) == 0u;
+  return (za == zb) && (za || ((ha ^ hb) >= 0));
+}
+
+#ifndef PVDER_FREEZE_BRANCHFREE
+#define PVDER_FREEZE_BRANCHFREE 0   // 1: freeze_bits without a branch (study switch, measured SLOWER: see there)
+#endif
+
 PVDER_DEV void phase_rot(int P, int k, double& rr, double& ri) {
   if (P == 1 || k == 0) { rr = 1.0; ri = 0.0; }
   else if (k == 1) { rr = -0.5; ri = -0.86602540378443864676; }
@@ -549,6 +571,32 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
   const double irefR = fma(par.Kp_DC, dV, xDC);
   const double irefI = fma(-par.Kp_Q, dQ, xQ);
   const bool i_over = (irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit;
+#if PVDER_FREEZE_BRANCHFREE
+  // Branch-free form (study switch, OFF).  The early return below makes the limit test -- a serial chain of ~15 dependent
+  // FP64 operations -- a basic block of its own at the head of the hot loop, with nothing to overlap it: 9 % of the loop's
+  // stall samples sit on 3.6 % of its instructions (ncu source page of the r2d capture).  This form evaluates every row test
+  // (sign tests on the integer pipe, +8 executed FP64 instructions per sub-step) and lets the two limit flags select, so
+  // the whole sub-step is one scheduling region.  MEASURED on B200 (profiles/r2e_branchfree_clamp_ab.txt): 1.397 -> 1.447 ms
+  // per 1 Mi-env step, 1.440 -> 1.477 ms over a full episode -- ptxas does not use the freedom, the extra work costs more.
+  {
+    unsigned mb = 0u, ib = 0u;
+#pragma unroll
+    for (int k = 0; k < P; ++k) {
+      double rr, ri;
+      phase_rot(P, k, rr, ri);
+      const double uR = y[6 * k + 4], uI = y[6 * k + 5];
+      const double duR = par.wp * (-uR + (rr * irefR - ri * irefI) - y[6 * k]);
+      const double duI = par.wp * (-uI + (ri * irefR + rr * irefI) - y[6 * k + 1]);
+      mb |= same_sign_bits(par.Ki_GCC * uR, y[6 * k + 2]) ? (1u << (4 * k)) : 0u;
+      mb |= same_sign_bits(par.Ki_GCC * uI, y[6 * k + 3]) ? (1u << (4 * k + 1)) : 0u;
+      mb |= same_sign_bits(duR, uR) ? (1u << (4 * k + 2)) : 0u;
+      mb |= same_sign_bits(duI, uI) ? (1u << (4 * k + 3)) : 0u;
+    }
+    ib |= same_sign_bits(par.Ki_DC * dV, xDC) ? (1u << (4 * P)) : 0u;
+    ib |= same_sign_bits(-par.Ki_Q * dQ, xQ) ? (1u << (4 * P + 1)) : 0u;
+    return (m_over ? mb : 0u) | (i_over ? ib : 0u);
+  }
+#endif
   if (!(m_over || i_over)) return 0u;
   unsigned bits = 0u;
   if (m_over) {
