@@ -228,13 +228,28 @@ PVDER_DEV unsigned opaque_bits(unsigned v) {
   return v;
 }
 
+#ifndef PVDER_CARRY_LIMIT_FLAGS
+#define PVDER_CARRY_LIMIT_FLAGS 0   // 1 (study switch, measured SLOWER): the limit test of the anti-windup clamp for the NEXT sub-step is
+#endif                              // evaluated at the end of the step (same basic block as the final side-input advance) instead of at
+                                    // the loop head, where its serial chain stands alone (9 % of the stall samples on 3.6 % of the
+                                    // instructions).  B200: 1.398 -> 1.441 ms per 1 Mi-env step, 1.442 -> 1.491 ms over a full episode
+                                    // (profiles/r2e_carried_limit_flags_ab.txt): at the loop head the test shares vR, vI, m, Q, i_ref
+                                    // with stage 1; moved away it computes them twice (+14 FP64 instructions), which costs more
+                                    // than the overlap buys.
+// Limit flags of the anti-windup clamp (A.3) at state y: |m| > 10 m_limit in some phase, |i_ref| > iref_limit.
+template <class M>
+PVDER_DEV void limit_flags(const double (&y)[M::NS], const Params& par, const Inputs& in, bool& m_over, bool& i_over);
+
 // One half-cycle step of the scheme PVDER_SCHEME selects.  `base` is the Aux record at y on entry and at the new y on exit.
 // Returns false (y, base untouched) when EXACT == false and a stage left the incremental range.
 // FREE: no clamp is active (frz == 0 in every lane that takes this instantiation): the effective gains are
 // the parameters themselves, read from the constant bank instead of occupying registers.
+// next_m / next_i (hot loop only, PVDER_CARRY_LIMIT_FLAGS): receive the clamp's limit flags at the NEW state when the step is
+// accepted (untouched otherwise) -- evaluated here so that their serial chain shares a scheduling region with the final
+// side-input advance instead of standing alone at the head of the next sub-step.
 template <class M, bool EXACT, bool FREE = false, class TAB>
 PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in, const TAB& tab,
-                           unsigned frz, Aux& base) {
+                           unsigned frz, Aux& base, bool* next_m = nullptr, bool* next_i = nullptr) {
   double gn[M::NGAIN];
   make_gains<M>(par, tab, FREE ? 0u : frz, gn);
 #if PVDER_LAZY_GAINS
@@ -393,10 +408,13 @@ PVDER_DEV bool ros_core(double (&y)[M::NS], const Params& par, const Inputs& in,
   aux_advance<M, EXACT>(par, in, base, dl0, V0, Y, ax, oor);
 #endif
 #endif
+  bool nm = false, ni = false;
+  if (next_m) limit_flags<M>(Y, par, in, nm, ni);
   if (oor) return false;
 #pragma unroll
   for (int i = 0; i < NS; ++i) y[i] = Y[i];
   base = ax;
+  if (next_m) { *next_m = nm; *next_i = ni; }
   return true;
 }
 #undef PVDER_WITH_GAINS
@@ -464,7 +482,7 @@ PVDER_SLOW_LINKAGE StepState<M> ros_slow(StepState<M> s, const Params* par, Inpu
 // the hot loop itself contains no call, so nothing in it is bound by the calling convention's register classes.
 template <class M, class TAB>
 PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in, const TAB& tab,
-                        unsigned frz, Aux& base) {
+                        unsigned frz, Aux& base, bool* next_m = nullptr, bool* next_i = nullptr) {
   // One instantiation serves clamped and unclamped envs (the clamp enters through the per-row
   // effective gains): with a random policy two thirds of the warps hold a clamped lane late in an
   // episode, so a separate divergent code path for them cost 2x there.
@@ -475,10 +493,10 @@ PVDER_DEV bool ros_step(double (&y)[M::NS], const Params& par, const Inputs& in,
 #else
   const bool any_frz = frz != 0u;
 #endif
-  return any_frz ? ros_core<M, false, false>(y, par, in, tab, frz, base)
-                 : ros_core<M, false, true>(y, par, in, tab, frz, base);
+  return any_frz ? ros_core<M, false, false>(y, par, in, tab, frz, base, next_m, next_i)
+                 : ros_core<M, false, true>(y, par, in, tab, frz, base, next_m, next_i);
 #else
-  return ros_core<M, false>(y, par, in, tab, frz, base);
+  return ros_core<M, false>(y, par, in, tab, frz, base, next_m, next_i);
 #endif
 }
 
@@ -536,8 +554,9 @@ PVDER_DEV void phase_rot(int P, int k, double& rr, double& ri) {
 
 // Anti-windup mode, sampled once per half-cycle sub-step.  Bit order = M::NFRZ
 // rows: per phase xR,xI,uR,uI ; then xDC, xQ.
-template <class M>
-PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, const Inputs& in, bool& m_over_out) {
+// MODE 0: flags and rows (freeze_bits); 1: flags only (limit_flags: returns 0); 2: rows for GIVEN flags (freeze_rows).
+template <class M, int MODE>
+PVDER_DEV unsigned freeze_impl(const double (&y)[M::NS], const Params& par, const Inputs& in, bool& m_over_io, bool& i_over_io) {
   constexpr int P = M::PHASES;
   constexpr int B = 6 * P;
   // Same expression trees as the generated right-hand side (vR, vI, qs, Qp, iref): when the stepper is inlined
@@ -551,7 +570,7 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
     const double iR = y[6 * k], iI = y[6 * k + 1];
     const double mR = fma(par.Kp_GCC, y[6 * k + 4], y[6 * k + 2]);
     const double mI = fma(par.Kp_GCC, y[6 * k + 5], y[6 * k + 3]);
-    m_over |= (mR * mR + mI * mI) > par.m_limit10 * par.m_limit10;
+    if (MODE != 2) m_over |= (mR * mR + mI * mI) > par.m_limit10 * par.m_limit10;
     const double vgk = M::BALANCED3 ? in.vg : vg_of_phase(in, P, k);
     double vR, vI;
     if (P == 1 || k == 0) {
@@ -564,13 +583,16 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
     const double qs = fma(vI, iR, -(vR * iI));
     Qs = (k == 0) ? qs : Qs + qs;
   }
-  m_over_out = m_over;
+  if (MODE == 2) m_over = m_over_io;
+  else m_over_io = m_over;
   const double Vdc = y[B], xDC = y[B + 1], xQ = y[B + 2];
   const double dV = in.Vdcref - Vdc;
   const double dQ = fma(-(0.5 * M::PMULT), Qs, in.Qref);      // Qref - Q
   const double irefR = fma(par.Kp_DC, dV, xDC);
   const double irefI = fma(-par.Kp_Q, dQ, xQ);
-  const bool i_over = (irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit;
+  const bool i_over = (MODE == 2) ? i_over_io : ((irefR * irefR + irefI * irefI) > par.iref_limit * par.iref_limit);
+  if (MODE != 2) i_over_io = i_over;
+  if (MODE == 1) return 0u;
 #if PVDER_FREEZE_BRANCHFREE
   // Branch-free form (study switch, OFF).  The early return below makes the limit test -- a serial chain of ~15 dependent
   // FP64 operations -- a basic block of its own at the head of the hot loop, with nothing to overlap it: 9 % of the loop's
@@ -618,6 +640,21 @@ PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, cons
     if (same_sign(-par.Ki_Q * dQ, xQ)) bits |= 1u << (4 * P + 1);
   }
   return bits;
+}
+
+template <class M>
+PVDER_DEV unsigned freeze_bits(const double (&y)[M::NS], const Params& par, const Inputs& in, bool& m_over_out) {
+  bool i_over = false;
+  return freeze_impl<M, 0>(y, par, in, m_over_out, i_over);
+}
+template <class M>
+PVDER_DEV void limit_flags(const double (&y)[M::NS], const Params& par, const Inputs& in, bool& m_over, bool& i_over) {
+  freeze_impl<M, 1>(y, par, in, m_over, i_over);
+}
+// the clamped rows for limit flags evaluated earlier at the same state (hot loop, PVDER_CARRY_LIMIT_FLAGS)
+template <class M>
+PVDER_DEV unsigned freeze_rows(const double (&y)[M::NS], const Params& par, const Inputs& in, bool m_over, bool i_over) {
+  return freeze_impl<M, 2>(y, par, in, m_over, i_over);
 }
 
 // Event j of (env, episode): which quantity changes and its new value (A.8).  Philox counter
@@ -940,14 +977,26 @@ PVDER_DEV bool advance_env(const pvder_env_config& cfg, const RodasTab& tab, Env
       if (seg > 0) {
         // hot loop: a countdown and the clamped-sub-step counter are all the integers it carries
         int left = seg, wind = 0;
+#if PVDER_CARRY_LIMIT_FLAGS
+        // the limit flags of the clamp travel from one sub-step to the next: ros_core evaluates them for the state it ends
+        // in (the inputs are constant within a run), the loop head only branches on them
+        bool m_next, i_next;
+        limit_flags<M>(r.y, par, in, m_next, i_next);
+#endif
 #if defined(PVDER_HOT_UNROLL) && defined(__CUDACC__)
         constexpr int kHotUnroll = PVDER_HOT_UNROLL;
 #pragma unroll kHotUnroll
 #endif
         do {
+#if PVDER_CARRY_LIMIT_FLAGS
+          const bool m_over = m_next;
+          const unsigned frz = (m_next || i_next) ? freeze_rows<M>(r.y, par, in, m_next, i_next) : 0u;
+          if (!ros_step<M>(r.y, par, in, tab, frz, base, &m_next, &i_next)) break;
+#else
           bool m_over;
           const unsigned frz = freeze_bits<M>(r.y, par, in, m_over);
           if (!ros_step<M>(r.y, par, in, tab, frz, base)) break;
+#endif
           wind += frz != 0u ? 1 : 0;
           // the duty-cycle clamp acts on Re/Im parts per phase and would break the symmetry the
           // balanced representation relies on: report instead of integrating something else

@@ -22,8 +22,12 @@ def load():
         return _lib
     deps = [_SRC] + [os.path.join(_cabi.CSRC, f) for f in os.listdir(_cabi.CSRC) if f.endswith(".cuh")]
     if not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(d) for d in deps):
+        # build to a private name and rename: several processes (the 2-rank gloo test, pytest-xdist) may find the library
+        # stale at the same time, and none of them may ever load a half-written file
+        tmp = f"{_LIB}.{os.getpid()}.tmp"
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                        "-o", _LIB, _SRC], check=True)
+                        "-o", tmp, _SRC], check=True)
+        os.replace(tmp, _LIB)
     _lib = C.CDLL(_LIB)
     return _lib
 
